@@ -1,0 +1,166 @@
+/* trimem_b200.h — C ABI of libtrimem_b200.so
+ *
+ * B200 (sm_100a) implementation of trimem's force-evaluation hot path. This is
+ * the drop-in boundary: plain pointers and sizes, no C++/torch types. The
+ * pybind11 module trimem_b200.core (host C++, mirrors the reference's
+ * trimem.core) and the benchmark both sit on top of exactly these entry points.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the
+ * reference tree, bio-phys/trimem @ 1a2a05c).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; tm_last_error()
+ *     returns a thread-local message for the last failing call.
+ *   - all reals are fp64, all indices int32, positions are (V,3) row-major,
+ *     exactly the memory TriMesh.points() exposes (src/mesh_py.cpp:96-106).
+ *   - vertex / half-edge / edge numbering at this boundary is the host's
+ *     (OpenMesh ArrayKernel numbering: edge k <-> half-edges 2k, 2k+1).
+ *   - calls are synchronous at the boundary unless suffixed _async.
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     fails with a message; nothing is silently evaluated on the host.
+ */
+#ifndef TRIMEM_B200_H
+#define TRIMEM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tm_mesh  tm_mesh;   /* device mirror of one TriMesh              */
+typedef struct tm_nlist tm_nlist;  /* device neighbour list (cell / verlet)      */
+
+/* ---- library ------------------------------------------------------------- */
+const char* tm_last_error(void);
+int  tm_abi_version(void);
+/* number of visible CUDA devices (0 when there is no driver / device)         */
+int  tm_device_count(void);
+/* pinned host memory for TriMesh.points() storage; falls back to malloc when
+ * there is no device (host-only unit tests).                                   */
+void* tm_host_alloc(unsigned long long bytes);
+void  tm_host_free(void* p);
+/* frees arrays returned by the tm_nlist_* query functions                      */
+void  tm_free(void* p);
+/* number of kernels this library has launched so far (bench: gpu_launches)     */
+unsigned long long tm_launch_count(void);
+
+/* ---- mesh mirror  (replaces OpenMesh TriMesh_ArrayKernelT storage,
+ *      src/mesh.h:15-31; flattened to SoA + CSR one-ring on the device) ------ */
+int tm_mesh_create(int device, tm_mesh** out);
+int tm_mesh_destroy(tm_mesh* m);
+/* Upload the half-edge connectivity (after construction and after host-side
+ * topology changes). he_next must be defined for boundary half-edges too
+ * (boundary loops), he_face = -1 for boundary half-edges, v_he = outgoing
+ * half-edge at which the clockwise one-ring circulation starts (-1: isolated). */
+int tm_mesh_set_topology(tm_mesh* m, int n_vertices, int n_halfedges,
+                         const int* he_to, const int* he_next,
+                         const int* he_face, const int* v_he);
+/* Download the device connectivity (device-side flips mutate it).              */
+int tm_mesh_get_topology(tm_mesh* m, int* he_to, int* he_next, int* he_face, int* v_he);
+/* CSR one-ring the kernels use: ring_off[V+1]; ring_v[n_halfedges] holds the
+ * neighbour ids in clockwise circulation order (tests / diagnostics).          */
+int tm_mesh_get_rings(tm_mesh* m, int* ring_off, int* ring_v, int* ring_flags);
+/* positions: the writable view of src/mesh_py.cpp:96-106 is host memory that
+ * Python mutates behind our back, so every evaluation re-uploads.              */
+int tm_mesh_set_positions(tm_mesh* m, const double* xyz);
+int tm_mesh_get_positions(tm_mesh* m, double* xyz);
+int tm_mesh_n_vertices(const tm_mesh* m);
+int tm_mesh_n_halfedges(const tm_mesh* m);
+
+/* ---- parameters  (POD mirror of src/params.h:19-71) ------------------------ */
+enum { TM_BOND_EDGE = 0, TM_BOND_AREA = 1, TM_BOND_NONE = 2 };
+enum { TM_NLIST_CELL = 0, TM_NLIST_VERLET = 1 };
+typedef struct tm_energy_params {
+    double kappa_b, kappa_a, kappa_v, kappa_c, kappa_t, kappa_r;
+    /* reference values interpolate_reference_properties() yields
+     * (src/energy.cpp:30-45); the host computes them, the device only uses them */
+    double ref_area, ref_volume, ref_curvature;
+    /* BondParams (src/params.h:19-26) */
+    double bond_lc0, bond_lc1, bond_a0;
+    int    bond_r, bond_type;
+    /* SurfaceRepulsionParams.{lc1,r} (src/params.h:34-41) */
+    double rep_lc1;
+    int    rep_r, _pad;
+} tm_energy_params;
+
+/* ---- neighbour lists  (src/nlists/nlist.cpp:10-53, cell_list.h, verlet_list.h) */
+/* make_nlist: kind x exclusion_level in {0,1,2}; built from the mesh's current
+ * device positions and connectivity.                                            */
+int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level,
+                    double box_eps, tm_nlist** out);
+int tm_nlist_destroy(tm_nlist* nl);
+/* NeighbourList::distance_matrix (cell_list.h:221-312 / verlet_list.h:37-72):
+ * COO triplets; cell-list: each pair once with i<j and dist <= rdist;
+ * verlet-list: both directions and dist < rdist. Output is sorted by (i,j);
+ * arrays are library-allocated, release with tm_free.                           */
+int tm_nlist_distance_matrix(tm_nlist* nl, tm_mesh* m, double rdist,
+                             long long* n, double** dist, int** idx, int** jdx);
+/* NeighbourList::point_distances (cell_list.h:131-219 / verlet_list.h:74-101):
+ * d_ij = x_pid - x_j (n x 3) and j for all listed j with |d_ij| < rdist.        */
+int tm_nlist_point_distances(tm_nlist* nl, tm_mesh* m, int pid, double rdist,
+                             int* n, double** dxyz, int** jdx);
+/* diagnostics: number of directed verlet entries (0 for a cell list), cells     */
+int tm_nlist_info(tm_nlist* nl, long long* n_entries, int shape[3], double box[6], double cell[3]);
+
+/* ---- energy / gradient  (src/energy.cpp:63-124, kernel.h, mesh_properties.cpp) */
+/* EnergyManager::properties: the six reduced sums
+ * (area, volume, curvature, bending, tethering, repulsion).                     */
+int tm_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double out[6]);
+/* per-vertex vertex_properties (mesh_properties.cpp:12-49): out is (V,6)        */
+int tm_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* out);
+/* EnergyManager::energy(mesh) = trimem_energy(properties) (kernel.h:110-122)    */
+int tm_energy(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* energy, double props[6]);
+/* EnergyManager::gradient (energy.cpp:93-124): grad is (V,3) host memory; props
+ * (optional) receives the reduced sums the gradient was evaluated with.         */
+int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* grad, double props[6]);
+
+/* device-resident variants: positions already on the device (tm_mesh_set_positions
+ * or a previous device update); results stay on the device until fetched.       */
+int tm_energy_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p);
+int tm_gradient_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p);
+int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, double props[6]);
+int tm_fetch_gradient(tm_mesh* m, double* grad);
+int tm_sync(tm_mesh* m);
+/* CUDA-event timing on the mesh's stream (bench.py)                             */
+int tm_timer_start(tm_mesh* m);
+int tm_timer_stop(tm_mesh* m, float* ms);
+/* write `bytes` of scratch on the mesh's stream to evict L2 between timed runs  */
+int tm_flush_l2(tm_mesh* m, unsigned long long bytes);
+
+/* ---- setup reductions  (src/util.cpp:9-41) --------------------------------- */
+/* area(mesh) = sum of face areas, edges_length(mesh) = sum over edges (each edge
+ * measured on its half-edge 2k, as util.cpp:29-31)                              */
+int tm_area_edges(tm_mesh* m, double* area, double* edges_length);
+
+/* ---- single half-edge primitives  (src/mesh_util.h:15-185; exposed to Python
+ *      by src/bindings.cpp:249-407 and pinned by tests/test_properties.py) ------
+ * out[0..3]   edge_length, face_area, face_volume, dihedral_angle
+ * out[4..9]   edge_length_grad     rows: from-vertex, to-vertex
+ * out[10..18] face_area_grad       rows: from, to, apex
+ * out[19..27] face_volume_grad     rows: from, to, apex
+ * out[28..39] dihedral_angle_grad  rows: from, to, apex, opposite apex             */
+int tm_halfedge_geometry(tm_mesh* m, int halfedge, double out[40]);
+
+/* ---- edge flips  (src/flips.cpp:22-165, flip_utils.cpp:19-114) --------------- */
+enum { TM_FLIP_SERIAL = 0, TM_FLIP_BATCH = 1 };
+/* One sweep over n_proposals proposed edges with their uniform variates u[k]
+ * (the host draws them; std::mt19937 in the reference, flips.cpp:20,105-106).
+ * TM_FLIP_SERIAL evaluates proposals strictly in order (flip_serial);
+ * TM_FLIP_BATCH processes them in conflict-free rounds (flip_parallel_batches),
+ * Metropolis on the device in proposal order inside a round.
+ * flipped[k] receives the edge id of the k-th accepted flip in application order
+ * (capacity n_proposals) so the host half-edge mirror can replay them;
+ * props_io: reduced properties before (in) / after (out) the sweep.             */
+int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
+                  int n_proposals, const int* edges, const double* u,
+                  int* n_accepted, int* flipped, double props_io[6]);
+/* edge_vertex_properties (flip_utils.cpp:19-41) of one edge on the device mesh  */
+int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p,
+                              int edge, double out[6]);
+/* TriConnectivity::is_flip_ok / flip on the device connectivity (tests)         */
+int tm_mesh_is_flip_ok(tm_mesh* m, int edge, int* ok);
+int tm_mesh_flip(tm_mesh* m, int edge);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIMEM_B200_H */

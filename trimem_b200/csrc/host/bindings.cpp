@@ -1,0 +1,306 @@
+// pybind11 module trimem_b200.core: drop-in for the reference's trimem.core
+// (PYBIND11_MODULE(core, m), src/bindings.cpp:1038). Same class / function /
+// attribute names, argument names and error types; every evaluation is
+// forwarded to libtrimem_b200 (CUDA) through the C ABI.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <sstream>
+
+#include "energy_manager.h"
+#include "halfedge_mesh.h"
+
+namespace py = pybind11;
+using namespace trimem_b200;
+
+namespace {
+
+struct HalfedgeHandle {
+    int idx = -1;
+};
+struct Point {   // opaque, as in the reference (src/bindings.cpp:896-905)
+    double v[3];
+};
+
+using darray = py::array_t<double, py::array::c_style | py::array::forcecast>;
+using iarray = py::array_t<int, py::array::c_style | py::array::forcecast>;
+
+// from_points_cells (src/mesh_py.cpp:12-70)
+std::unique_ptr<HalfedgeMesh> mesh_from_arrays(const py::array_t<double>& points_in,
+                                               const py::array_t<int>& cells_in) {
+    auto mesh = std::make_unique<HalfedgeMesh>();
+    if (points_in.size() == 0) return mesh;
+    if (points_in.ndim() != 2 || points_in.shape(1) != 3)
+        throw std::runtime_error("Array 'points' must have shape (n,3)");
+    darray points = darray::ensure(points_in);
+    mesh->set_points(points.data(), (int)points.shape(0));
+    if (mesh->n_vertices() < 3 || cells_in.size() == 0) return mesh;
+    if (cells_in.ndim() != 2 || cells_in.shape(1) != 3)
+        throw std::runtime_error("Array 'cells' must have shape (n,3)");
+    iarray cells = iarray::ensure(cells_in);
+    auto c = cells.unchecked<2>();
+    const int nv = mesh->n_vertices();
+    for (py::ssize_t f = 0; f < c.shape(0); ++f) {
+        int a = c(f, 0), b = c(f, 1), d = c(f, 2);
+        // faces with out-of-range ids are skipped silently
+        if (a < 0 || a >= nv || b < 0 || b >= nv || d < 0 || d >= nv) continue;
+        mesh->add_face(a, b, d);
+    }
+    return mesh;
+}
+
+void check_he(const HalfedgeMesh& mesh, const HalfedgeHandle& he) {
+    if (he.idx < 0 || he.idx >= mesh.n_halfedges()) throw std::runtime_error("invalid halfedge handle");
+}
+
+std::array<double, 40> he_geometry(HalfedgeMesh& mesh, const HalfedgeHandle& he) {
+    check_he(mesh, he);
+    std::array<double, 40> g;
+    if (tm_halfedge_geometry(mesh.device(), he.idx, g.data())) throw std::runtime_error(tm_last_error());
+    return g;
+}
+
+py::array_t<double> rows(const double* p, int n) {
+    py::array_t<double> a({n, 3});
+    std::memcpy(a.mutable_data(), p, sizeof(double) * 3 * n);
+    return a;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(core, m) {
+    m.doc() = "B200-native drop-in for trimem.core (force-evaluation hot path on CUDA)";
+
+    // ---- mesh (src/bindings.cpp:52-190) -----------------------------------------------
+    py::class_<HalfedgeHandle>(m, "HalfedgeHandle", "Handle/reference to a halfedge.")
+        .def(py::init())
+        .def("idx", [](const HalfedgeHandle& h) { return h.idx; });
+
+    py::class_<HalfedgeMesh>(m, "TriMesh", "Triangulation (half-edge mesh mirrored on the GPU).")
+        .def(py::init(), "Initialize empty mesh.")
+        .def(py::init(&mesh_from_arrays), py::arg("points"), py::arg("faces"),
+             "Initialize from arrays of vertices (N,3) float and faces (M,3) int.")
+        .def("fv_indices",
+             [](HalfedgeMesh& mesh) -> py::array_t<int> {
+                 // src/mesh_py.cpp:73-93
+                 if (mesh.n_faces() == 0) return py::array_t<int>();
+                 py::array_t<int> out({mesh.n_faces(), 3});
+                 auto o = out.mutable_unchecked<2>();
+                 for (int f = 0; f < mesh.n_faces(); f++) {
+                     int h = mesh.face_halfedge(f);
+                     for (int k = 0; k < 3; k++) { o(f, k) = mesh.to_vertex(h); h = mesh.next(h); }
+                 }
+                 return out;
+             },
+             "Get face-vertex indices as an (M,3) int array.")
+        .def("points",
+             [](py::object self) {
+                 // writable view aliasing the mesh's memory, base = the mesh (src/mesh_py.cpp:96-106)
+                 HalfedgeMesh& mesh = self.cast<HalfedgeMesh&>();
+                 if (mesh.n_vertices() == 0) throw std::runtime_error("TriMesh has no vertices");
+                 std::vector<py::ssize_t> shape = {mesh.n_vertices(), 3};
+                 std::vector<py::ssize_t> strides = {3 * (py::ssize_t)sizeof(double), (py::ssize_t)sizeof(double)};
+                 return py::array_t<double>(shape, strides, mesh.points(), self);
+             },
+             "Get vertex positions as a writable (N,3) view onto the mesh memory.")
+        .def("n_vertices", [](HalfedgeMesh& mesh) { return (size_t)mesh.n_vertices(); }, "Number of vertices in the mesh.")
+        .def("n_edges", [](HalfedgeMesh& mesh) { return (size_t)mesh.n_edges(); }, "Number of edges in the mesh.")
+        .def("n_faces", [](HalfedgeMesh& mesh) { return (size_t)mesh.n_faces(); }, "Number of faces in the mesh.")
+        .def("halfedge_handle", [](HalfedgeMesh&, int i) { return HalfedgeHandle{i}; }, py::arg("edge"),
+             "Returns handle to halfedge i.")
+        .def("opposite_halfedge_handle",
+             [](HalfedgeMesh& mesh, const HalfedgeHandle& he) { check_he(mesh, he); return HalfedgeHandle{he.idx ^ 1}; },
+             py::arg("edge"), "Returns handle to the opposite of halfedge he.")
+        .def("next_halfedge_handle",
+             [](HalfedgeMesh& mesh, const HalfedgeHandle& he) { check_he(mesh, he); return HalfedgeHandle{mesh.next(he.idx)}; },
+             py::arg("edge"), "Returns handle to the halfedge next to halfedge he.")
+        // extensions used by the parity tests (not part of the reference surface)
+        .def("halfedge_arrays",
+             [](HalfedgeMesh& mesh) {
+                 auto mk = [](const std::vector<int>& v) { return py::array_t<int>((py::ssize_t)v.size(), v.data()); };
+                 return py::make_tuple(mk(mesh.he_to()), mk(mesh.he_next()), mk(mesh.he_face()), mk(mesh.v_he()), mk(mesh.f_he()));
+             },
+             "(he_to, he_next, he_face, v_he, f_he) of the host half-edge mirror.")
+        .def("device_halfedge_arrays",
+             [](HalfedgeMesh& mesh) {
+                 tm_mesh* dm = mesh.device(false);
+                 py::array_t<int> a(mesh.n_halfedges()), b(mesh.n_halfedges()), c(mesh.n_halfedges()), d(mesh.n_vertices());
+                 if (tm_mesh_get_topology(dm, a.mutable_data(), b.mutable_data(), c.mutable_data(), d.mutable_data()))
+                     throw std::runtime_error(tm_last_error());
+                 return py::make_tuple(a, b, c, d);
+             },
+             "(he_to, he_next, he_face, v_he) as stored on the device.")
+        .def("is_flip_ok", [](HalfedgeMesh& mesh, int e) { return mesh.is_flip_ok(e); }, py::arg("edge"))
+        .def("flip", [](HalfedgeMesh& mesh, int e) { mesh.flip(e); }, py::arg("edge"));
+
+    m.def("read_mesh",
+          [](const std::string& fname) -> std::unique_ptr<HalfedgeMesh> {
+              throw std::runtime_error("read_mesh('" + fname + "'): mesh file IO is outside the accelerated "
+                                       "path; construct TriMesh(points, faces) from arrays");
+          },
+          py::arg("fname"), "Read mesh from file (not provided by the B200 build).");
+
+    // ---- properties (src/bindings.cpp:192-247) ------------------------------------------
+    py::class_<VertexProperties>(m, "VertexProperties", "Container for vertex-averaged properties.")
+        .def(py::init())
+        .def_readwrite("area", &VertexProperties::area, "Face area")
+        .def_readwrite("volume", &VertexProperties::volume, "Face volume")
+        .def_readwrite("curvature", &VertexProperties::curvature, "Edge curvature")
+        .def_readwrite("bending", &VertexProperties::bending, "Bending energy")
+        .def_readwrite("tethering", &VertexProperties::tethering, "Tether regularization")
+        .def_readwrite("repulsion", &VertexProperties::repulsion, "Repulsion penalty");
+
+    // ---- single half-edge primitives (src/bindings.cpp:249-407) --------------------------
+    m.def("edge_length", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return he_geometry(mesh, he)[0]; },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("edge_length_grad", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return rows(he_geometry(mesh, he).data() + 4, 2); },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("face_area", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return he_geometry(mesh, he)[1]; },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("face_area_grad", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return rows(he_geometry(mesh, he).data() + 10, 3); },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("face_volume", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return he_geometry(mesh, he)[2]; },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("face_volume_grad", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return rows(he_geometry(mesh, he).data() + 19, 3); },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("dihedral_angle", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return he_geometry(mesh, he)[3]; },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+    m.def("dihedral_angle_grad", [](HalfedgeMesh& mesh, HalfedgeHandle& he) { return rows(he_geometry(mesh, he).data() + 28, 4); },
+          py::arg("mesh"), py::arg("halfedge_handle"));
+
+    // ---- parameters (src/bindings.cpp:409-670) ---------------------------------------------
+    py::enum_<BondType>(m, "BondType", "Types for the tether potential.")
+        .value("Edge", BondType::Edge, "Smoothed well/box potential on edges.")
+        .value("Area", BondType::Area, "Harmonic potential on face area.")
+        .value("None", BondType::None, "None")
+        .export_values();
+
+    py::class_<BondParams>(m, "BondParams", "Tether regularization parameters.")
+        .def(py::init())
+        .def_readwrite("lc0", &BondParams::lc0, "Onset distance for attracting force (BondType::Edge).")
+        .def_readwrite("lc1", &BondParams::lc1, "Onset distance for repelling force (BondType::Edge).")
+        .def_readwrite("a0", &BondParams::a0, "Reference face area (BondType::Area).")
+        .def_readwrite("r", &BondParams::r, "Steepness of regularization potential (must be >=1).")
+        .def_readwrite("type", &BondParams::type, "Type of potential (edge-based, area-based).");
+
+    py::class_<SurfaceRepulsionParams>(m, "SurfaceRepulsionParams", "Surface repulsion parameters.")
+        .def(py::init())
+        .def_readwrite("lc1", &SurfaceRepulsionParams::lc1, "Onset distance for repelling force.")
+        .def_readwrite("r", &SurfaceRepulsionParams::r, "Steepness of repelling potential (must be >=1).")
+        .def_readwrite("n_search", &SurfaceRepulsionParams::n_search, "Neighbour list type: 'cell-list' or 'verlet-list'.")
+        .def_readwrite("rlist", &SurfaceRepulsionParams::rlist, "Neighbour search distance cutoff.")
+        .def_readwrite("exclusion_level", &SurfaceRepulsionParams::exclusion_level,
+                       "Connected neighbourhood exclusion for neighbour lists: one of [0,1,2].");
+
+    py::class_<ContinuationParams>(m, "ContinuationParams", "Parameter continuation.")
+        .def(py::init())
+        .def_readwrite("delta", &ContinuationParams::delta, "Interpolation blending `time` step.")
+        .def_readwrite("lam", &ContinuationParams::lambda, "Interpolation state.");
+
+    py::class_<EnergyParams>(m, "EnergyParams", "Parametrization of the Helfrich functional.")
+        .def(py::init())
+        .def_readwrite("kappa_b", &EnergyParams::kappa_b, "Weight of the Helfrich functional.")
+        .def_readwrite("kappa_a", &EnergyParams::kappa_a, "Weight of the surface area penalty.")
+        .def_readwrite("kappa_v", &EnergyParams::kappa_v, "Weight of the volume penalty.")
+        .def_readwrite("kappa_c", &EnergyParams::kappa_c, "Weight of the area-difference penalty.")
+        .def_readwrite("kappa_t", &EnergyParams::kappa_t, "Weight of the tether regularization.")
+        .def_readwrite("kappa_r", &EnergyParams::kappa_r, "Weight of the surface repulsion.")
+        .def_readwrite("area_frac", &EnergyParams::area_frac, "Target surface area fraction wrt. the initial geometry.")
+        .def_readwrite("volume_frac", &EnergyParams::volume_frac, "Target volume fraction wrt. the initial geometry.")
+        .def_readwrite("curvature_frac", &EnergyParams::curvature_frac, "Target curvature fraction wrt. the initial geometry.")
+        .def_readwrite("bond_params", &EnergyParams::bond_params, "Parameters for the tether regularization.")
+        .def_readwrite("repulse_params", &EnergyParams::repulse_params, "Parameters for the surface repulsion.")
+        .def_readwrite("continuation_params", &EnergyParams::continuation_params, "Parameters for the parameter continuation.");
+
+    // ---- EnergyManager (src/bindings.cpp:672-837) ----------------------------------------------
+    py::class_<EnergyManager>(m, "EnergyManager", "Helfrich functional evaluation (device resident).")
+        .def(py::init<HalfedgeMesh&, const EnergyParams&>(), py::arg("mesh"), py::arg("eparams"))
+        .def("properties", &EnergyManager::properties, py::arg("mesh"),
+             "Evaluate the reduced vertex properties of the mesh.")
+        .def("energy", static_cast<double (EnergyManager::*)(HalfedgeMesh&)>(&EnergyManager::energy), py::arg("mesh"),
+             "Evaluate the Helfrich functional on the mesh.")
+        .def("energy", static_cast<double (EnergyManager::*)(const VertexProperties&) const>(&EnergyManager::energy),
+             py::arg("vprops"), "Evaluate the Helfrich functional from pre-evaluated reduced properties.")
+        .def("gradient",
+             [](EnergyManager& self, HalfedgeMesh& mesh) {
+                 py::array_t<double> g({mesh.n_vertices(), 3});
+                 self.gradient(mesh, g.mutable_data());
+                 return g;
+             },
+             py::arg("mesh"), "Evaluate the gradient of the Helfrich functional as an (N,3) array.")
+        .def("update_reference_properties", &EnergyManager::update_reference_properties,
+             "Update reference configurations (parameter continuation).")
+        .def("update_repulsion", &EnergyManager::update_repulsion, py::arg("mesh"),
+             "Rebuild the neighbour list / repulsion penalty from the current mesh state.")
+        .def("print_info",
+             [](EnergyManager& self, HalfedgeMesh& mesh) { py::print(self.info(mesh), py::arg("end") = ""); },
+             py::arg("mesh"), "Print energy information evaluated on the state defined by mesh.")
+        .def_readonly("eparams", &EnergyManager::params, "Parametrization of the Helfrich functional.")
+        .def_readonly("initial_props", &EnergyManager::initial_props, "Initial reference properties.");
+
+    // ---- flips (src/bindings.cpp:839-891) ----------------------------------------------------------
+    m.def("flip",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed) {
+              return flip_serial(mesh, estore, flip_ratio, seed);
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("flip_ratio"), py::arg("seed") = -1,
+          "Serial flip sweep; returns the number of accepted flips.");
+    m.def("pflip",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed) {
+              return flip_parallel_batches(mesh, estore, flip_ratio, seed);
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("flip_ratio"), py::arg("seed") = -1,
+          "Batch-parallel flip sweep; returns the number of accepted flips.");
+
+    // ---- neighbour lists (src/bindings.cpp:893-985) -------------------------------------------------
+    py::class_<Point>(m, "Point", "3D point (opaque).")
+        .def("__getitem__", [](const Point& p, int i) {
+            if (i < 0 || i > 2) throw py::index_error();
+            return p.v[i];
+        })
+        .def("__len__", [](const Point&) { return 3; });
+
+    py::class_<NeighbourList>(m, "NeighbourList", "Neighbour list interface (cell list or verlet list).")
+        .def("distance_matrix", &NeighbourList::distance_matrix, py::arg("mesh"), py::arg("rdist"),
+             "Sparse distance matrix as a tuple of lists (distances, i, j).")
+        .def("point_distances",
+             [](NeighbourList& self, HalfedgeMesh& mesh, int pid, double rdist) {
+                 auto res = self.point_distances(mesh, pid, rdist);
+                 std::vector<Point> pts(std::get<0>(res).size());
+                 for (size_t k = 0; k < pts.size(); k++)
+                     for (int c = 0; c < 3; c++) pts[k].v[c] = std::get<0>(res)[k][c];
+                 return py::make_tuple(py::cast(pts), py::cast(std::get<1>(res)));
+             },
+             py::arg("mesh"), py::arg("pid"), py::arg("rdist"),
+             "Distance components between pid and listed vertices within rdist: (distances, ids).");
+
+    m.def("make_nlist", &make_nlist, py::arg("mesh"), py::arg("eparams"), "Neighbour list factory.");
+
+    // ---- utils (src/bindings.cpp:987-1036) -------------------------------------------------------------
+    m.def("area", &area, py::arg("mesh"), "Compute surface area.");
+    m.def("edges_length", &edges_length, py::arg("mesh"), "Compute cumulative edge length.");
+    m.def("avg_tri_props", &mean_tri_props, py::arg("mesh"), "Average triangle area and edge length.");
+
+    // forward finite-difference gradient for debugging (src/bindings.cpp:25-50,1072-1092)
+    m.def("gradient",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, py::array_t<double>& grad, double eps) {
+              double e0 = estore.energy(mesh);
+              auto g = grad.mutable_unchecked<2>();
+              double* x = mesh.points();
+              for (int i = 0; i < mesh.n_vertices(); i++)
+                  for (int j = 0; j < 3; j++) {
+                      x[3 * i + j] += eps;
+                      g(i, j) = (estore.energy(mesh) - e0) / eps;
+                      x[3 * i + j] -= eps;
+                  }
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("gradient"), py::arg("epsilon") = 1.0e-6,
+          "Finite difference gradient of energy.");
+
+    // ---- B200 extensions ----------------------------------------------------------------------------------
+    m.def("device_count", []() { return tm_device_count(); });
+    m.def("set_device", &set_default_device, py::arg("device"));
+    m.def("launch_count", []() { return tm_launch_count(); });
+    m.def("last_error", []() { return std::string(tm_last_error()); });
+}

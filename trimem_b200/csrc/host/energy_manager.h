@@ -1,0 +1,112 @@
+// Host-side operator interface of the hot path: parameter PODs, EnergyManager,
+// NeighbourList and the flip-sweep drivers. Same names, argument meaning and
+// error behaviour as the reference's C++ core (src/params.h, src/energy.h,
+// src/nlists/nlist.h, src/flips.h); every evaluation is forwarded to the C ABI
+// (include/trimem_b200.h) and runs on the device.
+#pragma once
+#include <array>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../../include/trimem_b200.h"
+#include "halfedge_mesh.h"
+
+namespace trimem_b200 {
+
+// ---- parameters: defaults as in src/params.h:19-71 ---------------------------
+enum class BondType : int { Edge, Area, None, Default = Edge };
+
+struct BondParams {
+    double lc0 = 1;
+    double lc1 = 0;
+    double a0 = 1;
+    int r = 2;
+    BondType type = BondType::Edge;
+};
+
+struct ContinuationParams {
+    double delta = 0;
+    double lambda = 1;
+};
+
+struct SurfaceRepulsionParams {
+    double lc1 = 0;
+    int r = 2;
+    std::string n_search = "cell-list";
+    double rlist = 0.1;
+    int exclusion_level = 2;
+};
+
+struct EnergyParams {
+    double kappa_b = 0, kappa_a = 0, kappa_v = 0, kappa_c = 0, kappa_t = 0, kappa_r = 0;
+    double area_frac = 1, volume_frac = 1, curvature_frac = 1;
+    BondParams bond_params;
+    ContinuationParams continuation_params;
+    SurfaceRepulsionParams repulse_params;
+};
+
+// reduced (or per-vertex) properties, src/mesh_properties.h:15-48
+struct VertexProperties {
+    double area = 0, volume = 0, curvature = 0, bending = 0, tethering = 0, repulsion = 0;
+};
+
+// ---- neighbour list handle (src/nlists/nlist.h:17-41) ---------------------------
+class NeighbourList {
+public:
+    NeighbourList(HalfedgeMesh& mesh, const EnergyParams& params);   // = make_nlist
+    ~NeighbourList();
+    NeighbourList(const NeighbourList&) = delete;
+    NeighbourList& operator=(const NeighbourList&) = delete;
+
+    std::tuple<std::vector<double>, std::vector<int>, std::vector<int>>
+    distance_matrix(HalfedgeMesh& mesh, double rdist) const;
+    // (n x 3 distance components x_pid - x_j, neighbour ids)
+    std::tuple<std::vector<std::array<double, 3>>, std::vector<int>>
+    point_distances(HalfedgeMesh& mesh, int pid, double rdist) const;
+
+    tm_nlist* handle() const { return nl_; }
+
+private:
+    tm_nlist* nl_ = nullptr;
+};
+
+std::unique_ptr<NeighbourList> make_nlist(HalfedgeMesh& mesh, const EnergyParams& params);
+
+// ---- EnergyManager (src/energy.h:20-56) ---------------------------------------------
+class EnergyManager {
+public:
+    EnergyManager(HalfedgeMesh& mesh, const EnergyParams& params);
+
+    void update_reference_properties();
+    VertexProperties interpolate_reference_properties() const;
+    void update_repulsion(HalfedgeMesh& mesh);
+
+    VertexProperties properties(HalfedgeMesh& mesh);
+    double energy(HalfedgeMesh& mesh);
+    double energy(const VertexProperties& props) const;
+    // gradient into caller memory (n_vertices x 3)
+    void gradient(HalfedgeMesh& mesh, double* out);
+    std::string info(HalfedgeMesh& mesh);
+
+    // C-ABI parameter block for the current state (reference values interpolated)
+    tm_energy_params abi_params() const;
+    tm_nlist* nlist_handle() const { return nlist ? nlist->handle() : nullptr; }
+
+    EnergyParams params;
+    VertexProperties initial_props;
+    std::unique_ptr<NeighbourList> nlist;
+};
+
+// ---- flips (src/flips.h) ----------------------------------------------------------------
+// `seed` < 0 seeds from the clock like the reference (flips.cpp:20,105-106).
+int flip_serial(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
+int flip_parallel_batches(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
+
+// ---- setup-time reductions (src/util.h) ------------------------------------------------
+double area(HalfedgeMesh& mesh);
+double edges_length(HalfedgeMesh& mesh);
+std::tuple<double, double> mean_tri_props(HalfedgeMesh& mesh);
+
+}  // namespace trimem_b200

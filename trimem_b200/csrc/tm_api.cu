@@ -1,0 +1,303 @@
+// C ABI of libtrimem_b200 (include/trimem_b200.h): handles, transfers, and the
+// host-side sequencing of the sweeps. No arithmetic of the hot path lives here.
+#include <cstdarg>
+#include <cmath>
+
+#include "tm_common.cuh"
+
+unsigned long long g_tm_launches = 0;
+static thread_local char g_err[1024] = "";
+
+void tm_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    TM_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+
+// trimem_energy (kernel.h:110-122) from the six reduced properties
+double energy_from_props(const tm_energy_params& p, const double s[6]) {
+    double e = 0.0, d;
+    d = s[0] / p.ref_area - 1.0;      e += p.kappa_a * d * d;
+    d = s[1] / p.ref_volume - 1.0;    e += p.kappa_v * d * d;
+    d = s[2] / p.ref_curvature - 1.0; e += p.kappa_c * d * d;
+    e += p.kappa_t * s[4];
+    e += p.kappa_r * s[5];
+    e += p.kappa_b * s[3];
+    return e;
+}
+
+int check_mesh(tm_mesh* m, bool need_pos = true) {
+    TM_CHECK(m != nullptr, "null mesh handle");
+    TM_CHECK(m->V > 0 && m->he_to != nullptr, "mesh has no topology (call tm_mesh_set_topology first)");
+    (void)need_pos;
+    TM_CUDA(cudaSetDevice(m->device));
+    return 0;
+}
+
+int check_params(const tm_energy_params* p) {
+    TM_CHECK(p != nullptr, "null parameter block");
+    TM_CHECK(p->bond_type == TM_BOND_EDGE || p->bond_type == TM_BOND_AREA, "Unknown bond potential");
+    return 0;
+}
+
+NlView view_of(tm_nlist* nl) { return nl ? nl->view() : tm_no_nlist(); }
+
+int fetch_sums(tm_mesh* m, double out[6]) {
+    TM_CUDA(cudaMemcpyAsync(m->h_sums, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    for (int q = 0; q < 6; q++) out[q] = m->h_sums[q];
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tm_last_error(void) { return g_err; }
+int tm_abi_version(void) { return 1; }
+
+int tm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void* tm_host_alloc(unsigned long long bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 8;
+    if (tm_device_count() > 0 && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+        // tag pinned blocks so tm_host_free knows how to release them
+        return p;
+    }
+    cudaGetLastError();
+    return malloc(bytes);
+}
+
+void tm_host_free(void* p) {
+    if (!p) return;
+    cudaPointerAttributes attr;
+    if (tm_device_count() > 0 && cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+        attr.type == cudaMemoryTypeHost) {
+        cudaFreeHost(p);
+        return;
+    }
+    cudaGetLastError();
+    free(p);
+}
+
+void tm_free(void* p) { free(p); }
+unsigned long long tm_launch_count(void) { return g_tm_launches; }
+
+// ------------------------------------------------------------------- mesh --
+int tm_mesh_create(int device, tm_mesh** out) {
+    TM_CHECK(out != nullptr, "null output pointer");
+    int n = tm_device_count();
+    TM_CHECK(n > 0, "no CUDA device available: libtrimem_b200 has no CPU fallback");
+    TM_CHECK(device >= 0 && device < n, "device %d out of range (have %d)", device, n);
+    TM_CUDA(cudaSetDevice(device));
+    tm_mesh* m = new tm_mesh();
+    m->device = device;
+    TM_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    TM_CUDA(cudaEventCreate(&m->ev0));
+    TM_CUDA(cudaEventCreate(&m->ev1));
+    TM_CUDA(cudaMalloc(&m->partials, sizeof(double) * 6 * TM_MAX_PARTIAL_BLOCKS));
+    TM_CUDA(cudaMalloc(&m->sums, sizeof(double) * 8));
+    TM_CUDA(cudaMalloc(&m->ticket, sizeof(unsigned) * 4));
+    TM_CUDA(cudaMemset(m->ticket, 0, sizeof(unsigned) * 4));
+    TM_CUDA(cudaMemset(m->sums, 0, sizeof(double) * 8));
+    TM_CUDA(cudaHostAlloc(&m->h_sums, sizeof(double) * 8, cudaHostAllocDefault));
+    *out = m;
+    return 0;
+}
+
+
+int tm_mesh_destroy(tm_mesh* m) {
+    if (!m) return 0;
+    cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream);
+    tm_flips_release(m);
+    cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
+    cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt);
+    cudaFree(m->x3); cudaFree(m->rho); cudaFree(m->vprops); cudaFree(m->grad);
+    cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
+    cudaFree(m->flush);
+    cudaFreeHost(m->h_sums);
+    cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
+    cudaStreamDestroy(m->stream);
+    delete m;
+    return 0;
+}
+
+int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int* he_next,
+                         const int* he_face, const int* v_he) {
+    TM_CHECK(m != nullptr, "null mesh handle");
+    TM_CHECK(V > 0 && HE >= 0 && (HE % 2) == 0, "bad mesh sizes: %d vertices, %d half-edges", V, HE);
+    TM_CHECK(V < TM_RING_FACE, "too many vertices (%d)", V);
+    TM_CUDA(cudaSetDevice(m->device));
+    if (V != m->V) {
+        if (dev_alloc(&m->v_he, V) || dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) ||
+            dev_alloc(&m->x3, 3 * (size_t)V) || dev_alloc(&m->rho, V) || dev_alloc(&m->grad, 3 * (size_t)V))
+            return 1;
+        if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
+        TM_CUDA(cudaMemsetAsync(m->x3, 0, sizeof(double) * 3 * (size_t)V, m->stream));
+    }
+    if (HE != m->HE) {
+        if (dev_alloc(&m->he_to, HE) || dev_alloc(&m->he_next, HE) || dev_alloc(&m->he_face, HE) ||
+            dev_alloc(&m->ring_v, HE))
+            return 1;
+    }
+    m->V = V; m->HE = HE;
+    TM_CUDA(cudaMemcpyAsync(m->he_to, he_to, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
+    TM_CUDA(cudaMemcpyAsync(m->he_next, he_next, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
+    TM_CUDA(cudaMemcpyAsync(m->he_face, he_face, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
+    TM_CUDA(cudaMemcpyAsync(m->v_he, v_he, sizeof(int) * V, cudaMemcpyHostToDevice, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    m->rings_valid = false;
+    return tm_ensure_rings(m);
+}
+
+int tm_mesh_get_topology(tm_mesh* m, int* he_to, int* he_next, int* he_face, int* v_he) {
+    if (check_mesh(m)) return 1;
+    if (he_to) TM_CUDA(cudaMemcpyAsync(he_to, m->he_to, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    if (he_next) TM_CUDA(cudaMemcpyAsync(he_next, m->he_next, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    if (he_face) TM_CUDA(cudaMemcpyAsync(he_face, m->he_face, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    if (v_he) TM_CUDA(cudaMemcpyAsync(v_he, m->v_he, sizeof(int) * m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_mesh_get_rings(tm_mesh* m, int* ring_off, int* ring_v, int* ring_flags) {
+    if (check_mesh(m) || tm_ensure_rings(m)) return 1;
+    std::vector<int> off(m->V + 1), rv(m->HE > 0 ? m->HE : 1);
+    TM_CUDA(cudaMemcpyAsync(off.data(), m->ring_off, sizeof(int) * (m->V + 1), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaMemcpyAsync(rv.data(), m->ring_v, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    if (ring_off) memcpy(ring_off, off.data(), sizeof(int) * (m->V + 1));
+    int n = off[m->V];
+    for (int k = 0; k < n; k++) {
+        if (ring_v) ring_v[k] = rv[k] & TM_RING_MASK;
+        if (ring_flags) ring_flags[k] = ((rv[k] & TM_RING_FACE) ? 1 : 0) | ((rv[k] & TM_RING_OFACE) ? 2 : 0);
+    }
+    return 0;
+}
+
+int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
+    if (check_mesh(m)) return 1;
+    TM_CHECK(xyz != nullptr, "null positions");
+    TM_CUDA(cudaMemcpyAsync(m->x3, xyz, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
+    return 0;
+}
+
+int tm_mesh_get_positions(tm_mesh* m, double* xyz) {
+    if (check_mesh(m)) return 1;
+    TM_CUDA(cudaMemcpyAsync(xyz, m->x3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_mesh_n_vertices(const tm_mesh* m) { return m ? m->V : 0; }
+int tm_mesh_n_halfedges(const tm_mesh* m) { return m ? m->HE : 0; }
+
+// ------------------------------------------------------- energy / gradient --
+int tm_energy_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
+    if (check_mesh(m) || check_params(p)) return 1;
+    return tm_launch_props(m, view_of(nl), *p, true, false);
+}
+
+int tm_gradient_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
+    if (check_mesh(m) || check_params(p)) return 1;
+    // property sweep without tether/repulsion (the gradient only needs A, V, C and rho),
+    // then the gather sweep; both on the mesh's stream, no host round trip in between.
+    if (tm_launch_props(m, view_of(nl), *p, false, false)) return 1;
+    return tm_launch_grad(m, view_of(nl), *p);
+}
+
+int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, double props[6]) {
+    if (check_mesh(m) || check_params(p)) return 1;
+    double s[6];
+    if (fetch_sums(m, s)) return 1;
+    if (props) for (int q = 0; q < 6; q++) props[q] = s[q];
+    if (energy) *energy = energy_from_props(*p, s);
+    return 0;
+}
+
+int tm_fetch_gradient(tm_mesh* m, double* grad) {
+    if (check_mesh(m)) return 1;
+    TM_CHECK(grad != nullptr, "null gradient buffer");
+    TM_CUDA(cudaMemcpyAsync(grad, m->grad, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_sync(tm_mesh* m) {
+    if (check_mesh(m)) return 1;
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double out[6]) {
+    if (tm_energy_async(m, nl, p)) return 1;
+    return fetch_sums(m, out);
+}
+
+int tm_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* out) {
+    if (check_mesh(m) || check_params(p)) return 1;
+    if (tm_launch_props(m, view_of(nl), *p, true, true)) return 1;
+    TM_CUDA(cudaMemcpyAsync(out, m->vprops, sizeof(double) * 6 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_energy(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* energy, double props[6]) {
+    if (tm_energy_async(m, nl, p)) return 1;
+    return tm_fetch_energy(m, p, energy, props);
+}
+
+int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* grad, double props[6]) {
+    if (tm_gradient_async(m, nl, p)) return 1;
+    if (props) {
+        TM_CUDA(cudaMemcpyAsync(m->h_sums, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (tm_fetch_gradient(m, grad)) return 1;
+    if (props) for (int q = 0; q < 6; q++) props[q] = m->h_sums[q];
+    return 0;
+}
+
+int tm_timer_start(tm_mesh* m) {
+    if (check_mesh(m)) return 1;
+    TM_CUDA(cudaEventRecord(m->ev0, m->stream));
+    return 0;
+}
+
+int tm_timer_stop(tm_mesh* m, float* ms) {
+    if (check_mesh(m)) return 1;
+    TM_CUDA(cudaEventRecord(m->ev1, m->stream));
+    TM_CUDA(cudaEventSynchronize(m->ev1));
+    TM_CUDA(cudaEventElapsedTime(ms, m->ev0, m->ev1));
+    return 0;
+}
+
+int tm_flush_l2(tm_mesh* m, unsigned long long bytes) {
+    if (check_mesh(m)) return 1;
+    if (m->flush_bytes < bytes) {
+        if (m->flush) cudaFree(m->flush);
+        m->flush = nullptr;
+        TM_CUDA(cudaMalloc(&m->flush, bytes));
+        m->flush_bytes = bytes;
+    }
+    TM_CUDA(cudaMemsetAsync(m->flush, 1, bytes, m->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// Property sweep (K1+K2) and gradient sweep (K3+K4) of the Helfrich functional.
+//
+// Replaces, in the reference:
+//   vertex_properties / vertex_properties_grad   src/mesh_properties.cpp:12-148
+//   edge/area/volume/dihedral primitives + grads src/mesh_util.h:15-185
+//   tether potentials                            src/mesh_tether.h:29-121
+//   surface repulsion                            src/mesh_repulsion.h:28-79
+//   penalty terms, parallel_for/reduction        src/kernel.h:19-137,243-262
+//   EnergyManager::properties/energy/gradient    src/energy.cpp:63-124
+//
+// Formulation. One thread owns one vertex i and walks its
+// one-ring j_0..j_{d-1} (clockwise CSR row). With e_s = x_{j_s} - x_i,
+//   n_s   = e_s x e_{s-1}            un-normalised normal of face (i, j_s, j_{s-1})
+//   p_s   = e_s . e_{s-1}
+//   theta_s = atan2(-|e_s| (e_{s+1} . n_s), n_s . n_{s+1})   dihedral of spoke s
+// everything the reference obtains from acos/tan of sector angles follows
+// algebraically (cot = dot/|cross|), so a sweep needs one atan2, two rsqrt per
+// ring slot and no other transcendental. The gradient is a gather: vertex i
+// only writes g_i (no fp64 atomics) and needs the ring positions plus
+// rho_v = c_v / a_v of itself and of its ring from the property sweep.
+// Global sums use warp shuffles, a fixed block tree and a fixed-order last-block
+// pass, so results are bit-reproducible run to run.
+#include "tm_common.cuh"
+#include "tm_neigh.cuh"
+
+namespace {
+
+struct DevParams {
+    double kappa_b, kappa_a, kappa_v, kappa_c, kappa_t, kappa_r;
+    double ref_area, ref_volume, ref_curvature;
+    double lc0, lc1, a0;
+    int bond_r, bond_type;
+    double rep_lc1;
+    int rep_r;
+};
+
+__device__ __forceinline__ double powi(double x, int r) {
+    if (r == 2) return x * x;
+    int a = r < 0 ? -r : r;
+    double acc = 1.0, b = x;
+    while (a) { if (a & 1) acc *= b; b *= b; a >>= 1; }
+    return r < 0 ? 1.0 / acc : acc;
+}
+
+// FlatBottomEdgePenalty::vertex_property (mesh_tether.h:40-54)
+__device__ __forceinline__ double tether_edge(double l, const DevParams& P) {
+    if (l > P.lc0) return powi((double)P.bond_r, P.bond_r + 1) * powi(l - P.lc0, P.bond_r);
+    if (l < P.lc1) return exp(l / (l - P.lc1)) / powi(l, P.bond_r);
+    return 0.0;
+}
+// slope factor of FlatBottomEdgePenalty::vertex_property_grad (mesh_tether.h:62-76)
+__device__ __forceinline__ double tether_edge_fac(double l, const DevParams& P) {
+    double fac = 0.0;
+    if (l > P.lc0) fac = powi((double)P.bond_r, P.bond_r + 2) * powi(l - P.lc0, P.bond_r - 1);
+    if (l < P.lc1) {
+        double lr = powi(l, P.bond_r);
+        double lmc = l - P.lc1;
+        fac -= P.lc1 / (lmc * lmc) + P.bond_r / l;
+        fac /= lr;
+        fac *= exp(l / lmc);
+    }
+    return fac;
+}
+
+// ---- reductions ---------------------------------------------------------------
+template <int NT, int NQ>
+__device__ __forceinline__ void block_reduce(double (&v)[NQ], double* out /* NQ, thread 0 */) {
+    __shared__ double sm[NQ][NT / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        double t = v[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) sm[q][w] = t;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double t = lane < NT / 32 ? sm[q][lane] : 0.0;
+#pragma unroll
+            for (int o = NT / 64; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) out[q] = t;
+        }
+    }
+    __syncthreads();
+}
+
+// ---- K1 + K2: per-vertex properties and their global sums ----------------------
+// FULL = also tether and repulsion (what energy()/properties() need); the property
+// sweep inside gradient() only needs area, volume, curvature and rho.
+template <bool FULL, bool WRITE_VPROPS>
+__global__ void __launch_bounds__(TM_PROPS_THREADS)
+k_props(MeshView mv, NlView nl, DevParams P, double* __restrict__ rho_out,
+        double* __restrict__ vprops, double* __restrict__ partials,
+        unsigned* __restrict__ ticket, double* __restrict__ sums) {
+    int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
+    if (i < mv.V) {
+        d3 xi = ldpos(mv.x3, i);
+        int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
+        double area = 0, vol = 0, curv = 0, teth = 0;
+        if (d > 0) {
+            const int* ring = mv.ring_v + beg;
+            d3 e_prev = ldpos(mv.x3, __ldg(ring + d - 1) & TM_RING_MASK) - xi;
+            int r_cur = __ldg(ring);
+            d3 e_cur = ldpos(mv.x3, r_cur & TM_RING_MASK) - xi;
+            d3 n_cur = cross3(e_cur, e_prev);
+            for (int s = 0; s < d; s++) {
+                int sn = s + 1 == d ? 0 : s + 1;
+                int r_next = __ldg(ring + sn);
+                d3 e_next = ldpos(mv.x3, r_next & TM_RING_MASK) - xi;
+                d3 n_next = cross3(e_next, e_cur);
+                if (r_cur & TM_RING_FACE) {           // `not he.is_boundary()`
+                    double l = sqrt(dot3(e_cur, e_cur));
+                    double a_f = 0.5 * sqrt(dot3(n_cur, n_cur));
+                    area += a_f;
+                    vol += dot3(xi, n_cur);           // = (x_j x x_k) . x_i
+                    if (r_cur & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
+                        double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
+                        curv = fma(l, th, curv);
+                    }
+                    if (FULL) {
+                        if (P.bond_type == TM_BOND_EDGE) teth += tether_edge(l, P);
+                        else { double q = a_f / P.a0 - 1.0; teth += q * q; }
+                    }
+                }
+                e_prev = e_cur; e_cur = e_next; n_cur = n_next; r_cur = r_next;
+            }
+        }
+        area = area / 3.0;
+        vol = vol / 18.0;                              // /6 per face, /3 multiplicity
+        curv = curv / 4.0;                             // 0.5 l theta per half-edge, /2 multiplicity
+        double bend = 2.0 * curv * curv / area;
+        double rep = 0.0;
+        if (FULL) {
+            teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
+            if (nl.kind >= 0 && P.rep_lc1 > 0.0) {
+                for_each_neighbour(mv, nl, i, xi, P.rep_lc1, [&](int, d3, double l) {
+                    rep += exp(l / (l - P.rep_lc1)) / powi(l, P.rep_r);
+                });
+            }
+        }
+        if (rho_out) rho_out[i] = curv / area;
+        if (WRITE_VPROPS) {
+            double* o = vprops + 6 * (size_t)i;
+            o[0] = area; o[1] = vol; o[2] = curv; o[3] = bend; o[4] = teth; o[5] = rep;
+        }
+        acc[0] = area; acc[1] = vol; acc[2] = curv; acc[3] = bend; acc[4] = teth; acc[5] = rep;
+    }
+
+    // block partials -> last block sums all partials in a fixed order
+    __shared__ double bsum[6];
+    __shared__ bool last;
+    block_reduce<TM_PROPS_THREADS, 6>(acc, bsum);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) partials[(size_t)q * gridDim.x + blockIdx.x] = bsum[q];
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double tot[6] = {0, 0, 0, 0, 0, 0};
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += TM_PROPS_THREADS) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) tot[q] += __ldcg(partials + (size_t)q * gridDim.x + b);
+        }
+        block_reduce<TM_PROPS_THREADS, 6>(tot, bsum);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) sums[q] = bsum[q];
+            *ticket = 0;
+        }
+    }
+}
+
+// ---- K3 + K4: gather gradient ----------------------------------------------------
+__global__ void __launch_bounds__(TM_GRAD_THREADS)
+k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
+       const double* __restrict__ sums, double* __restrict__ grad) {
+    int i = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
+    if (i >= mv.V) return;
+
+    // chain-rule factors of the global penalties (kernel.h:27-71,124-137)
+    const double fA = 2.0 * P.kappa_a / P.ref_area * (sums[0] / P.ref_area - 1.0);
+    const double fV = 2.0 * P.kappa_v / P.ref_volume * (sums[1] / P.ref_volume - 1.0);
+    const double fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
+    const double kb = P.kappa_b, kt = P.kappa_t;
+
+    d3 xi = ldpos(mv.x3, i);
+    d3 g = mk3(0, 0, 0);
+    int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
+    if (d > 0) {
+        const int* ring = mv.ring_v + beg;
+        const double rho_i = rho[i];
+        d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
+        d3 esum = mk3(0, 0, 0);      // sum of (e_{s-1} - e_s) over faces (0 for closed fans)
+
+        int r_prev = __ldg(ring + d - 1), r_cur = __ldg(ring);
+        int j_prev = r_prev & TM_RING_MASK, j_cur = r_cur & TM_RING_MASK;
+        d3 e_prev = ldpos(mv.x3, j_prev) - xi;
+        d3 e_cur = ldpos(mv.x3, j_cur) - xi;
+        double rho_prev = __ldg(rho + j_prev), rho_cur = __ldg(rho + j_cur);
+        double l2_prev = dot3(e_prev, e_prev), l2_cur = dot3(e_cur, e_cur);
+        double p_cur = dot3(e_cur, e_prev);
+        d3 n_cur = cross3(e_cur, e_prev);
+        double nn_cur = dot3(n_cur, n_cur);
+        double in_cur = rsqrt(nn_cur);                // 1/|n_s|
+
+        for (int s = 0; s < d; s++) {
+            int sn = s + 1 == d ? 0 : s + 1;
+            int r_next = __ldg(ring + sn);
+            int j_next = r_next & TM_RING_MASK;
+            d3 e_next = ldpos(mv.x3, j_next) - xi;
+            double rho_next = __ldg(rho + j_next);
+            double l2_next = dot3(e_next, e_next);
+            double p_next = dot3(e_next, e_cur);
+            d3 n_next = cross3(e_next, e_cur);
+            double nn_next = dot3(n_next, n_next);
+            double in_next = rsqrt(nn_next);
+
+            if (r_cur & TM_RING_FACE) {
+                const double il = rsqrt(l2_cur);       // 1/l_s
+                const double l = l2_cur * il;
+                const double inn_cur = in_cur * in_cur;
+                double cE = 0.0, cEp = 0.0, cN = 0.0, cNn = 0.0;
+
+                // spoke edge (i, j_s): owners i and j_s   (mesh_properties.cpp:88-98)
+                const double W = 0.5 * fC + kb * (rho_i + rho_cur);
+                if (r_cur & TM_RING_OFACE) {
+                    const double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
+                    cE -= W * th * il;                                   // theta * dl/dx_i
+                    cN += W * (l2_cur - p_cur) * inn_cur;                // l * dtheta/dx_i
+                    cNn += W * (l2_cur - p_next) * (in_next * in_next);
+                }
+                // face (i, j_s, j_{s-1}): owners i, j_s, j_{s-1}   (:103-118)
+                double U = fA - (2.0 / 3.0) * kb * (rho_i * rho_i + rho_cur * rho_cur + rho_prev * rho_prev);
+                if (P.bond_type == TM_BOND_AREA) {
+                    const double a_f = 0.5 * nn_cur * in_cur;
+                    U += kt * 2.0 * (a_f / P.a0 - 1.0) / P.a0;
+                }
+                const double h = 0.5 * U * in_cur;                       // dA_f/dx_i in the e basis
+                cEp += h * (p_cur - l2_cur);
+                cE -= h * (l2_prev - p_cur);
+                // link edge (j_s, j_{s-1}) seen from its apex i: owners j_s, j_{s-1}   (:121-129)
+                const double Wl = 0.5 * fC + kb * (rho_cur + rho_prev);
+                cN -= Wl * (l2_cur + l2_prev - 2.0 * p_cur) * inn_cur;
+                // tether bond (:132-133)
+                if (P.bond_type == TM_BOND_EDGE) {
+                    if (l > P.lc0 || l < P.lc1) cE -= kt * tether_edge_fac(l, P) * il;
+                }
+                axpy3(g, cE, e_cur);
+                axpy3(g, cEp, e_prev);
+                axpy3(g, cN, n_cur);
+                axpy3(g, cNn, n_next);
+                nsum = nsum + n_cur;
+                esum = esum + (e_prev - e_cur);
+            }
+            r_prev = r_cur; r_cur = r_next;
+            e_prev = e_cur; e_cur = e_next;
+            rho_prev = rho_cur; rho_cur = rho_next;
+            l2_prev = l2_cur; l2_cur = l2_next;
+            p_cur = p_next; n_cur = n_next; nn_cur = nn_next; in_cur = in_next;
+        }
+        // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
+        d3 vg = nsum + cross3(xi, esum);
+        axpy3(g, fV / 6.0, vg);
+    }
+
+    // repulsion (mesh_properties.cpp:139-146, mesh_repulsion.h:56-78)
+    if (nl.kind >= 0 && P.rep_lc1 > 0.0 && P.kappa_r != 0.0) {
+        d3 gr = mk3(0, 0, 0);
+        for_each_neighbour(mv, nl, i, xi, P.rep_lc1, [&](int, d3 dv, double l) {
+            double lr = powi(l, P.rep_r + 1);
+            double lmc = l - P.rep_lc1;
+            double fac = -(P.rep_lc1 / (lmc * lmc) + P.rep_r / l);
+            fac /= lr;
+            fac *= exp(l / lmc);
+            axpy3(gr, fac, dv);
+        });
+        axpy3(g, 2.0 * P.kappa_r, gr);
+    }
+
+    double* o = grad + 3 * (size_t)i;
+    o[0] = g.x; o[1] = g.y; o[2] = g.z;
+}
+
+DevParams to_dev(const tm_energy_params& p) {
+    DevParams P;
+    P.kappa_b = p.kappa_b; P.kappa_a = p.kappa_a; P.kappa_v = p.kappa_v;
+    P.kappa_c = p.kappa_c; P.kappa_t = p.kappa_t; P.kappa_r = p.kappa_r;
+    P.ref_area = p.ref_area; P.ref_volume = p.ref_volume; P.ref_curvature = p.ref_curvature;
+    P.lc0 = p.bond_lc0; P.lc1 = p.bond_lc1; P.a0 = p.bond_a0;
+    P.bond_r = p.bond_r; P.bond_type = p.bond_type;
+    P.rep_lc1 = p.rep_lc1; P.rep_r = p.rep_r;
+    return P;
+}
+
+}  // namespace
+
+int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
+    if (tm_ensure_rings(m)) return 1;
+    int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
+    TM_CHECK(nb <= TM_MAX_PARTIAL_BLOCKS, "mesh too large for the reduction workspace (%d vertices)", m->V);
+    DevParams P = to_dev(p);
+    MeshView mv = m->view();
+    if (write_vprops) {
+        if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
+        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, m->vprops,
+                                                                    m->partials, m->ticket, m->sums);
+    } else if (full) {
+        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, nullptr,
+                                                                     m->partials, m->ticket, m->sums);
+    } else {
+        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, nullptr,
+                                                                      m->partials, m->ticket, m->sums);
+    }
+    TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
+    if (tm_ensure_rings(m)) return 1;
+    int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
+    DevParams P = to_dev(p);
+    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), nl, P, m->rho, m->sums, m->grad);
+    TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,148 @@
+// Setup-time reductions and single half-edge primitives.
+//
+// Replaces, in the reference:
+//   area / edges_length                         src/util.cpp:9-35
+//   edge_length, face_area, face_volume, dihedral_angle and their gradients
+//                                               src/mesh_util.h:15-185
+// (the primitives are exposed to Python one half-edge at a time by
+// src/bindings.cpp:249-407 and pinned by tests/test_properties.py).
+#include "tm_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sm[NT / 32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < NT / 32 ? sm[lane] : 0.0;
+        for (int o = NT / 64; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    __syncthreads();
+    return t;
+}
+
+// per-block partials of (sum of face areas, sum of edge lengths); grid-stride so the
+// partial count is fixed and the final pass is a fixed-order sum
+__global__ void k_area_edges_partial(MeshView mv, double* __restrict__ part) {
+    double a = 0.0, l = 0.0;
+    for (int h = blockIdx.x * NT + threadIdx.x; h < mv.HE; h += gridDim.x * NT) {
+        int to = mv.he_to[h], from = mv.he_to[h ^ 1];
+        d3 x0 = ldpos(mv.x3, from), x1 = ldpos(mv.x3, to);
+        if ((h & 1) == 0) { d3 e = x1 - x0; l += sqrt(dot3(e, e)); }
+        if (mv.he_face[h] >= 0) {
+            d3 x2 = ldpos(mv.x3, mv.he_to[mv.he_next[h]]);
+            d3 n = cross3(x2 - x1, x0 - x1);
+            a += 0.5 * sqrt(dot3(n, n)) / 3.0;      // every face is visited by its 3 half-edges
+        }
+    }
+    a = block_sum(a);
+    l = block_sum(l);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = l; }
+}
+
+__global__ void k_area_edges_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    double a = 0.0, l = 0.0;
+    for (int b = threadIdx.x; b < nb; b += NT) { a += part[2 * b]; l += part[2 * b + 1]; }
+    a = block_sum(a);
+    l = block_sum(l);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = l; }
+}
+
+__device__ __forceinline__ void st3(double* o, d3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+
+// half-edge h: i -> j, apex k = to(next h); opposite half-edge j -> i with apex m
+__global__ void k_halfedge_geometry(MeshView mv, int h, double* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int o = h ^ 1;
+    const int i = mv.he_to[o], j = mv.he_to[h];
+    const int k = mv.he_to[mv.he_next[h]], m = mv.he_to[mv.he_next[o]];
+    const d3 xi = ldpos(mv.x3, i), xj = ldpos(mv.x3, j), xk = ldpos(mv.x3, k), xm = ldpos(mv.x3, m);
+    const bool boundary = mv.he_face[h] < 0 || mv.he_face[o] < 0;
+
+    // edge (mesh_util.h:30-56)
+    const d3 e = xj - xi;
+    const double l = sqrt(dot3(e, e));
+    const d3 eh = (1.0 / l) * e;
+    out[0] = l;
+    st3(out + 4, -1.0 * eh);
+    st3(out + 7, eh);
+
+    // face (i,j,k): sector normal of h (mesh_util.h:58-92)
+    const d3 n0 = cross3(xk - xj, xi - xj);
+    const double nn0 = dot3(n0, n0), ln0 = sqrt(nn0);
+    const d3 u0 = (1.0 / ln0) * n0;
+    out[1] = 0.5 * ln0;
+    st3(out + 10, 0.5 * cross3(u0, xk - xj));
+    st3(out + 13, 0.5 * cross3(u0, xi - xk));
+    st3(out + 16, 0.5 * cross3(u0, xj - xi));
+
+    // volume (mesh_util.h:94-128)
+    out[2] = dot3(cross3(xj, xk), xi) / 6.0;
+    st3(out + 19, (1.0 / 6.0) * cross3(xj, xk));
+    st3(out + 22, (1.0 / 6.0) * cross3(xk, xi));
+    st3(out + 25, (1.0 / 6.0) * cross3(xi, xj));
+
+    // dihedral angle and its gradient (mesh_util.h:130-185): cot of a sector angle is
+    // dot / |cross|, and |cross| is the face's un-normalised normal length
+    const d3 n1 = cross3(xm - xi, xj - xi);
+    const double nn1 = dot3(n1, n1), ln1 = sqrt(nn1);
+    const d3 u1 = (1.0 / ln1) * n1;
+    double theta = 0.0;
+    if (!boundary && ln0 * ln1 != 0.0)
+        theta = atan2(dot3(cross3(n0, n1), e) / l, dot3(n0, n1));
+    out[3] = theta;
+    const double cot01 = dot3(xj - xi, xk - xi) / ln0;   // angle at i in face (i,j,k)
+    const double cot03 = dot3(xk - xj, xi - xj) / ln0;   // angle at j in face (i,j,k)
+    const double cot02 = dot3(xm - xi, xj - xi) / ln1;   // angle at i in face (j,i,m)
+    const double cot04 = dot3(xi - xj, xm - xj) / ln1;   // angle at j in face (j,i,m)
+    const double il = 1.0 / l;
+    st3(out + 28, il * (cot03 * u0 + cot04 * u1));
+    st3(out + 31, il * (cot01 * u0 + cot02 * u1));
+    st3(out + 34, (-(cot01 + cot03) * il) * u0);
+    st3(out + 37, (-(cot02 + cot04) * il) * u1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tm_area_edges(tm_mesh* m, double* area, double* edges_length) {
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CUDA(cudaSetDevice(m->device));
+    const int nb = 296;
+    double *part = nullptr, *out = nullptr;
+    TM_CUDA(cudaMalloc(&part, sizeof(double) * 2 * nb));
+    TM_CUDA(cudaMalloc(&out, sizeof(double) * 2));
+    k_area_edges_partial<<<nb, NT, 0, m->stream>>>(m->view(), part); TM_LAUNCHED();
+    k_area_edges_final<<<1, NT, 0, m->stream>>>(part, nb, out); TM_LAUNCHED();
+    double h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    cudaFree(part); cudaFree(out);
+    TM_CHECK(e == cudaSuccess, "tm_area_edges failed: %s", cudaGetErrorString(e));
+    if (area) *area = h[0];
+    if (edges_length) *edges_length = h[1];
+    return 0;
+}
+
+int tm_halfedge_geometry(tm_mesh* m, int halfedge, double out[40]) {
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(halfedge >= 0 && halfedge < m->HE, "half-edge index %d out of range", halfedge);
+    TM_CUDA(cudaSetDevice(m->device));
+    double* d = nullptr;
+    TM_CUDA(cudaMalloc(&d, sizeof(double) * 40));
+    k_halfedge_geometry<<<1, 32, 0, m->stream>>>(m->view(), halfedge, d); TM_LAUNCHED();
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * 40, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    cudaFree(d);
+    TM_CHECK(e == cudaSuccess, "tm_halfedge_geometry failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // extern "C"
