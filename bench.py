@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the force-evaluation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one E+G evaluation = one EnergyManager.energy() + one .gradient() on the
+headline workload (BASELINE.json configs[2]): jittered icosphere, subdiv 8 (655,362
+vertices), tether + stress surface repulsion over a verlet list, exclusion level 2.
+
+  value    device-resident E+G evals/s (positions already in HBM, CUDA events on the
+           library's stream, L2 flushed before every timed step), whole job (all ranks)
+  e2e      the same through trimem_b200.core with host buffers: per step
+           np.copyto(mesh.points(), x) ; estore.energy(mesh) ; estore.gradient(mesh)
+  roofline dominant kernel (gather gradient sweep): algorithmic bytes / event time
+  cpu_baseline / --impl reference: the reference's own OpenMP C++ path (oracle/_ref)
+           on the host cores, same mesh and parameters.
+Multi-GPU (N>1): independent replicas, one per rank, no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLUSH_BYTES = 512 << 20          # > 126 MB L2
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_reference():
+    """The reference's trimem.core compiled from its own sources (oracle/_ref), or None."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    try:
+        import trimem.core as ref
+        return ref
+    except ImportError:
+        return None
+
+
+def time_reference(subdiv, steps, warmup, threads=None):
+    """E+G evals/s of the reference's OpenMP path on the host cores (same mesh, same parameters)."""
+    from trimem_b200 import workload
+    threads = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    ref = load_reference()
+    if ref is not None:
+        kind = "reference"
+        t0 = time.time()
+        mesh, estore, x = workload.make_case(ref, subdiv, repulsion="stress", n_search="verlet-list")
+        setup = time.time() - t0
+        def step():
+            np.copyto(mesh.points(), x)
+            e = estore.energy(mesh)
+            g = estore.gradient(mesh)
+            return e, g
+    else:
+        kind = "port"
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_port
+        case = oracle_port.make_case(subdiv, repulsion="stress", n_search="verlet-list", threads=threads)
+        setup = case.setup_seconds
+        step = case.energy_and_gradient
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    for _ in range(steps):
+        e, g = step()
+    dt = time.time() - t0
+    return {"value": steps / dt, "ms_per_step": 1e3 * dt / steps, "kind": kind, "cores": threads,
+            "setup_s": setup, "energy": float(e), "grad_norm": float(np.linalg.norm(g))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 = 655,362 vertices, the headline)")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="E+G evaluations of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    from trimem_b200 import workload
+    V = workload.N_VERTICES.get(args.subdiv, None)
+    wl = f"icosphere subdiv={args.subdiv} ({V} vertices) E+G: energy()+gradient(), tether + stress repulsion, verlet-list excl 2"
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        # bounded: one E+G takes ~1.4 s on 8 cores at 655k vertices; cap the run at ~3 minutes
+        probe_budget = 150.0
+        r = time_reference(args.subdiv, 1, min(args.warmup, 1))
+        steps = max(1, min(steps, int(probe_budget / max(r["ms_per_step"] / 1e3, 1e-3))))
+        if steps > 1:
+            r = time_reference(args.subdiv, steps, 0)
+        line = {"impl": "reference", "metric": "energy+gradient evals/s", "value": r["value"], "unit": "evals/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl, "n_vertices": V, "timing": "host wall clock, working set (~70 MB) exceeds CPU caches"},
+                "cpu_baseline": {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
+                                 "sample": f"{steps} E+G evaluations of the same {V}-vertex workload, OMP_NUM_THREADS={r['cores']}"},
+                "e2e": {"value": r["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "mvertex_evals_per_s": r["value"] * V / 1e6}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    import trimem_b200.core as core
+    from trimem_b200 import cabi
+    if core.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    core.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the public-API objects (e2e path) ...
+    t0 = time.time()
+    mesh, estore, x0 = workload.make_case(core, args.subdiv, repulsion="stress", n_search="verlet-list")
+    setup_s = time.time() - t0
+    V = mesh.n_vertices()
+    # ... and a C-ABI mirror of the same mesh for the device-resident loop
+    he_to, he_next, he_face, v_he, _ = mesh.halfedge_arrays()
+    cm = cabi.Mesh(he_to, he_next, he_face, v_he, xyz=x0, device=local)
+    rp = estore.eparams.repulse_params
+    t0 = time.time()
+    nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    cm.sync()
+    rebuild_first_ms = 1e3 * (time.time() - t0)
+    n_entries = nl.info()[0]
+    P = n_entries / V
+    p = workload.abi_params(estore)
+
+    def eg_device():
+        cm.energy_async(nl, p)
+        cm.gradient_async(nl, p)
+
+    for _ in range(max(args.warmup, 3)):
+        eg_device()
+    cm.sync()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = cabi.lib().tm_launch_count()
+    barrier()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        cm.flush_l2(FLUSH_BYTES)          # evict L2 (outside the timed span)
+        cm.timer_start()
+        eg_device()
+        total_ms += cm.timer_stop()
+    barrier()
+    launches = cabi.lib().tm_launch_count() - launches0
+    clocks = sampler.stop()
+
+    # dominant kernel: gather gradient sweep, timed alone, L2 flushed before every launch
+    k_ms = [cm.time_kernel(nl, p, w, max(10, min(args.steps, 50)), FLUSH_BYTES) for w in (0, 1, 2)]
+    # verlet-list rebuild (update_repulsion), device resident
+    reb = []
+    for _ in range(3):
+        cm.sync(); t0 = time.time()
+        nl2 = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level); cm.sync()
+        reb.append(1e3 * (time.time() - t0)); nl2.close()
+
+    # ---- e2e through the public API with host buffers (H2D of positions, D2H of the gradient)
+    xs = [x0 + 1e-6 * np.random.default_rng(s).normal(size=x0.shape) for s in range(2)]
+    def eg_api(k):
+        np.copyto(mesh.points(), xs[k % 2])
+        e = estore.energy(mesh)
+        g = estore.gradient(mesh)
+        return e, g
+    for k in range(3):
+        eg_api(k)
+    e2e_steps = max(5, min(args.steps, 30))
+    barrier()
+    t0 = time.time()
+    for k in range(e2e_steps):
+        e_last, g_last = eg_api(k)
+    barrier()
+    e2e_s = time.time() - t0
+
+    # parity spot check of the timed configuration against itself through both boundaries
+    e_dev, _ = cm.energy(nl, p)
+
+    # max over ranks
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = time_reference(args.subdiv, args.cpu_steps, 1)
+        cpu = {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{args.cpu_steps} E+G evaluations (after 1 warm-up) of the same {V}-vertex workload on the host, "
+                         f"OMP_NUM_THREADS={r['cores']}; reference E={r['energy']:.12e} |g|={r['grad_norm']:.12e}",
+               "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        ms_step = total_ms / args.steps
+        value = world * args.steps / (total_ms / 1e3)
+        alg_grad = workload.bytes_grad_sweep(P, True) * V          # bytes per launch of the gradient sweep
+        achieved = alg_grad / (k_ms[2] * 1e-3) / 1e9
+        alg_eg = workload.bytes_eg(P, True) * V
+        line = {
+            "metric": "energy+gradient evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "n_vertices": V, "verlet_entries": int(n_entries), "entries_per_vertex": P,
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": f"flushed before every timed step ({FLUSH_BYTES >> 20} MiB memset, outside the timed span)"},
+            "clocks": clocks,
+            "e2e": {"value": world * e2e_steps / e2e_s, "unit": "evals/s",
+                    "h2d_bytes_per_step": 2 * V * 24, "d2h_bytes_per_step": V * 24 + 2 * 48,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_grad (gather gradient sweep incl. repulsion)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_grad, "ms_per_launch": k_ms[2],
+                         "eg_algorithmic_bytes": alg_eg, "eg_frac_of_peak": alg_eg / (ms_step * 1e-3) / 1e9 / peak,
+                         "kernel_ms": {"props_full": k_ms[0], "props_for_gradient": k_ms[1], "grad": k_ms[2]}},
+            "cpu_baseline": cpu,
+            "mvertex_evals_per_s": value * V / 1e6,
+            "verlet_rebuild_ms": float(np.median(reb)),
+            "setup_s": setup_s,
+            "check": {"energy_device": e_dev, "energy_api_last": float(e_last), "grad_norm_api_last": float(np.linalg.norm(g_last))},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -288,6 +288,31 @@ int tm_timer_stop(tm_mesh* m, float* ms) {
     return 0;
 }
 
+int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int which, int iters,
+                   unsigned long long flush_bytes, float* ms_avg) {
+    if (check_mesh(m) || check_params(p)) return 1;
+    TM_CHECK(iters > 0 && ms_avg, "bad arguments");
+    TM_CHECK(which >= 0 && which <= 2, "which must be 0 (full property sweep), 1 (gradient's property sweep) or 2 (gradient sweep)");
+    // the gradient sweep consumes rho and the reduced sums of a property sweep
+    if (tm_launch_props(m, view_of(nl), *p, false, false)) return 1;
+    double total = 0.0;
+    for (int it = 0; it < iters; it++) {
+        if (flush_bytes && tm_flush_l2(m, flush_bytes)) return 1;
+        TM_CUDA(cudaEventRecord(m->ev0, m->stream));
+        int rc = which == 0 ? tm_launch_props(m, view_of(nl), *p, true, false)
+               : which == 1 ? tm_launch_props(m, view_of(nl), *p, false, false)
+                            : tm_launch_grad(m, view_of(nl), *p);
+        if (rc) return 1;
+        TM_CUDA(cudaEventRecord(m->ev1, m->stream));
+        TM_CUDA(cudaEventSynchronize(m->ev1));
+        float ms = 0.f;
+        TM_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        total += ms;
+    }
+    *ms_avg = (float)(total / iters);
+    return 0;
+}
+
 int tm_flush_l2(tm_mesh* m, unsigned long long bytes) {
     if (check_mesh(m)) return 1;
     if (m->flush_bytes < bytes) {
