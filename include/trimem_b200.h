@@ -153,12 +153,14 @@ enum { TM_FLIP_SERIAL = 0, TM_FLIP_BATCH = 1 };
  * TM_FLIP_SERIAL evaluates proposals strictly in order (flip_serial);
  * TM_FLIP_BATCH processes them in conflict-free rounds (flip_parallel_batches),
  * Metropolis on the device in proposal order inside a round.
- * flipped[k] receives the edge id of the k-th accepted flip in application order
- * (capacity n_proposals) so the host half-edge mirror can replay them;
- * props_io: reduced properties before (in) / after (out) the sweep.             */
+ * flipped[0..*n_flips) receives, in application order, the edge id of EVERY flip applied to
+ * the connectivity: each trial flip and, for a rejected trial, the flip back (the reference
+ * also flips back, flips.cpp:72,157, which does not restore half-edge orientation). Replaying
+ * that list on the host half-edge mirror keeps it identical to the device. Capacity must be
+ * 2 * n_proposals. props_io: reduced properties before (in) / after (out) the sweep.          */
 int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
                   int n_proposals, const int* edges, const double* u,
-                  int* n_accepted, int* flipped, double props_io[6]);
+                  int* n_accepted, int* n_flips, int* flipped, double props_io[6]);
 /* edge_vertex_properties (flip_utils.cpp:19-41) of one edge on the device mesh  */
 int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p,
                               int edge, double out[6]);

@@ -1,0 +1,94 @@
+"""Parity cases shared by tests/golden/make_golden.py (which records the reference's
+answers) and the tests (which compare the oracle port and the CUDA path with them)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from trimem_b200 import meshgen, workload  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+K1 = (1.0, 1.0, 1.0, 1.0, 1.0, 0.0)
+K1R = (1.0, 1.0, 1.0, 1.0, 1.0, 1.0)
+
+# name -> (mesh generator, args, workload.energy_params kwargs)
+CASES = {
+    # reference tests/test_gradient.py configuration, both bond types
+    "ico3_edge": ("icosphere", (3,), dict(kappa=K1, fracs=(0.8, 0.8, 0.8), bond="Edge", n_search="cell-list")),
+    "ico3_area": ("icosphere", (3,), dict(kappa=K1, fracs=(0.8, 0.8, 0.8), bond="Area", n_search="cell-list")),
+    # BASELINE config 1: subdiv 4, no repulsion
+    "ico4_config1": ("jittered_icosphere", (4,), dict(repulsion="none", n_search="cell-list")),
+    # stress repulsion, every list type x exclusion level
+    "ico4_stress_cell0": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="cell-list", exclusion=0)),
+    "ico4_stress_cell1": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="cell-list", exclusion=1)),
+    "ico4_stress_cell2": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="cell-list", exclusion=2)),
+    "ico4_stress_verlet0": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="verlet-list", exclusion=0)),
+    "ico4_stress_verlet1": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="verlet-list", exclusion=1)),
+    "ico4_stress_verlet2": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="verlet-list", exclusion=2)),
+    "ico4_physical_cell2": ("jittered_icosphere", (4,), dict(repulsion="physical", n_search="cell-list", exclusion=2)),
+    "ico4_area_stress": ("jittered_icosphere", (4,), dict(repulsion="stress", n_search="verlet-list", bond="Area")),
+    # BASELINE config 2 (40,962 vertices) and config 3 (655,362 vertices, headline)
+    "ico6_stress_cell2": ("jittered_icosphere", (6,), dict(repulsion="stress", n_search="cell-list", exclusion=2)),
+    "ico6_stress_verlet2": ("jittered_icosphere", (6,), dict(repulsion="stress", n_search="verlet-list", exclusion=2)),
+    "ico8_stress_verlet2": ("jittered_icosphere", (8,), dict(repulsion="stress", n_search="verlet-list", exclusion=2)),
+    "ico8_norep": ("jittered_icosphere", (8,), dict(repulsion="none", n_search="verlet-list", exclusion=2)),
+}
+FULL_GRADIENT_MAX_V = 3000      # cases up to this size store the whole gradient
+N_SAMPLED_ROWS = 512
+
+
+def mesh_of(case):
+    gen, args, _ = CASES[case]
+    return getattr(meshgen, gen)(*args)
+
+
+def build(mod, case):
+    """(mesh, estore) of `case` on module `mod` (reference build or trimem_b200.core)."""
+    v, f = mesh_of(case)
+    mesh = mod.TriMesh(v, f)
+    ep = workload.energy_params(mod, mesh, **CASES[case][2])
+    return mesh, mod.EnergyManager(mesh, ep)
+
+
+def sample_rows(n_vertices):
+    rng = np.random.default_rng(7)
+    return np.sort(rng.choice(n_vertices, size=min(N_SAMPLED_ROWS, n_vertices), replace=False))
+
+
+def props6(p):
+    return np.array([p.area, p.volume, p.curvature, p.bending, p.tethering, p.repulsion])
+
+
+def load_golden(name):
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    if not os.path.exists(path):
+        return None
+    return dict(np.load(path, allow_pickle=False))
+
+
+# flip sweeps with injected randomness: name -> (case, n_proposals, seed)
+FLIP_CASES = {
+    "flip_ico3_k1": ("ico3_flip", 960, 1),
+    "flip_ico4_cell": ("ico4_flip_cell", 768, 2),
+    "flip_ico4_verlet": ("ico4_flip_verlet", 768, 3),
+}
+CASES.update({
+    # reference tests/test_flips.py configuration
+    "ico3_flip": ("icosphere", (3,), dict(kappa=K1, fracs=(1.0, 1.0, 1.0), n_search="cell-list")),
+    "ico4_flip_cell": ("jittered_icosphere", (4,), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="stress",
+                                                        n_search="cell-list", exclusion=2)),
+    "ico4_flip_verlet": ("jittered_icosphere", (4,), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="stress",
+                                                          n_search="verlet-list", exclusion=2)),
+})
+
+
+def flip_inputs(name):
+    case, n, seed = FLIP_CASES[name]
+    v, f = mesh_of(case)
+    n_edges = 3 * len(v) - 6
+    rng = np.random.default_rng(seed)
+    return case, rng.integers(0, n_edges, n).astype(np.int32), rng.random(n)

@@ -1,0 +1,204 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures from the REFERENCE (oracle/_ref = the unmodified reference
+sources compiled against oracle/omshim; `make -C oracle ref`). Runs only in the build
+container (needs /root/reference to have been compiled); the .npz files it writes are
+committed so that the GPU box, where the reference does not exist, can check against them.
+
+    OMP_NUM_THREADS=1 python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import trimem.core as ref          # noqa: E402
+import refprobe                    # noqa: E402
+import cases                       # noqa: E402
+from trimem_b200 import meshgen    # noqa: E402
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    print("wrote", name, {k: np.shape(v) for k, v in arrays.items()})
+
+
+def energy_cases():
+    for name in cases.CASES:
+        if name.endswith(("_flip", "_flip_cell", "_flip_verlet")):
+            continue
+        mesh, es = cases.build(ref, name)
+        V = mesh.n_vertices()
+        props = cases.props6(es.properties(mesh))
+        energy = es.energy(mesh)
+        grad = es.gradient(mesh)
+        out = dict(n_vertices=V, props=props, energy=energy, grad_norm=np.linalg.norm(grad),
+                   grad_sum=grad.sum(axis=0), initial_props=cases.props6(es.initial_props))
+        if V <= cases.FULL_GRADIENT_MAX_V:
+            out["grad"] = grad
+            out["vprops"] = refprobe.vertex_properties(mesh, es)
+        else:
+            rows = cases.sample_rows(V)
+            out["rows"] = rows
+            out["grad_rows"] = grad[rows]
+        # neighbour-list content of the case
+        nl = ref.make_nlist(mesh, es.eparams)
+        rl = es.eparams.repulse_params.rlist
+        d, i, j = nl.distance_matrix(mesh, rl)
+        i, j = np.asarray(i, np.int64), np.asarray(j, np.int64)
+        lo, hi = np.minimum(i, j), np.maximum(i, j)
+        key = np.unique(lo * V + hi)
+        out["n_pairs_undirected"] = len(key)
+        out["pair_key_sum"] = np.array([int(key.sum() % (2 ** 61 - 1))], dtype=np.int64)
+        if V <= cases.FULL_GRADIENT_MAX_V:
+            out["pair_keys"] = key
+        save(name, **out)
+
+
+def neighbour_cases():
+    # reference tests/test_neighbours.py: rect(20,20)
+    v, f = meshgen.rect(20, 20)
+    mesh = ref.TriMesh(v, f)
+    out = {}
+    for lt in ("cell-list", "verlet-list"):
+        tag = lt.split("-")[0]
+        for rl in (0.2, 0.5, 1.2):
+            p = ref.EnergyParams()
+            p.repulse_params.n_search, p.repulse_params.rlist, p.repulse_params.exclusion_level = lt, rl, 0
+            d, i, j = ref.make_nlist(mesh, p).distance_matrix(mesh, 0.123)
+            order = np.lexsort((j, i))
+            out[f"{tag}_dm_{rl}_d"] = np.asarray(d)[order]
+            out[f"{tag}_dm_{rl}_i"] = np.asarray(i, np.int32)[order]
+            out[f"{tag}_dm_{rl}_j"] = np.asarray(j, np.int32)[order]
+        for ex in (0, 1, 2):
+            p = ref.EnergyParams()
+            p.repulse_params.n_search, p.repulse_params.rlist, p.repulse_params.exclusion_level = lt, 0.2, ex
+            _, jd = ref.make_nlist(mesh, p).point_distances(mesh, 151, 0.2)
+            out[f"{tag}_pd151_excl{ex}"] = np.sort(np.asarray(jd, np.int32))
+    save("neighbours_rect20", **out)
+
+
+def topology_cases():
+    out = {}
+    for name, (v, f) in {"ico3": meshgen.icosphere(3), "rect20": meshgen.rect(20, 20),
+                         "tube32": meshgen.tube(1.0, 1.0, 32), "ico4": meshgen.icosphere(4)}.items():
+        mesh = ref.TriMesh(v, f)
+        for k, a in zip(("he_to", "he_next", "he_face", "v_he", "f_he"), refprobe.halfedge_arrays(mesh)):
+            out[f"{name}_{k}"] = a
+        out[f"{name}_fv"] = mesh.fv_indices()
+    # after a fixed sequence of flips
+    v, f = meshgen.icosphere(3)
+    mesh = ref.TriMesh(v, f)
+    rng = np.random.default_rng(0)
+    edges = rng.integers(0, mesh.n_edges(), 2000).astype(np.int32)
+    ok = np.zeros(len(edges), np.int32)
+    for k, e in enumerate(edges):
+        ok[k] = refprobe.is_flip_ok(mesh, int(e))
+        if ok[k]:
+            refprobe.flip(mesh, int(e))
+    out["flipseq_edges"], out["flipseq_ok"] = edges, ok
+    for k, a in zip(("he_to", "he_next", "he_face", "v_he", "f_he"), refprobe.halfedge_arrays(mesh)):
+        out[f"flipseq_{k}"] = a
+    out["flipseq_fv"] = mesh.fv_indices()
+    save("topology", **out)
+
+
+def analytic_cases():
+    # reference tests/test_energy.py: sphere r=1,0.5 (icosphere(5)), tube n=32 r=1,0.5
+    out = {}
+    for tag, r in (("r1", 1.0), ("r05", 0.5)):
+        v, f = meshgen.icosphere(5)
+        mesh = ref.TriMesh(v * r, f)
+        out[f"sphere_{tag}"] = cases.props6(ref.EnergyManager(mesh, ref.EnergyParams()).properties(mesh))
+        v, f = meshgen.tube(1.0, r, 32)
+        mesh = ref.TriMesh(v, f)
+        out[f"tube_{tag}"] = cases.props6(ref.EnergyManager(mesh, ref.EnergyParams()).properties(mesh))
+    # docs example (doc/python-module.rst:60-98)
+    v, f = meshgen.icosphere(3, project_each_round=False)
+    v = v.astype(np.float32).astype(np.float64)
+    mesh = ref.TriMesh(v, f)
+    ep = ref.EnergyParams()
+    ep.kappa_b, ep.kappa_a, ep.kappa_v, ep.kappa_c, ep.kappa_t, ep.kappa_r = 30.0, 1e6, 1e6, 1e6, 1e5, 1e3
+    ep.area_frac = 0.5
+    es = ref.EnergyManager(mesh, ep)
+    out["docs_energy"] = es.energy(mesh)
+    out["docs_grad"] = es.gradient(mesh)
+    out["docs_props"] = cases.props6(es.properties(mesh))
+    save("analytic", **out)
+
+
+def primitive_cases():
+    # reference tests/test_properties.py: two triangles hinged at +-45 degrees
+    out = {}
+    for tag, alpha in (("p45", np.pi / 4), ("m45", -np.pi / 4)):
+        x, z = np.cos(alpha) * 0.5, np.sin(alpha) * 0.5
+        pts = np.array([[0.0, -0.5, 0.0], [0.0, 0.5, 0.0], [-x, 0.0, z], [x, 0.0, z]])
+        cells = np.array([[0, 1, 2], [1, 0, 3]])
+        mesh = ref.TriMesh(pts, cells)
+        e = mesh.halfedge_handle(0)
+        out[f"{tag}_scalars"] = np.array([ref.edge_length(mesh, e), ref.face_area(mesh, e),
+                                          ref.face_volume(mesh, e), ref.dihedral_angle(mesh, e)])
+        out[f"{tag}_d_length"] = ref.edge_length_grad(mesh, e)
+        out[f"{tag}_d_area"] = ref.face_area_grad(mesh, e)
+        out[f"{tag}_d_volume"] = ref.face_volume_grad(mesh, e)
+        out[f"{tag}_d_angle"] = ref.dihedral_angle_grad(mesh, e)
+    # every half-edge of a jittered icosphere(2): scalars + all gradients via the same calls
+    v, f = meshgen.jittered_icosphere(2, sigma_rel=0.1, seed=3)
+    mesh = ref.TriMesh(v, f)
+    nh = 2 * mesh.n_edges()
+    geo = np.zeros((nh, 40))
+    for h in range(nh):
+        e = mesh.halfedge_handle(h)
+        geo[h, 0:4] = [ref.edge_length(mesh, e), ref.face_area(mesh, e), ref.face_volume(mesh, e), ref.dihedral_angle(mesh, e)]
+        geo[h, 4:10] = ref.edge_length_grad(mesh, e).ravel()
+        geo[h, 10:19] = ref.face_area_grad(mesh, e).ravel()
+        geo[h, 19:28] = ref.face_volume_grad(mesh, e).ravel()
+        geo[h, 28:40] = ref.dihedral_angle_grad(mesh, e).ravel()
+    out["ico2_geometry"] = geo
+    save("primitives", **out)
+
+
+def flip_cases():
+    for name in cases.FLIP_CASES:
+        case, edges, u = cases.flip_inputs(name)
+        mesh, es = cases.build(ref, case)
+        # per-proposal edge_vertex_properties before the sweep (on the initial mesh)
+        evp = np.array([refprobe.edge_vertex_properties(mesh, es, int(e)) for e in edges[:64]])
+        flags, ener, props = refprobe.flip_sweep(mesh, es, edges, u)
+        out = dict(edges=edges, u=u, flags=flags, energies=ener, props_after=props, evp_first64=evp,
+                   fv_after=mesh.fv_indices())
+        for k, a in zip(("he_to", "he_next", "he_face", "v_he", "f_he"), refprobe.halfedge_arrays(mesh)):
+            out[f"after_{k}"] = a
+        save(name, **out)
+
+
+def thread_spread():
+    """The reference's own 1-vs-N-thread spread on the headline case (its noise floor)."""
+    import subprocess
+    code = ("import sys,os;sys.path.insert(0,%r);sys.path.insert(0,%r);sys.path.insert(0,%r);"
+            "import trimem.core as ref,cases,numpy as np;m,e=cases.build(ref,'ico8_stress_verlet2');"
+            "print(repr(e.energy(m)),repr(float(np.linalg.norm(e.gradient(m)))))"
+            % (os.path.join(ROOT, "oracle", "_ref"), ROOT, os.path.join(ROOT, "tests")))
+    res = {}
+    for thr in (1, 8):
+        env = dict(os.environ, OMP_NUM_THREADS=str(thr))
+        o = subprocess.check_output([sys.executable, "-c", code], env=env, text=True).split()
+        res[thr] = (float(o[0]), float(o[1]))
+    save("thread_spread", energy=np.array([res[1][0], res[8][0]]), grad_norm=np.array([res[1][1], res[8][1]]))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread"]
+    if "topology" in which: topology_cases()
+    if "analytic" in which: analytic_cases()
+    if "primitives" in which: primitive_cases()
+    if "neighbours" in which: neighbour_cases()
+    if "flips" in which: flip_cases()
+    if "energy" in which: energy_cases()
+    if "spread" in which: thread_spread()

@@ -88,7 +88,7 @@ def lib():
     L.tm_time_kernel.argtypes = [vp, vp, pp, C.c_int, C.c_int, C.c_ulonglong, C.POINTER(C.c_float)]
     L.tm_area_edges.argtypes = [vp, _dp, _dp]
     L.tm_halfedge_geometry.argtypes = [vp, C.c_int, _dp]
-    L.tm_flip_sweep.argtypes = [vp, vp, pp, C.c_int, C.c_int, _ip, _dp, _ip, _ip, _dp]
+    L.tm_flip_sweep.argtypes = [vp, vp, pp, C.c_int, C.c_int, _ip, _dp, _ip, _ip, _ip, _dp]
     L.tm_edge_vertex_properties.argtypes = [vp, vp, pp, C.c_int, _dp]
     L.tm_mesh_is_flip_ok.argtypes = [vp, C.c_int, _ip]
     L.tm_mesh_flip.argtypes = [vp, C.c_int]
@@ -220,12 +220,12 @@ class Mesh:
         edges = np.ascontiguousarray(edges, dtype=np.int32)
         u = np.ascontiguousarray(u, dtype=np.float64)
         n = len(edges)
-        nacc = C.c_int()
-        flipped = np.empty(max(n, 1), np.int32)
+        nacc, nfl = C.c_int(), C.c_int()
+        flipped = np.empty(max(2 * n, 1), np.int32)
         props = np.array(props, dtype=np.float64)
         _chk(lib().tm_flip_sweep(self.h, nl.h if nl else None, C.byref(p), mode, n, _i(edges), _d(u),
-                                 C.byref(nacc), _i(flipped), _d(props)))
-        return flipped[:nacc.value].copy(), props
+                                 C.byref(nacc), C.byref(nfl), _i(flipped), _d(props)))
+        return nacc.value, flipped[:nfl.value].copy(), props
 
     def edge_vertex_properties(self, nl, p, edge):
         out = np.empty(6)

@@ -196,13 +196,13 @@ int flip_sweep(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, lon
     tm_mesh* dm = mesh.device();
     double props[6];
     if (tm_properties(dm, estore.nlist_handle(), &p, props)) fail();
-    std::vector<int> flipped(nflips);
-    int nacc = 0;
+    std::vector<int> flipped(2 * (size_t)nflips);
+    int nacc = 0, napplied = 0;
     if (tm_flip_sweep(dm, estore.nlist_handle(), &p, mode, nflips, edges.data(), u.data(), &nacc,
-                      flipped.data(), props))
+                      &napplied, flipped.data(), props))
         fail();
-    // replay the accepted flips on the host mirror, in application order
-    for (int k = 0; k < nacc; k++) mesh.flip(flipped[k]);
+    // replay every applied flip (trial flips and flip-backs) on the host mirror, in order
+    for (int k = 0; k < napplied; k++) mesh.flip(flipped[k]);
     mesh.mark_device_in_sync();
     return nacc;
 }

@@ -22,45 +22,9 @@
 // pass, so results are bit-reproducible run to run.
 #include "tm_common.cuh"
 #include "tm_neigh.cuh"
+#include "tm_vertex.cuh"
 
 namespace {
-
-struct DevParams {
-    double kappa_b, kappa_a, kappa_v, kappa_c, kappa_t, kappa_r;
-    double ref_area, ref_volume, ref_curvature;
-    double lc0, lc1, a0;
-    int bond_r, bond_type;
-    double rep_lc1;
-    int rep_r;
-};
-
-__device__ __forceinline__ double powi(double x, int r) {
-    if (r == 2) return x * x;
-    int a = r < 0 ? -r : r;
-    double acc = 1.0, b = x;
-    while (a) { if (a & 1) acc *= b; b *= b; a >>= 1; }
-    return r < 0 ? 1.0 / acc : acc;
-}
-
-// FlatBottomEdgePenalty::vertex_property (mesh_tether.h:40-54)
-__device__ __forceinline__ double tether_edge(double l, const DevParams& P) {
-    if (l > P.lc0) return powi((double)P.bond_r, P.bond_r + 1) * powi(l - P.lc0, P.bond_r);
-    if (l < P.lc1) return exp(l / (l - P.lc1)) / powi(l, P.bond_r);
-    return 0.0;
-}
-// slope factor of FlatBottomEdgePenalty::vertex_property_grad (mesh_tether.h:62-76)
-__device__ __forceinline__ double tether_edge_fac(double l, const DevParams& P) {
-    double fac = 0.0;
-    if (l > P.lc0) fac = powi((double)P.bond_r, P.bond_r + 2) * powi(l - P.lc0, P.bond_r - 1);
-    if (l < P.lc1) {
-        double lr = powi(l, P.bond_r);
-        double lmc = l - P.lc1;
-        fac -= P.lc1 / (lmc * lmc) + P.bond_r / l;
-        fac /= lr;
-        fac *= exp(l / lmc);
-    }
-    return fac;
-}
 
 // ---- reductions ---------------------------------------------------------------
 template <int NT, int NQ>
@@ -98,56 +62,15 @@ k_props(MeshView mv, NlView nl, DevParams P, double* __restrict__ rho_out,
     int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
     double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
     if (i < mv.V) {
-        d3 xi = ldpos(mv.x3, i);
-        int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
-        double area = 0, vol = 0, curv = 0, teth = 0;
-        if (d > 0) {
-            const int* ring = mv.ring_v + beg;
-            d3 e_prev = ldpos(mv.x3, __ldg(ring + d - 1) & TM_RING_MASK) - xi;
-            int r_cur = __ldg(ring);
-            d3 e_cur = ldpos(mv.x3, r_cur & TM_RING_MASK) - xi;
-            d3 n_cur = cross3(e_cur, e_prev);
-            for (int s = 0; s < d; s++) {
-                int sn = s + 1 == d ? 0 : s + 1;
-                int r_next = __ldg(ring + sn);
-                d3 e_next = ldpos(mv.x3, r_next & TM_RING_MASK) - xi;
-                d3 n_next = cross3(e_next, e_cur);
-                if (r_cur & TM_RING_FACE) {           // `not he.is_boundary()`
-                    double l = sqrt(dot3(e_cur, e_cur));
-                    double a_f = 0.5 * sqrt(dot3(n_cur, n_cur));
-                    area += a_f;
-                    vol += dot3(xi, n_cur);           // = (x_j x x_k) . x_i
-                    if (r_cur & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
-                        double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
-                        curv = fma(l, th, curv);
-                    }
-                    if (FULL) {
-                        if (P.bond_type == TM_BOND_EDGE) teth += tether_edge(l, P);
-                        else { double q = a_f / P.a0 - 1.0; teth += q * q; }
-                    }
-                }
-                e_prev = e_cur; e_cur = e_next; n_cur = n_next; r_cur = r_next;
-            }
-        }
-        area = area / 3.0;
-        vol = vol / 18.0;                              // /6 per face, /3 multiplicity
-        curv = curv / 4.0;                             // 0.5 l theta per half-edge, /2 multiplicity
-        double bend = 2.0 * curv * curv / area;
-        double rep = 0.0;
-        if (FULL) {
-            teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
-            if (nl.kind >= 0 && P.rep_lc1 > 0.0) {
-                for_each_neighbour(mv, nl, i, xi, P.rep_lc1, [&](int, d3, double l) {
-                    rep += exp(l / (l - P.rep_lc1)) / powi(l, P.rep_r);
-                });
-            }
-        }
-        if (rho_out) rho_out[i] = curv / area;
+        const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
+        const int* ring = mv.ring_v + beg;
+        vertex_props<FULL, false>(mv, nl, P, i, d, [ring](int s) { return __ldg(ring + s); }, acc);
+        if (rho_out) rho_out[i] = acc[2] / acc[0];
         if (WRITE_VPROPS) {
             double* o = vprops + 6 * (size_t)i;
-            o[0] = area; o[1] = vol; o[2] = curv; o[3] = bend; o[4] = teth; o[5] = rep;
+#pragma unroll
+            for (int q = 0; q < 6; q++) o[q] = acc[q];
         }
-        acc[0] = area; acc[1] = vol; acc[2] = curv; acc[3] = bend; acc[4] = teth; acc[5] = rep;
     }
 
     // block partials -> last block sums all partials in a fixed order
@@ -289,24 +212,13 @@ k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
     o[0] = g.x; o[1] = g.y; o[2] = g.z;
 }
 
-DevParams to_dev(const tm_energy_params& p) {
-    DevParams P;
-    P.kappa_b = p.kappa_b; P.kappa_a = p.kappa_a; P.kappa_v = p.kappa_v;
-    P.kappa_c = p.kappa_c; P.kappa_t = p.kappa_t; P.kappa_r = p.kappa_r;
-    P.ref_area = p.ref_area; P.ref_volume = p.ref_volume; P.ref_curvature = p.ref_curvature;
-    P.lc0 = p.bond_lc0; P.lc1 = p.bond_lc1; P.a0 = p.bond_a0;
-    P.bond_r = p.bond_r; P.bond_type = p.bond_type;
-    P.rep_lc1 = p.rep_lc1; P.rep_r = p.rep_r;
-    return P;
-}
-
 }  // namespace
 
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
     if (tm_ensure_rings(m)) return 1;
     int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
     TM_CHECK(nb <= TM_MAX_PARTIAL_BLOCKS, "mesh too large for the reduction workspace (%d vertices)", m->V);
-    DevParams P = to_dev(p);
+    DevParams P = tm_to_dev(p);
     MeshView mv = m->view();
     if (write_vprops) {
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
@@ -327,7 +239,7 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     if (tm_ensure_rings(m)) return 1;
     int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
-    DevParams P = to_dev(p);
+    DevParams P = tm_to_dev(p);
     k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), nl, P, m->rho, m->sums, m->grad);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());

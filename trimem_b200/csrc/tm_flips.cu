@@ -1,13 +1,476 @@
-// Edge flips on the device connectivity (placeholder until the flip kernels land).
-#include "tm_common.cuh"
+// Edge-flip sweeps on the device connectivity.
+//
+// Replaces, in the reference:
+//   flip_serial / flip_parallel_batches      src/flips.cpp:22-165
+//   edge_vertex_properties, flip_patch,
+//   test_patch (+ OmpGuard try-locks)        src/flip_utils.cpp:19-114, src/omp_guard.cpp
+//   TriConnectivity::is_flip_ok / flip       OpenMesh
+//
+// TM_FLIP_SERIAL: one persistent warp walks the proposals strictly in order (same
+// arithmetic and the same order of updates as flip_serial); lanes 0-3 evaluate the
+// four vertex patches of a proposal concurrently.
+//
+// TM_FLIP_BATCH: rounds of conflict-free proposals. Every remaining proposal claims
+// the edges of its patch (star + link edges of its 4 vertices = flip_patch) with
+// atomicMin(owner[edge], proposal index); a proposal that owns its whole patch is
+// selected -- the index is a random priority because proposals are drawn at random,
+// and conflicting proposals are therefore always processed in proposal order, like
+// the reference's lock-or-skip rounds but without dropping proposals. Selected
+// proposals evaluate their patch before/after in parallel (4 threads each), the
+// flips are applied in parallel (patches are disjoint), and the Metropolis test
+// runs on the device as an ordered scan over the round, because acceptance depends
+// on the global energy through the non-linear penalties (the reference's
+// `omp critical`, flips.cpp:142-160). Rejected flips are flipped back.
+#include <climits>
 
-int tm_flips_release(tm_mesh* m) { (void)m; return 0; }
+#include "tm_common.cuh"
+#include "tm_neigh.cuh"
+#include "tm_vertex.cuh"
+
+namespace {
+
+constexpr int MAXV = 64;          // largest valence the flip kernels handle
+constexpr int NT = 128;
+
+struct Topo {                      // mutable connectivity
+    int* he_to;
+    int* he_next;
+    int* he_face;
+    int* v_he;
+};
+
+struct FlipWS {
+    int cap = 0, E = 0;
+    int *edges = nullptr, *owner = nullptr, *rem_a = nullptr, *rem_b = nullptr, *sel = nullptr;
+    int *flips = nullptr, *counters = nullptr;   // counters: [0] n_rem_next [1] n_flips [2] n_acc [3] err
+    double *u = nullptr, *before = nullptr, *after = nullptr, *state = nullptr;   // state: props[6], e0
+};
+
+// ---- connectivity primitives (volatile: other threads mutate these arrays) ---------
+__device__ __forceinline__ int vld(const int* p) { return *(const volatile int*)p; }
+
+__device__ bool d_is_flip_ok(const Topo& t, int e) {
+    const int hh = 2 * e, oh = hh + 1;
+    if (vld(t.he_face + hh) < 0 || vld(t.he_face + oh) < 0) return false;
+    const int ah = vld(t.he_to + vld(t.he_next + hh));
+    const int bh = vld(t.he_to + vld(t.he_next + oh));
+    if (ah == bh) return false;
+    const int h0 = vld(t.v_he + ah);
+    if (h0 >= 0) {
+        int h = h0, guard = 0;
+        do {
+            if (vld(t.he_to + h) == bh) return false;
+            h = vld(t.he_next + (h ^ 1));
+        } while (h != h0 && ++guard < 4096);
+    }
+    return true;
+}
+
+__device__ void d_flip(const Topo& t, int e) {
+    const int a0 = 2 * e, b0 = a0 + 1;
+    const int a1 = vld(t.he_next + a0), a2 = vld(t.he_next + a1);
+    const int b1 = vld(t.he_next + b0), b2 = vld(t.he_next + b1);
+    const int va0 = vld(t.he_to + a0), va1 = vld(t.he_to + a1);
+    const int vb0 = vld(t.he_to + b0), vb1 = vld(t.he_to + b1);
+    const int fa = vld(t.he_face + a0), fb = vld(t.he_face + b0);
+    t.he_to[a0] = va1;
+    t.he_to[b0] = vb1;
+    t.he_next[a0] = a2; t.he_next[a2] = b1; t.he_next[b1] = a0;
+    t.he_next[b0] = b2; t.he_next[b2] = a1; t.he_next[a1] = b0;
+    t.he_face[a1] = fb;
+    t.he_face[b1] = fa;
+    if (vld(t.v_he + va0) == b0) t.v_he[va0] = a1;
+    if (vld(t.v_he + vb0) == a0) t.v_he[vb0] = b1;
+}
+
+// the 4 vertices of edge_vertex_properties, in its order (flip_utils.cpp:27-38)
+__device__ __forceinline__ int patch_vertex(const Topo& t, int e, int q) {
+    const int heh = 2 * e + (q >> 1);
+    return (q & 1) ? vld(t.he_to + vld(t.he_next + heh)) : vld(t.he_to + heh);
+}
+
+// clockwise one-ring of v from the live half-edge arrays; returns the valence or -1
+__device__ int collect_ring(const Topo& t, int v, int* rw) {
+    const int h0 = vld(t.v_he + v);
+    if (h0 < 0) return 0;
+    int h = h0, d = 0;
+    do {
+        if (d >= MAXV) return -1;
+        int w = vld(t.he_to + h);
+        if (vld(t.he_face + h) >= 0) w |= TM_RING_FACE;
+        if (vld(t.he_face + (h ^ 1)) >= 0) w |= TM_RING_OFACE;
+        rw[d++] = w;
+        h = vld(t.he_next + (h ^ 1));
+    } while (h != h0);
+    return d;
+}
+
+__device__ bool live_vertex_props(const MeshView& mv, const Topo& t, const NlView& nl, const DevParams& P,
+                                  int v, double out[6]) {
+    int rw[MAXV];
+    const int d = collect_ring(t, v, rw);
+    if (d < 0) return false;
+    vertex_props<true, true>(mv, nl, P, v, d, [&rw](int s) { return rw[s]; }, out);
+    return true;
+}
+
+// ---- TM_FLIP_SERIAL ------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_flip_serial(MeshView mv, Topo t, NlView nl, DevParams P, int n, const int* __restrict__ edges,
+              const double* __restrict__ u, double* __restrict__ state, int* __restrict__ flips,
+              int* __restrict__ counters) {
+    const int lane = threadIdx.x;
+    double props[6];
+    for (int q = 0; q < 6; q++) props[q] = state[q];
+    double e0 = energy_of(P, props);
+    int nflips = 0, nacc = 0, err = 0;
+
+    for (int p = 0; p < n; p++) {
+        const int e = edges[p];
+        int ok = 0;
+        if (lane == 0) ok = d_is_flip_ok(t, e) ? 1 : 0;     // also false on boundary edges
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+
+        double vp[6] = {0, 0, 0, 0, 0, 0}, oprops[6], nprops[6];
+        if (lane < 4 && !live_vertex_props(mv, t, nl, P, patch_vertex(t, e, lane), vp)) err = 1;
+        for (int q = 0; q < 6; q++) {   // props{0} += vp(v0) += vp(v1) ... in the reference's order
+            double s = 0.0;
+            for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[q], l);
+            oprops[q] = s;
+        }
+        __syncwarp();
+        if (lane == 0) d_flip(t, e);
+        __syncwarp();
+        if (lane < 4 && !live_vertex_props(mv, t, nl, P, patch_vertex(t, e, lane), vp)) err = 1;
+        for (int q = 0; q < 6; q++) {
+            double s = 0.0;
+            for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[q], l);
+            nprops[q] = s;
+        }
+        // flips.cpp:49-76
+        for (int q = 0; q < 6; q++) { props[q] -= oprops[q]; props[q] += nprops[q]; }
+        const double en = energy_of(P, props);
+        const double de = en - e0;
+        const double alpha = de < 0.0 ? 1.0 : exp(-de);
+        const bool accept = u[p] <= alpha;
+        if (lane == 0) flips[nflips] = e;
+        ++nflips;
+        if (accept) {
+            e0 = en;
+            ++nacc;
+        } else {
+            __syncwarp();
+            if (lane == 0) { d_flip(t, e); flips[nflips] = e; }
+            ++nflips;
+            for (int q = 0; q < 6; q++) { props[q] -= nprops[q]; props[q] += oprops[q]; }
+            __syncwarp();
+        }
+    }
+    err = __any_sync(0xffffffffu, err);
+    if (lane == 0) {
+        for (int q = 0; q < 6; q++) state[q] = props[q];
+        state[6] = e0;
+        counters[1] = nflips; counters[2] = nacc; counters[3] = err;
+    }
+}
+
+// ---- TM_FLIP_BATCH ---------------------------------------------------------------------
+// visit every edge of flip_patch(e) (flip_utils.cpp:43-68)
+template <class F>
+__device__ __forceinline__ void for_each_patch_edge(const Topo& t, int e, F f) {
+    for (int q = 0; q < 4; q++) {
+        const int v = patch_vertex(t, e, q);
+        const int h0 = vld(t.v_he + v);
+        if (h0 < 0) continue;
+        int h = h0, guard = 0;
+        do {
+            f(h >> 1);
+            f(vld(t.he_next + h) >> 1);
+            h = vld(t.he_next + (h ^ 1));
+        } while (h != h0 && ++guard < 4096);
+    }
+}
+
+__global__ void k_batch_mark(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
+                             int* __restrict__ owner) {
+    const int r = blockIdx.x * NT + threadIdx.x;
+    if (r >= nrem) return;
+    const int p = rem[r];
+    for_each_patch_edge(t, edges[p], [&](int ed) { atomicMin(owner + ed, p); });
+}
+
+// sel[p]: 0 = not selected this round, 1 = selected and flippable, 2 = selected, not flippable
+__global__ void k_batch_select(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
+                               const int* __restrict__ owner, int* __restrict__ sel) {
+    const int r = blockIdx.x * NT + threadIdx.x;
+    if (r >= nrem) return;
+    const int p = rem[r];
+    const int e = edges[p];
+    bool mine = true;
+    for_each_patch_edge(t, e, [&](int ed) { if (owner[ed] != p) mine = false; });
+    sel[p] = !mine ? 0 : (d_is_flip_ok(t, e) ? 1 : 2);
+}
+
+// 4 threads per remaining proposal: patch properties on the current connectivity
+__global__ void k_batch_props(MeshView mv, Topo t, NlView nl, DevParams P, int nrem,
+                              const int* __restrict__ rem, const int* __restrict__ edges,
+                              const int* __restrict__ sel, double* __restrict__ out, int* __restrict__ counters) {
+    const int gid = blockIdx.x * NT + threadIdx.x;
+    const int r = gid >> 2, q = gid & 3;
+    const bool active = r < nrem && sel[rem[r]] == 1;
+    double vp[6] = {0, 0, 0, 0, 0, 0};
+    int p = 0;
+    if (active) {
+        p = rem[r];
+        if (!live_vertex_props(mv, t, nl, P, patch_vertex(t, edges[p], q), vp)) counters[3] = 1;
+    }
+    // sum the 4 vertices in the reference's order (all 4 lanes of a group take the same branch)
+    const unsigned base = (threadIdx.x & 31) & ~3u;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double s = 0.0;
+        for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[c], base + l);
+        if (active && q == 0) out[6 * (size_t)p + c] = s;
+    }
+}
+
+__global__ void k_batch_apply(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
+                              const int* __restrict__ sel, int want) {
+    const int r = blockIdx.x * NT + threadIdx.x;
+    if (r >= nrem) return;
+    const int p = rem[r];
+    if (sel[p] == want) d_flip(t, edges[p]);
+}
+
+// ordered Metropolis scan over the round (single thread: inherently sequential, ~50 flops per
+// proposal); also compacts the not-yet-processed proposals for the next round and appends
+// the applied / reverted flips to the replay list.
+__global__ void k_batch_metropolis(DevParams P, int nrem, const int* __restrict__ rem, int* __restrict__ rem_next,
+                                   const double* __restrict__ u, const int* __restrict__ edges,
+                                   int* __restrict__ sel, const double* __restrict__ before,
+                                   const double* __restrict__ after, double* __restrict__ state,
+                                   int* __restrict__ flips, int* __restrict__ counters) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double props[6];
+    for (int q = 0; q < 6; q++) props[q] = state[q];
+    double e0 = state[6];
+    int nflips = counters[1], nacc = counters[2], nnext = 0;
+    // replay list of this round: first every applied flip ...
+    for (int r = 0; r < nrem; r++) {
+        const int p = rem[r];
+        if (sel[p] == 1) flips[nflips++] = edges[p];
+    }
+    for (int r = 0; r < nrem; r++) {
+        const int p = rem[r];
+        const int s = sel[p];
+        if (s == 0) { rem_next[nnext++] = p; continue; }
+        if (s != 1) continue;
+        // flips.cpp:133-160: dprops = before - after; props -= dprops
+        double d[6];
+        for (int q = 0; q < 6; q++) { d[q] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q]; props[q] -= d[q]; }
+        const double en = energy_of(P, props);
+        const double de = en - e0;
+        const double alpha = de < 0.0 ? 1.0 : exp(-de);
+        if (u[p] <= alpha) {
+            e0 = en;
+            ++nacc;
+        } else {
+            for (int q = 0; q < 6; q++) props[q] += d[q];
+            sel[p] = 3;                      // rejected: flip back
+            flips[nflips++] = edges[p];      // ... then every reverted flip
+        }
+    }
+    for (int q = 0; q < 6; q++) state[q] = props[q];
+    state[6] = e0;
+    counters[0] = nnext; counters[1] = nflips; counters[2] = nacc;
+}
+
+__global__ void k_iota(int n, int* a) {
+    const int i = blockIdx.x * NT + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+__global__ void k_init_state(DevParams P, double* state) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) state[6] = energy_of(P, state);
+}
+
+__global__ void k_evp(MeshView mv, Topo t, NlView nl, DevParams P, int e, double* out, int* err) {
+    const int lane = threadIdx.x;
+    double vp[6] = {0, 0, 0, 0, 0, 0};
+    if (lane < 4 && !live_vertex_props(mv, t, nl, P, patch_vertex(t, e, lane), vp)) *err = 1;
+    for (int q = 0; q < 6; q++) {
+        double s = 0.0;
+        for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[q], l);
+        if (lane == 0) out[q] = s;
+    }
+}
+
+__global__ void k_flip_ok(Topo t, int e, int* out) {
+    if (threadIdx.x == 0) *out = d_is_flip_ok(t, e) ? 1 : 0;
+}
+__global__ void k_flip_one(Topo t, int e) {
+    if (threadIdx.x == 0) d_flip(t, e);
+}
+
+Topo topo_of(tm_mesh* m) { return Topo{m->he_to, m->he_next, m->he_face, m->v_he}; }
+
+int ensure_ws(tm_mesh* m, int n) {
+    FlipWS* ws = (FlipWS*)m->flipws;
+    if (!ws) { ws = new FlipWS(); m->flipws = ws; }
+    const int E = m->HE / 2;
+    if (ws->E != E) {
+        cudaFree(ws->owner); ws->owner = nullptr;
+        TM_CUDA(cudaMalloc(&ws->owner, sizeof(int) * (size_t)(E > 0 ? E : 1)));
+        ws->E = E;
+    }
+    if (ws->cap < n) {
+        cudaFree(ws->edges); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel); cudaFree(ws->flips);
+        cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after);
+        ws->cap = 0;
+        size_t c = (size_t)n;
+        TM_CUDA(cudaMalloc(&ws->edges, sizeof(int) * c));
+        TM_CUDA(cudaMalloc(&ws->rem_a, sizeof(int) * c));
+        TM_CUDA(cudaMalloc(&ws->rem_b, sizeof(int) * c));
+        TM_CUDA(cudaMalloc(&ws->sel, sizeof(int) * c));
+        TM_CUDA(cudaMalloc(&ws->flips, sizeof(int) * 2 * c));
+        TM_CUDA(cudaMalloc(&ws->u, sizeof(double) * c));
+        TM_CUDA(cudaMalloc(&ws->before, sizeof(double) * 6 * c));
+        TM_CUDA(cudaMalloc(&ws->after, sizeof(double) * 6 * c));
+        ws->cap = n;
+    }
+    if (!ws->counters) TM_CUDA(cudaMalloc(&ws->counters, sizeof(int) * 8));
+    if (!ws->state) TM_CUDA(cudaMalloc(&ws->state, sizeof(double) * 8));
+    return 0;
+}
+
+int check(tm_mesh* m, const tm_energy_params* p) {
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(p != nullptr, "null parameter block");
+    TM_CHECK(p->bond_type == TM_BOND_EDGE || p->bond_type == TM_BOND_AREA, "Unknown bond potential");
+    TM_CUDA(cudaSetDevice(m->device));
+    return 0;
+}
+
+}  // namespace
+
+int tm_flips_release(tm_mesh* m) {
+    FlipWS* ws = (FlipWS*)m->flipws;
+    if (!ws) return 0;
+    cudaFree(ws->edges); cudaFree(ws->owner); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel);
+    cudaFree(ws->flips); cudaFree(ws->counters); cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after);
+    cudaFree(ws->state);
+    delete ws;
+    m->flipws = nullptr;
+    return 0;
+}
 
 extern "C" {
-int tm_flip_sweep(tm_mesh*, tm_nlist*, const tm_energy_params*, int, int, const int*, const double*,
-                  int*, int*, double*) { tm_set_error("tm_flip_sweep: not implemented yet"); return 1; }
-int tm_edge_vertex_properties(tm_mesh*, tm_nlist*, const tm_energy_params*, int, double*) {
-    tm_set_error("tm_edge_vertex_properties: not implemented yet"); return 1; }
-int tm_mesh_is_flip_ok(tm_mesh*, int, int*) { tm_set_error("tm_mesh_is_flip_ok: not implemented yet"); return 1; }
-int tm_mesh_flip(tm_mesh*, int) { tm_set_error("tm_mesh_flip: not implemented yet"); return 1; }
+
+int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode, int n,
+                  const int* edges, const double* u, int* n_accepted, int* n_flips, int* flipped,
+                  double props_io[6]) {
+    if (check(m, p)) return 1;
+    TM_CHECK(mode == TM_FLIP_SERIAL || mode == TM_FLIP_BATCH, "unknown flip mode %d", mode);
+    TM_CHECK(n >= 0 && props_io && n_accepted, "bad arguments");
+    *n_accepted = 0;
+    if (n_flips) *n_flips = 0;
+    if (n == 0) return 0;
+    TM_CHECK(edges && u, "null proposal arrays");
+    const int E = m->HE / 2;
+    for (int k = 0; k < n; k++) TM_CHECK(edges[k] >= 0 && edges[k] < E, "proposal %d: edge %d out of range", k, edges[k]);
+    // cell lists evaluate exclusions on the live connectivity: keep the ring table usable for
+    // everything outside the sweep, and walk half-edges inside it
+    if (tm_ensure_rings(m) || ensure_ws(m, n)) return 1;
+    FlipWS* ws = (FlipWS*)m->flipws;
+    cudaStream_t st = m->stream;
+    const DevParams P = tm_to_dev(*p);
+    const NlView nv = nl ? nl->view() : tm_no_nlist();
+    const MeshView mv = m->view();
+    const Topo t = topo_of(m);
+
+    TM_CUDA(cudaMemcpyAsync(ws->edges, edges, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    TM_CUDA(cudaMemcpyAsync(ws->u, u, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TM_CUDA(cudaMemcpyAsync(ws->state, props_io, sizeof(double) * 6, cudaMemcpyHostToDevice, st));
+    TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, st));
+    int hc[4] = {0, 0, 0, 0};
+
+    if (mode == TM_FLIP_SERIAL) {
+        k_flip_serial<<<1, 32, 0, st>>>(mv, t, nv, P, n, ws->edges, ws->u, ws->state, ws->flips, ws->counters);
+        TM_LAUNCHED();
+    } else {
+        k_init_state<<<1, 32, 0, st>>>(P, ws->state); TM_LAUNCHED();
+        k_iota<<<(n + NT - 1) / NT, NT, 0, st>>>(n, ws->rem_a); TM_LAUNCHED();
+        int nrem = n;
+        int *rem = ws->rem_a, *rem_next = ws->rem_b;
+        while (nrem > 0) {
+            const int nb = (nrem + NT - 1) / NT, nb4 = (4 * nrem + NT - 1) / NT;
+            TM_CUDA(cudaMemsetAsync(ws->owner, 0x7f, sizeof(int) * (size_t)ws->E, st));
+            k_batch_mark<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner); TM_LAUNCHED();
+            k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel); TM_LAUNCHED();
+            k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->before, ws->counters); TM_LAUNCHED();
+            k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 1); TM_LAUNCHED();
+            k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->after, ws->counters); TM_LAUNCHED();
+            k_batch_metropolis<<<1, 32, 0, st>>>(P, nrem, rem, rem_next, ws->u, ws->edges, ws->sel, ws->before,
+                                                 ws->after, ws->state, ws->flips, ws->counters); TM_LAUNCHED();
+            k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 3); TM_LAUNCHED();
+            TM_CUDA(cudaMemcpyAsync(hc, ws->counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            TM_CUDA(cudaStreamSynchronize(st));
+            TM_CHECK(hc[0] < nrem, "flip sweep made no progress (%d proposals left)", nrem);
+            nrem = hc[0];
+            int* tmp = rem; rem = rem_next; rem_next = tmp;
+        }
+    }
+    TM_CUDA(cudaGetLastError());
+    TM_CUDA(cudaMemcpyAsync(hc, ws->counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    TM_CUDA(cudaMemcpyAsync(props_io, ws->state, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
+    TM_CUDA(cudaStreamSynchronize(st));
+    m->rings_valid = false;                 // connectivity changed: the ring table is rebuilt lazily
+    TM_CHECK(hc[3] == 0, "flip sweep met a vertex of valence > %d", MAXV);
+    if (flipped && hc[1] > 0)
+        TM_CUDA(cudaMemcpy(flipped, ws->flips, sizeof(int) * hc[1], cudaMemcpyDeviceToHost));
+    if (n_flips) *n_flips = hc[1];
+    *n_accepted = hc[2];
+    return 0;
 }
+
+int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int edge, double out[6]) {
+    if (check(m, p)) return 1;
+    TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
+    if (ensure_ws(m, 1)) return 1;
+    FlipWS* ws = (FlipWS*)m->flipws;
+    TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, m->stream));
+    k_evp<<<1, 32, 0, m->stream>>>(m->view(), topo_of(m), nl ? nl->view() : tm_no_nlist(), tm_to_dev(*p), edge,
+                                   ws->state, ws->counters + 3);
+    TM_LAUNCHED();
+    int err = 0;
+    TM_CUDA(cudaMemcpyAsync(out, ws->state, sizeof(double) * 6, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaMemcpyAsync(&err, ws->counters + 3, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    TM_CHECK(err == 0, "vertex of valence > %d", MAXV);
+    return 0;
+}
+
+int tm_mesh_is_flip_ok(tm_mesh* m, int edge, int* ok) {
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to && ok, "bad arguments");
+    TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
+    TM_CUDA(cudaSetDevice(m->device));
+    if (ensure_ws(m, 1)) return 1;
+    FlipWS* ws = (FlipWS*)m->flipws;
+    k_flip_ok<<<1, 32, 0, m->stream>>>(topo_of(m), edge, ws->counters + 4); TM_LAUNCHED();
+    TM_CUDA(cudaMemcpyAsync(ok, ws->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_mesh_flip(tm_mesh* m, int edge) {
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "bad arguments");
+    TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
+    TM_CUDA(cudaSetDevice(m->device));
+    k_flip_one<<<1, 32, 0, m->stream>>>(topo_of(m), edge); TM_LAUNCHED();
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    m->rings_valid = false;
+    return 0;
+}
+
+}  // extern "C"

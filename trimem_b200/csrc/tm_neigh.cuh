@@ -1,8 +1,10 @@
-// Neighbour-list traversal shared by the energy sweeps and the list queries.
+// Neighbour-list traversal shared by the energy sweeps, the list queries and the flips.
 #pragma once
 #include "tm_common.cuh"
 
-// Is j within `excl` rings of i on the live connectivity? (cell_list.h:167-201)
+// Is j within `excl` rings of i on the current connectivity? (cell_list.h:167-201)
+// CSR variant: reads the one-ring table (valid whenever the table is in sync with the
+// half-edge arrays, i.e. everywhere except inside a flip sweep).
 __device__ __forceinline__ bool excluded(const MeshView& mv, int i, int j, int excl) {
     if (excl <= 0) return false;
     int b = mv.ring_off[i], e = mv.ring_off[i + 1];
@@ -18,13 +20,38 @@ __device__ __forceinline__ bool excluded(const MeshView& mv, int i, int j, int e
     return false;
 }
 
+// Live variant: walks the half-edge arrays (h -> next(opposite(h))) exactly like the
+// reference's vv_range circulators; used while flips mutate the connectivity.
+__device__ __forceinline__ bool excluded_live(const MeshView& mv, int i, int j, int excl) {
+    if (excl <= 0) return false;
+    const int h0 = mv.v_he[i];
+    if (h0 < 0) return false;
+    int h = h0;
+    do {
+        const int v = mv.he_to[h];
+        if (v == j) return true;
+        if (excl > 1) {
+            const int g0 = mv.v_he[v];
+            if (g0 >= 0) {
+                int g = g0;
+                do {
+                    if (mv.he_to[g] == j) return true;
+                    g = mv.he_next[g ^ 1];
+                } while (g != g0);
+            }
+        }
+        h = mv.he_next[h ^ 1];
+    } while (h != h0);
+    return false;
+}
+
 // Calls f(j, d = x_i - x_j, l = |d|) for every neighbour-list candidate with l < dmax,
 // with the semantics of CellList/VerletList::point_distances (cell_list.h:131-219,
 // verlet_list.h:74-101): cell lists use build-time occupancy, the query vertex's live
 // position and live exclusions; verlet lists filter the frozen rows.
-template <class F>
-__device__ __forceinline__ void for_each_neighbour(const MeshView& mv, const NlView& nl, int i,
-                                                   d3 xi, double dmax, F f) {
+template <bool LIVE, class F>
+__device__ __forceinline__ void for_each_neighbour_t(const MeshView& mv, const NlView& nl, int i,
+                                                     d3 xi, double dmax, F f) {
     if (nl.kind == TM_NLIST_VERLET) {
         int b = nl.row_off[i], e = nl.row_off[i + 1];
         for (int k = b; k < e; k++) {
@@ -55,7 +82,10 @@ __device__ __forceinline__ void for_each_neighbour(const MeshView& mv, const NlV
                         d3 d = sub_nofma(xi, ldpos(mv.x3, j));
                         double l = dist_nofma(d);
                         // the reference tests the exclusion first; the selected set is the same
-                        if (l < dmax && !excluded(mv, i, j, nl.excl)) f(j, d, l);
+                        if (l < dmax) {
+                            bool ex = LIVE ? excluded_live(mv, i, j, nl.excl) : excluded(mv, i, j, nl.excl);
+                            if (!ex) f(j, d, l);
+                        }
                     }
                 }
             }
@@ -63,3 +93,8 @@ __device__ __forceinline__ void for_each_neighbour(const MeshView& mv, const NlV
     }
 }
 
+template <class F>
+__device__ __forceinline__ void for_each_neighbour(const MeshView& mv, const NlView& nl, int i,
+                                                   d3 xi, double dmax, F f) {
+    for_each_neighbour_t<false>(mv, nl, i, xi, dmax, f);
+}

@@ -1,0 +1,126 @@
+// Per-vertex property evaluation shared by the property sweep (tm_energy.cu) and the
+// flip kernels (tm_flips.cu), so that both produce bit-identical per-vertex values.
+//
+// Reference: vertex_properties (src/mesh_properties.cpp:12-49), tether potentials
+// (src/mesh_tether.h:29-121), surface repulsion (src/mesh_repulsion.h:28-54),
+// trimem_energy (src/kernel.h:110-122).
+#pragma once
+#include "tm_common.cuh"
+#include "tm_neigh.cuh"
+
+struct DevParams {
+    double kappa_b, kappa_a, kappa_v, kappa_c, kappa_t, kappa_r;
+    double ref_area, ref_volume, ref_curvature;
+    double lc0, lc1, a0;
+    int bond_r, bond_type;
+    double rep_lc1;
+    int rep_r;
+};
+
+inline DevParams tm_to_dev(const tm_energy_params& p) {
+    DevParams P;
+    P.kappa_b = p.kappa_b; P.kappa_a = p.kappa_a; P.kappa_v = p.kappa_v;
+    P.kappa_c = p.kappa_c; P.kappa_t = p.kappa_t; P.kappa_r = p.kappa_r;
+    P.ref_area = p.ref_area; P.ref_volume = p.ref_volume; P.ref_curvature = p.ref_curvature;
+    P.lc0 = p.bond_lc0; P.lc1 = p.bond_lc1; P.a0 = p.bond_a0;
+    P.bond_r = p.bond_r; P.bond_type = p.bond_type;
+    P.rep_lc1 = p.rep_lc1; P.rep_r = p.rep_r;
+    return P;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double powi(double x, int r) {
+    if (r == 2) return x * x;
+    int a = r < 0 ? -r : r;
+    double acc = 1.0, b = x;
+    while (a) { if (a & 1) acc *= b; b *= b; a >>= 1; }
+    return r < 0 ? 1.0 / acc : acc;
+}
+
+// FlatBottomEdgePenalty::vertex_property (mesh_tether.h:40-54)
+__device__ __forceinline__ double tether_edge(double l, const DevParams& P) {
+    if (l > P.lc0) return powi((double)P.bond_r, P.bond_r + 1) * powi(l - P.lc0, P.bond_r);
+    if (l < P.lc1) return exp(l / (l - P.lc1)) / powi(l, P.bond_r);
+    return 0.0;
+}
+// slope factor of FlatBottomEdgePenalty::vertex_property_grad (mesh_tether.h:62-76)
+__device__ __forceinline__ double tether_edge_fac(double l, const DevParams& P) {
+    double fac = 0.0;
+    if (l > P.lc0) fac = powi((double)P.bond_r, P.bond_r + 2) * powi(l - P.lc0, P.bond_r - 1);
+    if (l < P.lc1) {
+        double lr = powi(l, P.bond_r);
+        double lmc = l - P.lc1;
+        fac -= P.lc1 / (lmc * lmc) + P.bond_r / l;
+        fac /= lr;
+        fac *= exp(l / lmc);
+    }
+    return fac;
+}
+
+// trimem_energy (kernel.h:110-122)
+__device__ __forceinline__ double energy_of(const DevParams& P, const double* s) {
+    double e = 0.0, d;
+    d = s[0] / P.ref_area - 1.0;      e += P.kappa_a * d * d;
+    d = s[1] / P.ref_volume - 1.0;    e += P.kappa_v * d * d;
+    d = s[2] / P.ref_curvature - 1.0; e += P.kappa_c * d * d;
+    e += P.kappa_t * s[4];
+    e += P.kappa_r * s[5];
+    e += P.kappa_b * s[3];
+    return e;
+}
+
+// Six properties of vertex i whose clockwise one-ring is ring(0..d-1) (neighbour id |
+// TM_RING_FACE | TM_RING_OFACE). With e_s = x_{j_s} - x_i, n_s = e_s x e_{s-1}:
+//   A_f = |n_s|/2, V_f = x_i . n_s / 6, theta_s = atan2(-|e_s| (e_{s+1}.n_s), n_s.n_{s+1}).
+// FULL adds tether and repulsion; LIVE selects the exclusion walk used by cell lists.
+template <bool FULL, bool LIVE, class RingFn>
+__device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& nl, const DevParams& P,
+                                             int i, int d, RingFn ring, double out[6]) {
+    const d3 xi = ldpos(mv.x3, i);
+    double area = 0, vol = 0, curv = 0, teth = 0;
+    if (d > 0) {
+        d3 e_prev = ldpos(mv.x3, ring(d - 1) & TM_RING_MASK) - xi;
+        int r_cur = ring(0);
+        d3 e_cur = ldpos(mv.x3, r_cur & TM_RING_MASK) - xi;
+        d3 n_cur = cross3(e_cur, e_prev);
+        for (int s = 0; s < d; s++) {
+            const int sn = s + 1 == d ? 0 : s + 1;
+            const int r_next = ring(sn);
+            const d3 e_next = ldpos(mv.x3, r_next & TM_RING_MASK) - xi;
+            const d3 n_next = cross3(e_next, e_cur);
+            if (r_cur & TM_RING_FACE) {           // `not he.is_boundary()`
+                const double l = sqrt(dot3(e_cur, e_cur));
+                const double a_f = 0.5 * sqrt(dot3(n_cur, n_cur));
+                area += a_f;
+                vol += dot3(xi, n_cur);           // = (x_j x x_k) . x_i
+                if (r_cur & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
+                    const double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
+                    curv = fma(l, th, curv);
+                }
+                if (FULL) {
+                    if (P.bond_type == TM_BOND_EDGE) teth += tether_edge(l, P);
+                    else { const double q = a_f / P.a0 - 1.0; teth += q * q; }
+                }
+            }
+            e_prev = e_cur; e_cur = e_next; n_cur = n_next; r_cur = r_next;
+        }
+    }
+    area = area / 3.0;
+    vol = vol / 18.0;                              // /6 per face, /3 multiplicity
+    curv = curv / 4.0;                             // 0.5 l theta per half-edge, /2 multiplicity
+    double rep = 0.0;
+    if (FULL) {
+        teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
+        if (nl.kind >= 0 && P.rep_lc1 > 0.0) {
+            const double lc1 = P.rep_lc1;
+            const int rr = P.rep_r;
+            for_each_neighbour_t<LIVE>(mv, nl, i, xi, lc1, [&rep, lc1, rr](int, d3, double l) {
+                rep += exp(l / (l - lc1)) / powi(l, rr);
+            });
+        }
+    }
+    out[0] = area; out[1] = vol; out[2] = curv;
+    out[3] = 2.0 * curv * curv / area;
+    out[4] = teth; out[5] = rep;
+}
+#endif
