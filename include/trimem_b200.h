@@ -63,6 +63,14 @@ int tm_mesh_get_rings(tm_mesh* m, int* ring_off, int* ring_v, int* ring_flags);
  * Python mutates behind our back, so every evaluation re-uploads.              */
 int tm_mesh_set_positions(tm_mesh* m, const double* xyz);
 int tm_mesh_get_positions(tm_mesh* m, double* xyz);
+/* Extension (no reference counterpart): the device stores vertices sorted by the Morton code
+ * of a coarse grid cell so that warps work on compact surface patches; the order is built from
+ * the first positions a mesh receives. All ids at this boundary stay in the caller's numbering.
+ * tm_mesh_reorder recomputes the order from the current positions (neighbour lists built before
+ * the call are refused afterwards: rebuild them); tm_mesh_get_vertex_order returns, per device
+ * slot, the caller's vertex id stored there (V ints; diagnostics).                              */
+int tm_mesh_reorder(tm_mesh* m);
+int tm_mesh_get_vertex_order(tm_mesh* m, int* slot_to_vertex);
 int tm_mesh_n_vertices(const tm_mesh* m);
 int tm_mesh_n_halfedges(const tm_mesh* m);
 

@@ -64,6 +64,8 @@ def lib():
     L.tm_mesh_get_rings.argtypes = [vp, _ip, _ip, _ip]
     L.tm_mesh_set_positions.argtypes = [vp, _dp]
     L.tm_mesh_get_positions.argtypes = [vp, _dp]
+    L.tm_mesh_reorder.argtypes = [vp]
+    L.tm_mesh_get_vertex_order.argtypes = [vp, _ip]
     L.tm_mesh_n_vertices.argtypes = [vp]
     L.tm_mesh_n_halfedges.argtypes = [vp]
     L.tm_nlist_create.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.c_double, C.POINTER(vp)]
@@ -147,6 +149,14 @@ class Mesh:
         x = np.empty((self.V, 3))
         _chk(lib().tm_mesh_get_positions(self.h, _d(x)))
         return x
+
+    def reorder(self):
+        _chk(lib().tm_mesh_reorder(self.h))
+
+    def vertex_order(self):
+        o = np.empty(self.V, np.int32)
+        _chk(lib().tm_mesh_get_vertex_order(self.h, _i(o)))
+        return o
 
     def topology(self):
         a = [np.empty(self.HE, np.int32) for _ in range(3)] + [np.empty(self.V, np.int32)]

@@ -37,11 +37,13 @@ double energy_from_props(const tm_energy_params& p, const double s[6]) {
     return e;
 }
 
-int check_mesh(tm_mesh* m, bool need_pos = true) {
+// every compute entry: device selected, vertex order / device connectivity / staged positions
+// / one-ring table brought up to date (tm_layout.cu)
+int check_mesh(tm_mesh* m, bool need_layout = true) {
     TM_CHECK(m != nullptr, "null mesh handle");
-    TM_CHECK(m->V > 0 && m->he_to != nullptr, "mesh has no topology (call tm_mesh_set_topology first)");
-    (void)need_pos;
+    TM_CHECK(m->V > 0 && m->he_to_h != nullptr, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CUDA(cudaSetDevice(m->device));
+    if (need_layout && tm_ensure_layout(m)) return 1;
     return 0;
 }
 
@@ -129,7 +131,8 @@ int tm_mesh_destroy(tm_mesh* m) {
     tm_flips_release(m);
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
     cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt);
-    cudaFree(m->x3); cudaFree(m->rho); cudaFree(m->vprops); cudaFree(m->grad);
+    cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
+    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     cudaFreeHost(m->h_sums);
@@ -146,62 +149,87 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
     TM_CHECK(V < TM_RING_FACE, "too many vertices (%d)", V);
     TM_CUDA(cudaSetDevice(m->device));
     if (V != m->V) {
-        if (dev_alloc(&m->v_he, V) || dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) ||
-            dev_alloc(&m->x3, 3 * (size_t)V) || dev_alloc(&m->rho, V) || dev_alloc(&m->grad, 3 * (size_t)V))
+        if (dev_alloc(&m->v_he, V) || dev_alloc(&m->v_he_h, V) || dev_alloc(&m->d2h, V) || dev_alloc(&m->h2d, V) ||
+            dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) ||
+            dev_alloc(&m->pos, V) || dev_alloc(&m->xio3, 3 * (size_t)V) || dev_alloc(&m->xout3, 3 * (size_t)V) ||
+            dev_alloc(&m->grad, 3 * (size_t)V))
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
-        TM_CUDA(cudaMemsetAsync(m->x3, 0, sizeof(double) * 3 * (size_t)V, m->stream));
+        TM_CUDA(cudaMemsetAsync(m->pos, 0, sizeof(P4) * (size_t)V, m->stream));
+        m->perm_valid = false;          // a new vertex set: the order is rebuilt from its first positions
+        m->have_positions = false;
+        m->stage_pending = false;
     }
     if (HE != m->HE) {
-        if (dev_alloc(&m->he_to, HE) || dev_alloc(&m->he_next, HE) || dev_alloc(&m->he_face, HE) ||
-            dev_alloc(&m->ring_v, HE))
+        if (dev_alloc(&m->he_to, HE) || dev_alloc(&m->he_to_h, HE) || dev_alloc(&m->he_next, HE) ||
+            dev_alloc(&m->he_face, HE) || dev_alloc(&m->ring_v, HE))
             return 1;
     }
     m->V = V; m->HE = HE;
-    TM_CUDA(cudaMemcpyAsync(m->he_to, he_to, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
+    // he_next / he_face do not hold vertex ids; he_to / v_he are kept as uploaded (host numbering)
+    // and converted to the device numbering by tm_ensure_layout
+    TM_CUDA(cudaMemcpyAsync(m->he_to_h, he_to, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
     TM_CUDA(cudaMemcpyAsync(m->he_next, he_next, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
     TM_CUDA(cudaMemcpyAsync(m->he_face, he_face, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));
-    TM_CUDA(cudaMemcpyAsync(m->v_he, v_he, sizeof(int) * V, cudaMemcpyHostToDevice, m->stream));
+    TM_CUDA(cudaMemcpyAsync(m->v_he_h, v_he, sizeof(int) * V, cudaMemcpyHostToDevice, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
+    m->topo_dev_valid = false;
+    m->raw_stale = false;
     m->rings_valid = false;
-    return tm_ensure_rings(m);
+    m->pos_epoch++;
+    return 0;
 }
 
 int tm_mesh_get_topology(tm_mesh* m, int* he_to, int* he_next, int* he_face, int* v_he) {
-    if (check_mesh(m)) return 1;
-    if (he_to) TM_CUDA(cudaMemcpyAsync(he_to, m->he_to, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    if (check_mesh(m, false)) return 1;
+    if (tm_refresh_raw_topology(m)) return 1;      // flips mutate the device-numbered arrays
+    if (he_to) TM_CUDA(cudaMemcpyAsync(he_to, m->he_to_h, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
     if (he_next) TM_CUDA(cudaMemcpyAsync(he_next, m->he_next, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
     if (he_face) TM_CUDA(cudaMemcpyAsync(he_face, m->he_face, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
-    if (v_he) TM_CUDA(cudaMemcpyAsync(v_he, m->v_he, sizeof(int) * m->V, cudaMemcpyDeviceToHost, m->stream));
+    if (v_he) TM_CUDA(cudaMemcpyAsync(v_he, m->v_he_h, sizeof(int) * m->V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
 
 int tm_mesh_get_rings(tm_mesh* m, int* ring_off, int* ring_v, int* ring_flags) {
-    if (check_mesh(m) || tm_ensure_rings(m)) return 1;
-    std::vector<int> off(m->V + 1), rv(m->HE > 0 ? m->HE : 1);
-    TM_CUDA(cudaMemcpyAsync(off.data(), m->ring_off, sizeof(int) * (m->V + 1), cudaMemcpyDeviceToHost, m->stream));
+    if (check_mesh(m)) return 1;
+    const int V = m->V;
+    std::vector<int> off(V + 1), rv(m->HE > 0 ? m->HE : 1), d2h(V), h2d(V);
+    TM_CUDA(cudaMemcpyAsync(off.data(), m->ring_off, sizeof(int) * (V + 1), cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaMemcpyAsync(rv.data(), m->ring_v, sizeof(int) * m->HE, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaMemcpyAsync(d2h.data(), m->d2h, sizeof(int) * V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaMemcpyAsync(h2d.data(), m->h2d, sizeof(int) * V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
-    if (ring_off) memcpy(ring_off, off.data(), sizeof(int) * (m->V + 1));
-    int n = off[m->V];
-    for (int k = 0; k < n; k++) {
-        if (ring_v) ring_v[k] = rv[k] & TM_RING_MASK;
-        if (ring_flags) ring_flags[k] = ((rv[k] & TM_RING_FACE) ? 1 : 0) | ((rv[k] & TM_RING_OFACE) ? 2 : 0);
+    // rows in host vertex order, neighbour ids in host numbering, circulation order kept
+    int o = 0;
+    for (int hv = 0; hv < V; hv++) {
+        if (ring_off) ring_off[hv] = o;
+        const int d = h2d[hv];
+        for (int k = off[d]; k < off[d + 1]; k++, o++) {
+            if (ring_v) ring_v[o] = d2h[rv[k] & TM_RING_MASK];
+            if (ring_flags) ring_flags[o] = ((rv[k] & TM_RING_FACE) ? 1 : 0) | ((rv[k] & TM_RING_OFACE) ? 2 : 0);
+        }
     }
+    if (ring_off) ring_off[V] = o;
     return 0;
 }
 
 int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
-    if (check_mesh(m)) return 1;
+    if (check_mesh(m, false)) return 1;
     TM_CHECK(xyz != nullptr, "null positions");
-    TM_CUDA(cudaMemcpyAsync(m->x3, xyz, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
+    // staged in host numbering; scattered into the packed device records by the next compute
+    // entry on the same stream (tm_ensure_layout)
+    TM_CUDA(cudaMemcpyAsync(m->xio3, xyz, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
+    m->stage_pending = true;
+    m->have_positions = true;
     return 0;
 }
 
 int tm_mesh_get_positions(tm_mesh* m, double* xyz) {
     if (check_mesh(m)) return 1;
-    TM_CUDA(cudaMemcpyAsync(xyz, m->x3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CHECK(xyz != nullptr, "null positions");
+    if (tm_export_positions(m)) return 1;
+    TM_CUDA(cudaMemcpyAsync(xyz, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
@@ -211,20 +239,23 @@ int tm_mesh_n_halfedges(const tm_mesh* m) { return m ? m->HE : 0; }
 
 // ------------------------------------------------------- energy / gradient --
 int tm_energy_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
-    if (check_mesh(m) || check_params(p)) return 1;
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     return tm_launch_props(m, view_of(nl), *p, true, false);
 }
 
 int tm_gradient_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
-    if (check_mesh(m) || check_params(p)) return 1;
-    // property sweep without tether/repulsion (the gradient only needs A, V, C and rho),
-    // then the gather sweep; both on the mesh's stream, no host round trip in between.
-    if (tm_launch_props(m, view_of(nl), *p, false, false)) return 1;
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
+    // Sweep 1: area, volume, curvature sums and rho = c/a per vertex (all the gradient needs from
+    // the properties; no tether, no repulsion). They depend on positions and connectivity only,
+    // so a property sweep already evaluated for the current positions (energy() immediately
+    // before gradient(), the usual E+G pair) is reused. Sweep 2: the gather sweep. Both on the
+    // mesh's stream, no host round trip in between.
+    if (m->geo_epoch != m->pos_epoch && tm_launch_props(m, view_of(nl), *p, false, false)) return 1;
     return tm_launch_grad(m, view_of(nl), *p);
 }
 
 int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, double props[6]) {
-    if (check_mesh(m) || check_params(p)) return 1;
+    if (check_mesh(m, false) || check_params(p)) return 1;
     double s[6];
     if (fetch_sums(m, s)) return 1;
     if (props) for (int q = 0; q < 6; q++) props[q] = s[q];
@@ -235,13 +266,14 @@ int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, doubl
 int tm_fetch_gradient(tm_mesh* m, double* grad) {
     if (check_mesh(m)) return 1;
     TM_CHECK(grad != nullptr, "null gradient buffer");
-    TM_CUDA(cudaMemcpyAsync(grad, m->grad, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    if (tm_export_gradient(m)) return 1;           // device order -> host vertex numbering
+    TM_CUDA(cudaMemcpyAsync(grad, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
 
 int tm_sync(tm_mesh* m) {
-    if (check_mesh(m)) return 1;
+    if (check_mesh(m, false)) return 1;
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
@@ -252,10 +284,15 @@ int tm_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double ou
 }
 
 int tm_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* out) {
-    if (check_mesh(m) || check_params(p)) return 1;
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     if (tm_launch_props(m, view_of(nl), *p, true, true)) return 1;
-    TM_CUDA(cudaMemcpyAsync(out, m->vprops, sizeof(double) * 6 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    std::vector<double> tmp(6 * (size_t)m->V);
+    std::vector<int> d2h(m->V);
+    TM_CUDA(cudaMemcpyAsync(tmp.data(), m->vprops, sizeof(double) * 6 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaMemcpyAsync(d2h.data(), m->d2h, sizeof(int) * m->V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
+    for (int d = 0; d < m->V; d++)
+        for (int q = 0; q < 6; q++) out[6 * (size_t)d2h[d] + q] = tmp[6 * (size_t)d + q];
     return 0;
 }
 
@@ -275,13 +312,13 @@ int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* gra
 }
 
 int tm_timer_start(tm_mesh* m) {
-    if (check_mesh(m)) return 1;
+    if (check_mesh(m, false)) return 1;
     TM_CUDA(cudaEventRecord(m->ev0, m->stream));
     return 0;
 }
 
 int tm_timer_stop(tm_mesh* m, float* ms) {
-    if (check_mesh(m)) return 1;
+    if (check_mesh(m, false)) return 1;
     TM_CUDA(cudaEventRecord(m->ev1, m->stream));
     TM_CUDA(cudaEventSynchronize(m->ev1));
     TM_CUDA(cudaEventElapsedTime(ms, m->ev0, m->ev1));
@@ -290,7 +327,7 @@ int tm_timer_stop(tm_mesh* m, float* ms) {
 
 int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int which, int iters,
                    unsigned long long flush_bytes, float* ms_avg) {
-    if (check_mesh(m) || check_params(p)) return 1;
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     TM_CHECK(iters > 0 && ms_avg, "bad arguments");
     TM_CHECK(which >= 0 && which <= 2, "which must be 0 (full property sweep), 1 (gradient's property sweep) or 2 (gradient sweep)");
     // the gradient sweep consumes rho and the reduced sums of a property sweep
@@ -314,7 +351,7 @@ int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int whic
 }
 
 int tm_flush_l2(tm_mesh* m, unsigned long long bytes) {
-    if (check_mesh(m)) return 1;
+    if (check_mesh(m, false)) return 1;
     if (m->flush_bytes < bytes) {
         if (m->flush) cudaFree(m->flush);
         m->flush = nullptr;

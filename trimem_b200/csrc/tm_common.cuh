@@ -39,6 +39,16 @@ constexpr int TM_GRAD_THREADS  = 128;
 constexpr int TM_MAX_PARTIAL_BLOCKS = 1 << 17;  // 16.7M vertices at 128 threads
 
 // ------------------------------------------------------------ device views --
+// One 32-byte record per vertex = one DRAM/L2 sector: position plus rho = c/a (curvature /
+// area ratio of the last property sweep), so the gather sweeps fetch everything they need
+// about a ring neighbour with a single 256-bit load.
+struct __align__(32) P4 { double x, y, z, w; };
+
+// All device arrays use the DEVICE vertex numbering: vertices sorted by the Morton code of a
+// coarse grid cell (tm_layout.cu), so that the 32 vertices of a warp form a compact surface
+// patch and their ring / neighbour-list gathers hit the same few cache lines. d2h / h2d map
+// to and from the host (OpenMesh) numbering at the C-ABI boundary; half-edge, edge and face
+// ids are not renumbered.
 struct MeshView {
     int V, HE;
     const int* he_to;
@@ -47,7 +57,7 @@ struct MeshView {
     const int* v_he;
     const int* ring_off;   // V+1
     const int* ring_v;     // HE entries, flags in the two top bits
-    const double* x3;      // V*3 positions, row-major (host layout)
+    const P4* pos;         // V packed (x, y, z, rho) records, device vertex numbering
 };
 
 struct NlView {
@@ -74,10 +84,22 @@ struct tm_mesh {
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
     bool rings_valid = false;
-    double* x3 = nullptr;        // V*3
-    double* rho = nullptr;       // V   curvature/area ratio of the last props sweep
+    // host-numbered connectivity as uploaded (he_to_h, v_he_h) and the vertex permutation
+    int *he_to_h = nullptr, *v_he_h = nullptr;
+    int *d2h = nullptr, *h2d = nullptr;
+    bool perm_valid = false;       // d2h/h2d computed for the current vertex set
+    bool topo_dev_valid = false;   // he_to / v_he (device numbering) reflect he_to_h / v_he_h
+    bool raw_stale = false;        // device connectivity mutated by flips; he_to_h / v_he_h are old
+    bool stage_pending = false;    // xio3 holds uploaded positions not yet imported into pos
+    bool have_positions = false;
+    unsigned long long layout_epoch = 0;   // bumped whenever the permutation changes
+    unsigned long long pos_epoch = 1;      // bumped whenever positions or connectivity change
+    unsigned long long geo_epoch = 0;      // pos_epoch at which sums[0..2] and rho were evaluated
+    P4* pos = nullptr;           // V   (x, y, z, rho), device numbering
+    double* xio3 = nullptr;      // V*3 staging in HOST numbering: uploaded positions
+    double* xout3 = nullptr;     // V*3 staging in HOST numbering: results on their way out
     double* vprops = nullptr;    // V*6 (allocated on demand)
-    double* grad = nullptr;      // V*3
+    double* grad = nullptr;      // V*3 device numbering
     double* partials = nullptr;  // 6 * TM_MAX_PARTIAL_BLOCKS
     double* sums = nullptr;      // 8
     unsigned* ticket = nullptr;
@@ -92,7 +114,7 @@ struct tm_mesh {
         MeshView v;
         v.V = V; v.HE = HE;
         v.he_to = he_to; v.he_next = he_next; v.he_face = he_face; v.v_he = v_he;
-        v.ring_off = ring_off; v.ring_v = ring_v; v.x3 = x3;
+        v.ring_off = ring_off; v.ring_v = ring_v; v.pos = pos;
         return v;
     }
 };
@@ -109,6 +131,7 @@ struct tm_nlist {
     int *row_off = nullptr, *row_j = nullptr;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
     long long n_entries = 0;
+    unsigned long long layout_epoch = 0;   // vertex numbering the list was built in
     NlView view() const {
         NlView v;
         v.kind = kind; v.excl = excl;
@@ -130,6 +153,14 @@ inline NlView tm_no_nlist() {
 }
 
 // ------------------------------------------------- internal host interfaces --
+int tm_ensure_layout(tm_mesh* m);                                // tm_layout.cu: permutation, device-numbered
+                                                                 // connectivity, staged positions, rings
+int tm_refresh_raw_topology(tm_mesh* m);                         // tm_layout.cu
+int tm_export_positions(tm_mesh* m);                             // tm_layout.cu: pos -> xio3 (host numbering)
+int tm_export_gradient(tm_mesh* m);                              // tm_layout.cu: grad -> xio3 (host numbering)
+int tm_bbox(tm_mesh* m, const double* x, int stride, int V, double out[6]);   // tm_layout.cu: min xyz, max xyz
+int tm_sort_segments(tm_mesh* m, long long nseg, const int* start, int* items);   // tm_layout.cu
+int tm_check_nlist(const tm_mesh* m, const tm_nlist* nl);        // tm_layout.cu
 int tm_ensure_rings(tm_mesh* m);                                 // tm_rings.cu
 int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* total);  // tm_rings.cu
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
@@ -151,9 +182,39 @@ __device__ __forceinline__ d3 cross3(d3 a, d3 b) {
 __device__ __forceinline__ void axpy3(d3& acc, double s, d3 a) {
     acc.x = fma(s, a.x, acc.x); acc.y = fma(s, a.y, acc.y); acc.z = fma(s, a.z, acc.z);
 }
-__device__ __forceinline__ d3 ldpos(const double* __restrict__ x3, int i) {
-    const double* p = x3 + 3 * (size_t)i;
-    return mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+// position of vertex i. Coherent loads of the first 24 bytes only: the property sweep writes
+// rho (.w) of other vertices while it runs, so .w must not be touched (nor the record read
+// through the non-coherent path) there.
+__device__ __forceinline__ d3 ldpos(const P4* pos, int i) {
+    const double2 xy = *reinterpret_cast<const double2*>(pos + i);
+    const double z = pos[i].z;
+    return mk3(xy.x, xy.y, z);
+}
+// whole record through the read-only path (one LDG.E.256.CONSTANT): only in kernels that do
+// not write pos
+__device__ __forceinline__ P4 ldrec(const P4* __restrict__ pos, int i) {
+    P4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(pos + i));
+    return r;
+}
+// 1/x and 1/sqrt(x) for normal, positive x: MUFU seed + two Newton steps, branch-free (the
+// compiler's own sequences carry a slow-path call for denormals/inf that these arguments never take)
+__device__ __forceinline__ double rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);     // 0.5 (1 - x y^2)
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
 }
 // x^r for the small integer exponents of the potentials (std::pow(l, r_) in the reference)
 __device__ __forceinline__ double ipow(double x, int r) {

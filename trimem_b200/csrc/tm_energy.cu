@@ -56,7 +56,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NQ], double* out /* NQ,
 // sweep inside gradient() only needs area, volume, curvature and rho.
 template <bool FULL, bool WRITE_VPROPS>
 __global__ void __launch_bounds__(TM_PROPS_THREADS)
-k_props(MeshView mv, NlView nl, DevParams P, double* __restrict__ rho_out,
+k_props(MeshView mv, NlView nl, DevParams P, P4* pos_rw,
         double* __restrict__ vprops, double* __restrict__ partials,
         unsigned* __restrict__ ticket, double* __restrict__ sums) {
     int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
@@ -65,7 +65,7 @@ k_props(MeshView mv, NlView nl, DevParams P, double* __restrict__ rho_out,
         const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
         const int* ring = mv.ring_v + beg;
         vertex_props<FULL, false>(mv, nl, P, i, d, [ring](int s) { return __ldg(ring + s); }, acc);
-        if (rho_out) rho_out[i] = acc[2] / acc[0];
+        pos_rw[i].w = acc[2] / acc[0];        // rho_i = c_i / a_i rides in the position record
         if (WRITE_VPROPS) {
             double* o = vprops + 6 * (size_t)i;
 #pragma unroll
@@ -102,9 +102,10 @@ k_props(MeshView mv, NlView nl, DevParams P, double* __restrict__ rho_out,
 }
 
 // ---- K3 + K4: gather gradient ----------------------------------------------------
+// Reads only: every ring / list neighbour costs one 256-bit read-only load of its
+// (x, y, z, rho) record.
 __global__ void __launch_bounds__(TM_GRAD_THREADS)
-k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
-       const double* __restrict__ sums, double* __restrict__ grad) {
+k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ sums, double* __restrict__ grad) {
     int i = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
     if (i >= mv.V) return;
 
@@ -114,40 +115,41 @@ k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
     const double fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
     const double kb = P.kappa_b, kt = P.kappa_t;
 
-    d3 xi = ldpos(mv.x3, i);
+    const P4 ri = ldrec(mv.pos, i);
+    const d3 xi = mk3(ri.x, ri.y, ri.z);
     d3 g = mk3(0, 0, 0);
     int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
     if (d > 0) {
         const int* ring = mv.ring_v + beg;
-        const double rho_i = rho[i];
+        const double rho_i = ri.w;
         d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
         d3 esum = mk3(0, 0, 0);      // sum of (e_{s-1} - e_s) over faces (0 for closed fans)
 
         int r_prev = __ldg(ring + d - 1), r_cur = __ldg(ring);
-        int j_prev = r_prev & TM_RING_MASK, j_cur = r_cur & TM_RING_MASK;
-        d3 e_prev = ldpos(mv.x3, j_prev) - xi;
-        d3 e_cur = ldpos(mv.x3, j_cur) - xi;
-        double rho_prev = __ldg(rho + j_prev), rho_cur = __ldg(rho + j_cur);
+        const P4 q_prev = ldrec(mv.pos, r_prev & TM_RING_MASK), q_cur = ldrec(mv.pos, r_cur & TM_RING_MASK);
+        d3 e_prev = mk3(q_prev.x, q_prev.y, q_prev.z) - xi;
+        d3 e_cur = mk3(q_cur.x, q_cur.y, q_cur.z) - xi;
+        double rho_prev = q_prev.w, rho_cur = q_cur.w;
         double l2_prev = dot3(e_prev, e_prev), l2_cur = dot3(e_cur, e_cur);
         double p_cur = dot3(e_cur, e_prev);
         d3 n_cur = cross3(e_cur, e_prev);
         double nn_cur = dot3(n_cur, n_cur);
-        double in_cur = rsqrt(nn_cur);                // 1/|n_s|
+        double in_cur = rsqrt_pos(nn_cur);            // 1/|n_s|
 
         for (int s = 0; s < d; s++) {
             int sn = s + 1 == d ? 0 : s + 1;
             int r_next = __ldg(ring + sn);
-            int j_next = r_next & TM_RING_MASK;
-            d3 e_next = ldpos(mv.x3, j_next) - xi;
-            double rho_next = __ldg(rho + j_next);
+            const P4 q_next = ldrec(mv.pos, r_next & TM_RING_MASK);
+            d3 e_next = mk3(q_next.x, q_next.y, q_next.z) - xi;
+            double rho_next = q_next.w;
             double l2_next = dot3(e_next, e_next);
             double p_next = dot3(e_next, e_cur);
             d3 n_next = cross3(e_next, e_cur);
             double nn_next = dot3(n_next, n_next);
-            double in_next = rsqrt(nn_next);
+            double in_next = rsqrt_pos(nn_next);
 
             if (r_cur & TM_RING_FACE) {
-                const double il = rsqrt(l2_cur);       // 1/l_s
+                const double il = rsqrt_pos(l2_cur);   // 1/l_s
                 const double l = l2_cur * il;
                 const double inn_cur = in_cur * in_cur;
                 double cE = 0.0, cEp = 0.0, cN = 0.0, cNn = 0.0;
@@ -197,13 +199,12 @@ k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
     // repulsion (mesh_properties.cpp:139-146, mesh_repulsion.h:56-78)
     if (nl.kind >= 0 && P.rep_lc1 > 0.0 && P.kappa_r != 0.0) {
         d3 gr = mk3(0, 0, 0);
-        for_each_neighbour(mv, nl, i, xi, P.rep_lc1, [&](int, d3 dv, double l) {
-            double lr = powi(l, P.rep_r + 1);
-            double lmc = l - P.rep_lc1;
-            double fac = -(P.rep_lc1 / (lmc * lmc) + P.rep_r / l);
-            fac /= lr;
-            fac *= exp(l / lmc);
-            axpy3(gr, fac, dv);
+        const double lc1 = P.rep_lc1;
+        const int rr = P.rep_r;
+        for_each_pair_fast<false, true>(mv, nl, i, xi, lc1 * lc1, [&gr, lc1, rr](int, d3 dv, double l2) {
+            double sl;
+            repulsion_pair<true>(l2, lc1, rr, sl);
+            axpy3(gr, sl, dv);
         });
         axpy3(g, 2.0 * P.kappa_r, gr);
     }
@@ -215,32 +216,33 @@ k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ rho,
 }  // namespace
 
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
-    if (tm_ensure_rings(m)) return 1;
+    if (tm_ensure_layout(m)) return 1;
     int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
     TM_CHECK(nb <= TM_MAX_PARTIAL_BLOCKS, "mesh too large for the reduction workspace (%d vertices)", m->V);
     DevParams P = tm_to_dev(p);
     MeshView mv = m->view();
     if (write_vprops) {
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
-        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, m->vprops,
+        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, m->vprops,
                                                                     m->partials, m->ticket, m->sums);
     } else if (full) {
-        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, nullptr,
+        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, nullptr,
                                                                      m->partials, m->ticket, m->sums);
     } else {
-        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->rho, nullptr,
+        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, nullptr,
                                                                       m->partials, m->ticket, m->sums);
     }
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
+    m->geo_epoch = m->pos_epoch;        // sums[0..2] and rho now belong to the current positions
     return 0;
 }
 
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
-    if (tm_ensure_rings(m)) return 1;
+    if (tm_ensure_layout(m)) return 1;
     int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     DevParams P = tm_to_dev(p);
-    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), nl, P, m->rho, m->sums, m->grad);
+    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), nl, P, m->sums, m->grad);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     return 0;

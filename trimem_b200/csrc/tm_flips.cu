@@ -345,11 +345,11 @@ int ensure_ws(tm_mesh* m, int n) {
 }
 
 int check(tm_mesh* m, const tm_energy_params* p) {
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CHECK(p != nullptr, "null parameter block");
     TM_CHECK(p->bond_type == TM_BOND_EDGE || p->bond_type == TM_BOND_AREA, "Unknown bond potential");
     TM_CUDA(cudaSetDevice(m->device));
-    return 0;
+    return tm_ensure_layout(m);
 }
 
 }  // namespace
@@ -381,7 +381,7 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     for (int k = 0; k < n; k++) TM_CHECK(edges[k] >= 0 && edges[k] < E, "proposal %d: edge %d out of range", k, edges[k]);
     // cell lists evaluate exclusions on the live connectivity: keep the ring table usable for
     // everything outside the sweep, and walk half-edges inside it
-    if (tm_ensure_rings(m) || ensure_ws(m, n)) return 1;
+    if (tm_check_nlist(m, nl) || ensure_ws(m, n)) return 1;
     FlipWS* ws = (FlipWS*)m->flipws;
     cudaStream_t st = m->stream;
     const DevParams P = tm_to_dev(*p);
@@ -425,7 +425,9 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     TM_CUDA(cudaMemcpyAsync(hc, ws->counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
     TM_CUDA(cudaMemcpyAsync(props_io, ws->state, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
     TM_CUDA(cudaStreamSynchronize(st));
-    m->rings_valid = false;                 // connectivity changed: the ring table is rebuilt lazily
+    m->rings_valid = false;                 // connectivity changed: the ring table is rebuilt lazily,
+    m->raw_stale = true;                    // the host-numbered copies on request,
+    m->pos_epoch++;                         // and cached per-vertex properties are void
     TM_CHECK(hc[3] == 0, "flip sweep met a vertex of valence > %d", MAXV);
     if (flipped && hc[1] > 0)
         TM_CUDA(cudaMemcpy(flipped, ws->flips, sizeof(int) * hc[1], cudaMemcpyDeviceToHost));
@@ -437,7 +439,7 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
 int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int edge, double out[6]) {
     if (check(m, p)) return 1;
     TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
-    if (ensure_ws(m, 1)) return 1;
+    if (tm_check_nlist(m, nl) || ensure_ws(m, 1)) return 1;
     FlipWS* ws = (FlipWS*)m->flipws;
     TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, m->stream));
     k_evp<<<1, 32, 0, m->stream>>>(m->view(), topo_of(m), nl ? nl->view() : tm_no_nlist(), tm_to_dev(*p), edge,
@@ -452,10 +454,10 @@ int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* 
 }
 
 int tm_mesh_is_flip_ok(tm_mesh* m, int edge, int* ok) {
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to && ok, "bad arguments");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h && ok, "bad arguments");
     TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
     TM_CUDA(cudaSetDevice(m->device));
-    if (ensure_ws(m, 1)) return 1;
+    if (tm_ensure_layout(m) || ensure_ws(m, 1)) return 1;
     FlipWS* ws = (FlipWS*)m->flipws;
     k_flip_ok<<<1, 32, 0, m->stream>>>(topo_of(m), edge, ws->counters + 4); TM_LAUNCHED();
     TM_CUDA(cudaMemcpyAsync(ok, ws->counters + 4, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -464,12 +466,15 @@ int tm_mesh_is_flip_ok(tm_mesh* m, int edge, int* ok) {
 }
 
 int tm_mesh_flip(tm_mesh* m, int edge) {
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "bad arguments");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h, "bad arguments");
     TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
     TM_CUDA(cudaSetDevice(m->device));
+    if (tm_ensure_layout(m)) return 1;
     k_flip_one<<<1, 32, 0, m->stream>>>(topo_of(m), edge); TM_LAUNCHED();
     TM_CUDA(cudaStreamSynchronize(m->stream));
     m->rings_valid = false;
+    m->raw_stale = true;
+    m->pos_epoch++;
     return 0;
 }
 

@@ -33,10 +33,10 @@ __global__ void k_area_edges_partial(MeshView mv, double* __restrict__ part) {
     double a = 0.0, l = 0.0;
     for (int h = blockIdx.x * NT + threadIdx.x; h < mv.HE; h += gridDim.x * NT) {
         int to = mv.he_to[h], from = mv.he_to[h ^ 1];
-        d3 x0 = ldpos(mv.x3, from), x1 = ldpos(mv.x3, to);
+        d3 x0 = ldpos(mv.pos, from), x1 = ldpos(mv.pos, to);
         if ((h & 1) == 0) { d3 e = x1 - x0; l += sqrt(dot3(e, e)); }
         if (mv.he_face[h] >= 0) {
-            d3 x2 = ldpos(mv.x3, mv.he_to[mv.he_next[h]]);
+            d3 x2 = ldpos(mv.pos, mv.he_to[mv.he_next[h]]);
             d3 n = cross3(x2 - x1, x0 - x1);
             a += 0.5 * sqrt(dot3(n, n)) / 3.0;      // every face is visited by its 3 half-edges
         }
@@ -62,7 +62,7 @@ __global__ void k_halfedge_geometry(MeshView mv, int h, double* __restrict__ out
     const int o = h ^ 1;
     const int i = mv.he_to[o], j = mv.he_to[h];
     const int k = mv.he_to[mv.he_next[h]], m = mv.he_to[mv.he_next[o]];
-    const d3 xi = ldpos(mv.x3, i), xj = ldpos(mv.x3, j), xk = ldpos(mv.x3, k), xm = ldpos(mv.x3, m);
+    const d3 xi = ldpos(mv.pos, i), xj = ldpos(mv.pos, j), xk = ldpos(mv.pos, k), xm = ldpos(mv.pos, m);
     const bool boundary = mv.he_face[h] < 0 || mv.he_face[o] < 0;
 
     // edge (mesh_util.h:30-56)
@@ -113,8 +113,9 @@ __global__ void k_halfedge_geometry(MeshView mv, int h, double* __restrict__ out
 extern "C" {
 
 int tm_area_edges(tm_mesh* m, double* area, double* edges_length) {
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CUDA(cudaSetDevice(m->device));
+    if (tm_ensure_layout(m)) return 1;
     const int nb = 296;
     double *part = nullptr, *out = nullptr;
     TM_CUDA(cudaMalloc(&part, sizeof(double) * 2 * nb));
@@ -132,9 +133,10 @@ int tm_area_edges(tm_mesh* m, double* area, double* edges_length) {
 }
 
 int tm_halfedge_geometry(tm_mesh* m, int halfedge, double out[40]) {
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CHECK(halfedge >= 0 && halfedge < m->HE, "half-edge index %d out of range", halfedge);
     TM_CUDA(cudaSetDevice(m->device));
+    if (tm_ensure_layout(m)) return 1;
     double* d = nullptr;
     TM_CUDA(cudaMalloc(&d, sizeof(double) * 40));
     k_halfedge_geometry<<<1, 32, 0, m->stream>>>(m->view(), halfedge, d); TM_LAUNCHED();

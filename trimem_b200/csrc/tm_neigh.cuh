@@ -56,7 +56,7 @@ __device__ __forceinline__ void for_each_neighbour_t(const MeshView& mv, const N
         int b = nl.row_off[i], e = nl.row_off[i + 1];
         for (int k = b; k < e; k++) {
             int j = __ldg(nl.row_j + k);
-            d3 d = sub_nofma(xi, ldpos(mv.x3, j));
+            d3 d = sub_nofma(xi, ldpos(mv.pos, j));
             double l = dist_nofma(d);
             if (l < dmax) f(j, d, l);
         }
@@ -79,7 +79,7 @@ __device__ __forceinline__ void for_each_neighbour_t(const MeshView& mv, const N
                     for (int k = cb; k < ce; k++) {
                         int j = nl.cell_items[k];
                         if (j == i) continue;
-                        d3 d = sub_nofma(xi, ldpos(mv.x3, j));
+                        d3 d = sub_nofma(xi, ldpos(mv.pos, j));
                         double l = dist_nofma(d);
                         // the reference tests the exclusion first; the selected set is the same
                         if (l < dmax) {
@@ -97,4 +97,68 @@ template <class F>
 __device__ __forceinline__ void for_each_neighbour(const MeshView& mv, const NlView& nl, int i,
                                                    d3 xi, double dmax, F f) {
     for_each_neighbour_t<false>(mv, nl, i, xi, dmax, f);
+}
+
+
+// Sweep variant: calls f(j, d = x_i - x_j, l2 = |d|^2) for every candidate with l2 < dmax2. FMA
+// arithmetic and no square root: the caller re-tests l < lc1 on the rounded length, and a pair
+// whose length rounds differently from the reference's non-FMA value lies within an ulp of the
+// cut-off, where the potential and all its derivatives vanish (exp(l/(l-lc1)) -> 0), so the
+// sums are unaffected. Cell lists keep the reference's candidate and exclusion semantics
+// (cell_list.h:131-219): build-time occupancy, the query vertex's live position, live exclusions.
+// REC: fetch the whole (x,y,z,rho) record through the read-only path (kernels that do not write pos).
+template <bool LIVE, bool REC, class F>
+__device__ __forceinline__ void for_each_pair_fast(const MeshView& mv, const NlView& nl, int i,
+                                                   d3 xi, double dmax2, F f) {
+    if (nl.kind == TM_NLIST_VERLET) {
+        const int b = nl.row_off[i], e = nl.row_off[i + 1];
+        if (b >= e) return;
+        // software pipeline of depth 1: the next neighbour's record is in flight while the
+        // current pair is evaluated
+        int jn = __ldg(nl.row_j + b);
+        d3 xn;
+        if (REC) { const P4 r = ldrec(mv.pos, jn); xn = mk3(r.x, r.y, r.z); } else xn = ldpos(mv.pos, jn);
+        for (int k = b; k < e; k++) {
+            const int j = jn;
+            const d3 xj = xn;
+            if (k + 1 < e) {
+                jn = __ldg(nl.row_j + k + 1);
+                if (REC) { const P4 r = ldrec(mv.pos, jn); xn = mk3(r.x, r.y, r.z); } else xn = ldpos(mv.pos, jn);
+            }
+            const d3 d = xi - xj;
+            const double l2 = dot3(d, d);
+            if (l2 < dmax2) f(j, d, l2);
+        }
+    } else if (nl.kind == TM_NLIST_CELL) {
+        int c[3];
+        c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
+        c[1] = (int)((xi.y - nl.box_min[1]) / nl.cell[1]);
+        c[2] = (int)((xi.z - nl.box_min[2]) / nl.cell[2]);
+        for (int a = -1; a < 2; a++) {
+            const int ii = c[0] + a;
+            if (ii < 0 || ii >= nl.shape[0]) continue;
+            for (int b = -1; b < 2; b++) {
+                const int jj = c[1] + b;
+                if (jj < 0 || jj >= nl.shape[1]) continue;
+                for (int g = -1; g < 2; g++) {
+                    const int kk = c[2] + g;
+                    if (kk < 0 || kk >= nl.shape[2]) continue;
+                    const int cell = ii * nl.strides[0] + jj * nl.strides[1] + kk * nl.strides[2];
+                    const int cb = nl.cell_start[cell], ce = nl.cell_start[cell + 1];
+                    for (int k = cb; k < ce; k++) {
+                        const int j = nl.cell_items[k];
+                        if (j == i) continue;
+                        d3 xj;
+                        if (REC) { const P4 r = ldrec(mv.pos, j); xj = mk3(r.x, r.y, r.z); } else xj = ldpos(mv.pos, j);
+                        const d3 d = xi - xj;
+                        const double l2 = dot3(d, d);
+                        if (l2 < dmax2) {
+                            const bool ex = LIVE ? excluded_live(mv, i, j, nl.excl) : excluded(mv, i, j, nl.excl);
+                            if (!ex) f(j, d, l2);
+                        }
+                    }
+                }
+            }
+        }
+    }
 }

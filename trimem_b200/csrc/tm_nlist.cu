@@ -15,6 +15,7 @@
 // bit-identical to the x86-64 build of the reference.
 #include <cfloat>
 #include <algorithm>
+#include <vector>
 
 #include "tm_common.cuh"
 #include "tm_neigh.cuh"
@@ -22,45 +23,6 @@
 namespace {
 
 constexpr int NT = 256;
-
-// ---- bounding box ------------------------------------------------------------
-__global__ void k_bbox_partial(const double* __restrict__ x3, int V, double* __restrict__ part) {
-    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-    for (int i = blockIdx.x * NT + threadIdx.x; i < V; i += gridDim.x * NT) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            double v = x3[3 * (size_t)i + k];
-            mn[k] = fmin(mn[k], v);
-            mx[k] = fmax(mx[k], v);
-        }
-    }
-    __shared__ double smn[3][NT / 32], smx[3][NT / 32];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-        }
-        if (lane == 0) { smn[k][w] = mn[k]; smx[k][w] = mx[k]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        int k = threadIdx.x;
-        double a = smn[k][0], b = smx[k][0];
-        for (int q = 1; q < NT / 32; q++) { a = fmin(a, smn[k][q]); b = fmax(b, smx[k][q]); }
-        part[blockIdx.x * 6 + k] = a;
-        part[blockIdx.x * 6 + 3 + k] = b;
-    }
-}
-
-__global__ void k_bbox_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
-    int k = threadIdx.x;
-    if (k >= 6) return;
-    double a = part[k];
-    for (int b = 1; b < nb; b++) a = k < 3 ? fmin(a, part[b * 6 + k]) : fmax(a, part[b * 6 + k]);
-    out[k] = a;
-}
 
 // ---- cell grid ------------------------------------------------------------------
 struct Grid {
@@ -76,11 +38,11 @@ __device__ __forceinline__ int cell_of_point(const Grid& g, d3 p) {
     return id;
 }
 
-__global__ void k_cell_count(Grid g, const double* __restrict__ x3, int V, int* __restrict__ cell_of,
+__global__ void k_cell_count(Grid g, const P4* __restrict__ pos, int V, int* __restrict__ cell_of,
                              int* __restrict__ count) {
     int i = blockIdx.x * NT + threadIdx.x;
     if (i >= V) return;
-    int c = cell_of_point(g, ldpos(x3, i));
+    int c = cell_of_point(g, ldpos(pos, i));
     cell_of[i] = c;
     atomicAdd(count + c, 1);
 }
@@ -94,18 +56,6 @@ __global__ void k_cell_fill(int V, const int* __restrict__ cell_of, const int* _
     items[cell_start[c] + slot] = i;
 }
 
-// ascending ids inside every segment (cells / verlet rows): deterministic output
-__global__ void k_sort_segments(long long nseg, const int* __restrict__ start, int* __restrict__ items) {
-    long long c = (long long)blockIdx.x * NT + threadIdx.x;
-    if (c >= nseg) return;
-    int b = start[c], e = start[c + 1];
-    for (int a = b + 1; a < e; a++) {
-        int v = items[a], q = a - 1;
-        while (q >= b && items[q] > v) { items[q + 1] = items[q]; --q; }
-        items[q + 1] = v;
-    }
-}
-
 // ---- pair search -------------------------------------------------------------------
 // Visits every j != i in the 27 cells around the BUILD-TIME cell of i that is not
 // topologically excluded and lies within `cut` (<= when INCLUSIVE, else <).
@@ -116,7 +66,7 @@ __device__ __forceinline__ void for_each_cell_pair(const MeshView& mv, const NlV
     int rem = cell % nl.strides[2];
     int jc = rem / nl.strides[1];
     int ic = rem % nl.strides[1];
-    d3 xi = ldpos(mv.x3, i);
+    d3 xi = ldpos(mv.pos, i);
     for (int a = -1; a < 2; a++) {
         int ii = ic + a;
         if (ii < 0 || ii >= nl.shape[0]) continue;
@@ -131,7 +81,7 @@ __device__ __forceinline__ void for_each_cell_pair(const MeshView& mv, const NlV
                 for (int k = cb; k < ce; k++) {
                     int j = nl.cell_items[k];
                     if (j == i) continue;
-                    double l = dist_nofma(sub_nofma(xi, ldpos(mv.x3, j)));
+                    double l = dist_nofma(sub_nofma(xi, ldpos(mv.pos, j)));
                     bool in = INCLUSIVE ? (l <= cut) : (l < cut);
                     if (in && !excluded(mv, i, j, nl.excl)) f(j, l);
                 }
@@ -188,10 +138,10 @@ __global__ void k_cell_dm_fill(MeshView mv, NlView nl, const int* __restrict__ c
 __global__ void k_verlet_dm_count(MeshView mv, NlView nl, double dmax, int* __restrict__ cnt) {
     int i = blockIdx.x * NT + threadIdx.x;
     if (i >= mv.V) return;
-    d3 xi = ldpos(mv.x3, i);
+    d3 xi = ldpos(mv.pos, i);
     int n = 0;
     for (int k = nl.row_off[i]; k < nl.row_off[i + 1]; k++)
-        if (dist_nofma(sub_nofma(xi, ldpos(mv.x3, nl.row_j[k]))) < dmax) ++n;
+        if (dist_nofma(sub_nofma(xi, ldpos(mv.pos, nl.row_j[k]))) < dmax) ++n;
     cnt[i] = n;
 }
 
@@ -199,11 +149,11 @@ __global__ void k_verlet_dm_fill(MeshView mv, NlView nl, double dmax, const int*
                                  double* __restrict__ dist, int* __restrict__ idx, int* __restrict__ jdx) {
     int i = blockIdx.x * NT + threadIdx.x;
     if (i >= mv.V) return;
-    d3 xi = ldpos(mv.x3, i);
+    d3 xi = ldpos(mv.pos, i);
     int o = off[i];
     for (int k = nl.row_off[i]; k < nl.row_off[i + 1]; k++) {
         int j = nl.row_j[k];
-        double l = dist_nofma(sub_nofma(xi, ldpos(mv.x3, j)));
+        double l = dist_nofma(sub_nofma(xi, ldpos(mv.pos, j)));
         if (l < dmax) { dist[o] = l; idx[o] = i; jdx[o] = j; ++o; }
     }
 }
@@ -213,7 +163,7 @@ __global__ void k_point_distances(MeshView mv, NlView nl, int pid, double dmax, 
                                   int* __restrict__ n_out, double* __restrict__ dxyz, int* __restrict__ jdx) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int n = 0;
-    d3 xi = ldpos(mv.x3, pid);
+    d3 xi = ldpos(mv.pos, pid);
     for_each_neighbour(mv, nl, pid, xi, dmax, [&](int j, d3 d, double) {
         if (n < cap) { dxyz[3 * n] = d.x; dxyz[3 * n + 1] = d.y; dxyz[3 * n + 2] = d.z; jdx[n] = j; }
         ++n;
@@ -231,14 +181,8 @@ struct DevBuf {
 int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
     const int V = m->V;
     // bounding box (cell_list.h:45-56, including its initial values)
-    int nb = std::min((V + NT - 1) / NT, 1024);
-    DevBuf<double> part, box;
-    if (part.alloc((size_t)nb * 6) || box.alloc(6)) return 1;
-    k_bbox_partial<<<nb, NT, 0, m->stream>>>(m->x3, V, part.p); TM_LAUNCHED();
-    k_bbox_final<<<1, 32, 0, m->stream>>>(part.p, nb, box.p); TM_LAUNCHED();
     double hb[6];
-    TM_CUDA(cudaMemcpyAsync(hb, box.p, sizeof(hb), cudaMemcpyDeviceToHost, m->stream));
-    TM_CUDA(cudaStreamSynchronize(m->stream));
+    if (tm_bbox(m, reinterpret_cast<const double*>(m->pos), 4, V, hb)) return 1;
     const double init_min[3] = {DBL_MAX, 0.0, 0.0}, init_max[3] = {-1.0, 0.0, 0.0};
     long long ncell = 1;
     for (int k = 0; k < 3; k++) {
@@ -270,12 +214,11 @@ int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
         g.shape[k] = nl->shape[k]; g.strides[k] = nl->strides[k];
     }
     int vb = (V + NT - 1) / NT;
-    k_cell_count<<<vb, NT, 0, m->stream>>>(g, m->x3, V, cell_of, count.p); TM_LAUNCHED();
+    k_cell_count<<<vb, NT, 0, m->stream>>>(g, m->pos, V, cell_of, count.p); TM_LAUNCHED();
     if (tm_exclusive_scan(m, count.p, nl->cell_start, (int)ncell, nullptr)) return 1;
     TM_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)(ncell + 1), m->stream));
     k_cell_fill<<<vb, NT, 0, m->stream>>>(V, cell_of, nl->cell_start, count.p, nl->cell_items); TM_LAUNCHED();
-    k_sort_segments<<<(unsigned)((ncell + NT - 1) / NT), NT, 0, m->stream>>>(ncell, nl->cell_start, nl->cell_items);
-    TM_LAUNCHED();
+    if (tm_sort_segments(m, ncell, nl->cell_start, nl->cell_items)) return 1;
     TM_CUDA(cudaGetLastError());
     TM_CUDA(cudaStreamSynchronize(m->stream));   // `count` is released on return
     return 0;
@@ -291,14 +234,15 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
     // argument errors first, with the reference's messages (nlist.cpp:32,49,52)
     TM_CHECK(kind == TM_NLIST_CELL || kind == TM_NLIST_VERLET, "Unknown neighbour search algorithm.");
     TM_CHECK(exclusion_level >= 0 && exclusion_level <= 2, "Unsupported exclusion level");
-    TM_CHECK(m != nullptr && m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(m != nullptr && m->V > 0 && m->he_to_h, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CHECK(rlist > 0.0, "rlist must be positive (got %g)", rlist);
     TM_CUDA(cudaSetDevice(m->device));
-    if (tm_ensure_rings(m)) return 1;
+    if (tm_ensure_layout(m)) return 1;
 
     tm_nlist* nl = new tm_nlist();
     nl->device = m->device;
     nl->kind = kind; nl->excl = exclusion_level; nl->rlist = rlist; nl->box_eps = box_eps; nl->V = m->V;
+    nl->layout_epoch = m->layout_epoch;
     int* cell_of = nullptr;
     int rc = build_cells(m, nl, &cell_of);
     if (rc == 0 && kind == TM_NLIST_VERLET) {
@@ -321,8 +265,8 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
         }
         if (!rc) {
             k_verlet_fill<<<vb, NT, 0, m->stream>>>(m->view(), cv, cell_of, rlist, nl->row_off, nl->row_j); TM_LAUNCHED();
-            k_sort_segments<<<vb, NT, 0, m->stream>>>(m->V, nl->row_off, nl->row_j); TM_LAUNCHED();
-            rc = (cudaStreamSynchronize(m->stream) != cudaSuccess);
+            rc = tm_sort_segments(m, m->V, nl->row_off, nl->row_j);
+            if (!rc) rc = (cudaStreamSynchronize(m->stream) != cudaSuccess);
             if (rc) tm_set_error("verlet build failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         // a verlet list does not keep the grid
@@ -359,9 +303,8 @@ int tm_nlist_info(tm_nlist* nl, long long* n_entries, int shape[3], double box[6
 int tm_nlist_distance_matrix(tm_nlist* nl, tm_mesh* m, double rdist, long long* n, double** dist,
                              int** idx, int** jdx) {
     TM_CHECK(nl && m && n && dist && idx && jdx, "null argument");
-    TM_CHECK(m->V == nl->V, "neighbour list was built for %d vertices, mesh has %d", nl->V, m->V);
     TM_CUDA(cudaSetDevice(m->device));
-    if (tm_ensure_rings(m)) return 1;
+    if (tm_ensure_layout(m) || tm_check_nlist(m, nl)) return 1;
     const int V = m->V, vb = (V + NT - 1) / NT;
     DevBuf<int> off;
     if (off.alloc((size_t)V + 1)) return 1;
@@ -391,18 +334,46 @@ int tm_nlist_distance_matrix(tm_nlist* nl, tm_mesh* m, double rdist, long long* 
     TM_CUDA(cudaMemcpyAsync(*dist, dd.p, total * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaMemcpyAsync(*idx, di.p, total * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaMemcpyAsync(*jdx, dj.p, total * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    std::vector<int> d2h(V);
+    TM_CUDA(cudaMemcpyAsync(d2h.data(), m->d2h, sizeof(int) * V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
+    // device numbering -> host numbering (a query entry, not the hot path): map the ids, keep
+    // i < j for cell lists (the distance is symmetric bit for bit), sort by (i, j)
+    std::vector<long long> order((size_t)total);
+    for (long long k = 0; k < total; k++) {
+        int a = d2h[(*idx)[k]], b = d2h[(*jdx)[k]];
+        if (nl->kind == TM_NLIST_CELL && a > b) std::swap(a, b);
+        (*idx)[k] = a; (*jdx)[k] = b;
+        order[(size_t)k] = k;
+    }
+    const int* pi = *idx;
+    const int* pj = *jdx;
+    std::sort(order.begin(), order.end(), [pi, pj](long long x, long long y) {
+        return pi[x] != pi[y] ? pi[x] < pi[y] : pj[x] < pj[y];
+    });
+    std::vector<double> td((size_t)total);
+    std::vector<int> ti((size_t)total), tj((size_t)total);
+    for (long long k = 0; k < total; k++) {
+        td[(size_t)k] = (*dist)[order[(size_t)k]]; ti[(size_t)k] = pi[order[(size_t)k]]; tj[(size_t)k] = pj[order[(size_t)k]];
+    }
+    if (total > 0) {
+        memcpy(*dist, td.data(), sizeof(double) * (size_t)total);
+        memcpy(*idx, ti.data(), sizeof(int) * (size_t)total);
+        memcpy(*jdx, tj.data(), sizeof(int) * (size_t)total);
+    }
     *n = total;
     return 0;
 }
 
 int tm_nlist_point_distances(tm_nlist* nl, tm_mesh* m, int pid, double rdist, int* n, double** dxyz, int** jdx) {
     TM_CHECK(nl && m && n && dxyz && jdx, "null argument");
-    TM_CHECK(m->V == nl->V, "neighbour list was built for %d vertices, mesh has %d", nl->V, m->V);
     TM_CHECK(pid >= 0 && pid < m->V, "vertex index %d out of range", pid);
     TM_CUDA(cudaSetDevice(m->device));
-    if (tm_ensure_rings(m)) return 1;
+    if (tm_ensure_layout(m) || tm_check_nlist(m, nl)) return 1;
     NlView v = nl->view();
+    int hpid = pid;                      // host id -> device slot
+    TM_CUDA(cudaMemcpyAsync(&pid, m->h2d + hpid, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
     int cap = 4096;
     for (int attempt = 0; attempt < 2; attempt++) {
         DevBuf<double> dd;
@@ -418,6 +389,22 @@ int tm_nlist_point_distances(tm_nlist* nl, tm_mesh* m, int pid, double rdist, in
         TM_CHECK(*dxyz && *jdx, "out of host memory");
         TM_CUDA(cudaMemcpy(*dxyz, dd.p, sizeof(double) * 3 * (size_t)cnt, cudaMemcpyDeviceToHost));
         TM_CUDA(cudaMemcpy(*jdx, dj.p, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost));
+        // neighbour ids back to host numbering, ascending
+        std::vector<int> d2h(m->V), order(cnt);
+        TM_CUDA(cudaMemcpy(d2h.data(), m->d2h, sizeof(int) * m->V, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt; k++) { (*jdx)[k] = d2h[(*jdx)[k]]; order[k] = k; }
+        const int* pj = *jdx;
+        std::sort(order.begin(), order.end(), [pj](int x, int y) { return pj[x] < pj[y]; });
+        std::vector<double> td(3 * (size_t)cnt);
+        std::vector<int> tj(cnt);
+        for (int k = 0; k < cnt; k++) {
+            tj[k] = pj[order[k]];
+            for (int c = 0; c < 3; c++) td[3 * (size_t)k + c] = (*dxyz)[3 * (size_t)order[k] + c];
+        }
+        if (cnt > 0) {
+            memcpy(*dxyz, td.data(), sizeof(double) * 3 * (size_t)cnt);
+            memcpy(*jdx, tj.data(), sizeof(int) * (size_t)cnt);
+        }
         *n = cnt;
         return 0;
     }

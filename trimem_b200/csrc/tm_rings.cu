@@ -149,7 +149,7 @@ int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* tot
 
 int tm_ensure_rings(tm_mesh* m) {
     if (m->rings_valid) return 0;
-    TM_CHECK(m->V > 0 && m->he_to, "mesh has no topology (call tm_mesh_set_topology first)");
+    TM_CHECK(m->V > 0 && m->he_to && m->topo_dev_valid, "mesh has no device connectivity (internal: tm_ensure_layout first)");
     int nb = (m->V + 255) / 256;
     k_ring_count<<<nb, 256, 0, m->stream>>>(m->V, m->v_he, m->he_next, m->ring_cnt); TM_LAUNCHED();
     long long total = 0;

@@ -69,6 +69,30 @@ __device__ __forceinline__ double energy_of(const DevParams& P, const double* s)
     return e;
 }
 
+// surface-repulsion pair potential exp(l/(l-lc1)) / l^r (mesh_repulsion.h:44-53) from the
+// squared length; `sl` receives the slope factor of mesh_repulsion.h:65-75,
+//   -(lc1/(l-lc1)^2 + r/l) / l^(r+1) * exp(l/(l-lc1)),  when WITH_SLOPE.
+// One rsqrt, one reciprocal and one exp per pair, no division.
+template <bool WITH_SLOPE>
+__device__ __forceinline__ double repulsion_pair(double l2, double lc1, int r, double& sl) {
+    const double il = rsqrt_pos(l2);
+    const double l = l2 * il;
+    sl = 0.0;
+    if (!(l < lc1)) return 0.0;            // the rounded length decides, as in the reference
+    const double w = rcp_pos(l - lc1);     // 1/(l - lc1) < 0
+    const double ex = exp(l * w);
+    const double ilr = r == 2 ? il * il : powi(il, r);
+    const double phi = ex * ilr;
+    if (WITH_SLOPE) sl = -fma(lc1 * w, w, (double)r * il) * (phi * il);
+    return phi;
+}
+
+// sqrt for non-negative arguments: x * rsqrt(x), 0 for 0 (branch-free select)
+__device__ __forceinline__ double sqrt_nn(double x) {
+    const double y = x * rsqrt_pos(x);
+    return x > 0.0 ? y : 0.0;
+}
+
 // Six properties of vertex i whose clockwise one-ring is ring(0..d-1) (neighbour id |
 // TM_RING_FACE | TM_RING_OFACE). With e_s = x_{j_s} - x_i, n_s = e_s x e_{s-1}:
 //   A_f = |n_s|/2, V_f = x_i . n_s / 6, theta_s = atan2(-|e_s| (e_{s+1}.n_s), n_s.n_{s+1}).
@@ -76,21 +100,21 @@ __device__ __forceinline__ double energy_of(const DevParams& P, const double* s)
 template <bool FULL, bool LIVE, class RingFn>
 __device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& nl, const DevParams& P,
                                              int i, int d, RingFn ring, double out[6]) {
-    const d3 xi = ldpos(mv.x3, i);
+    const d3 xi = ldpos(mv.pos, i);
     double area = 0, vol = 0, curv = 0, teth = 0;
     if (d > 0) {
-        d3 e_prev = ldpos(mv.x3, ring(d - 1) & TM_RING_MASK) - xi;
+        d3 e_prev = ldpos(mv.pos, ring(d - 1) & TM_RING_MASK) - xi;
         int r_cur = ring(0);
-        d3 e_cur = ldpos(mv.x3, r_cur & TM_RING_MASK) - xi;
+        d3 e_cur = ldpos(mv.pos, r_cur & TM_RING_MASK) - xi;
         d3 n_cur = cross3(e_cur, e_prev);
         for (int s = 0; s < d; s++) {
             const int sn = s + 1 == d ? 0 : s + 1;
             const int r_next = ring(sn);
-            const d3 e_next = ldpos(mv.x3, r_next & TM_RING_MASK) - xi;
+            const d3 e_next = ldpos(mv.pos, r_next & TM_RING_MASK) - xi;
             const d3 n_next = cross3(e_next, e_cur);
             if (r_cur & TM_RING_FACE) {           // `not he.is_boundary()`
-                const double l = sqrt(dot3(e_cur, e_cur));
-                const double a_f = 0.5 * sqrt(dot3(n_cur, n_cur));
+                const double l = sqrt_nn(dot3(e_cur, e_cur));
+                const double a_f = 0.5 * sqrt_nn(dot3(n_cur, n_cur));
                 area += a_f;
                 vol += dot3(xi, n_cur);           // = (x_j x x_k) . x_i
                 if (r_cur & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
@@ -98,7 +122,7 @@ __device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& n
                     curv = fma(l, th, curv);
                 }
                 if (FULL) {
-                    if (P.bond_type == TM_BOND_EDGE) teth += tether_edge(l, P);
+                    if (P.bond_type == TM_BOND_EDGE) { if (l > P.lc0 || l < P.lc1) teth += tether_edge(l, P); }
                     else { const double q = a_f / P.a0 - 1.0; teth += q * q; }
                 }
             }
@@ -114,8 +138,9 @@ __device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& n
         if (nl.kind >= 0 && P.rep_lc1 > 0.0) {
             const double lc1 = P.rep_lc1;
             const int rr = P.rep_r;
-            for_each_neighbour_t<LIVE>(mv, nl, i, xi, lc1, [&rep, lc1, rr](int, d3, double l) {
-                rep += exp(l / (l - lc1)) / powi(l, rr);
+            for_each_pair_fast<LIVE, false>(mv, nl, i, xi, lc1 * lc1, [&rep, lc1, rr](int, d3, double l2) {
+                double sl;
+                rep += repulsion_pair<false>(l2, lc1, rr, sl);
             });
         }
     }
