@@ -14,7 +14,10 @@ __all__ = ["core", "install_as_trimem", "lib_path"]
 
 
 def lib_path():
-    """Path of the C-ABI shared library."""
+    """Path of the C-ABI shared library (TRIMEM_B200_LIB overrides it for the ctypes binding only:
+    a developer knob to time kernel variants built by scripts/build_variant.py)."""
+    if os.environ.get("TRIMEM_B200_LIB"):
+        return os.environ["TRIMEM_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtrimem_b200.so")
 
 

@@ -16,7 +16,7 @@ LIB = os.path.join(LIBDIR, "libtrimem_b200.so")
 CORE = os.path.join(HERE, "core" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 CU_SOURCES = ["tm_api.cu", "tm_layout.cu", "tm_rings.cu", "tm_energy.cu", "tm_nlist.cu", "tm_flips.cu", "tm_geometry.cu"]
-CU_HEADERS = ["tm_common.cuh", "tm_neigh.cuh", "tm_vertex.cuh"]
+CU_HEADERS = ["tm_common.cuh", "tm_neigh.cuh", "tm_vertex.cuh", "tm_math.cuh"]
 HOST_SOURCES = ["host/halfedge_mesh.cpp", "host/energy_manager.cpp", "host/bindings.cpp"]
 HOST_HEADERS = ["host/halfedge_mesh.h", "host/energy_manager.h"]
 # the image exports CXX=/opt/gcc/bin/g++ whose OpenMP link is broken; use the system compiler
@@ -43,20 +43,22 @@ def _run(cmd, verbose):
     return r.stdout
 
 
-def build_cuda(force=False, verbose=False, ptxas_info=False):
+def build_cuda(force=False, verbose=False, ptxas_info=False, defines=(), out=None):
+    """defines/out: build a kernel variant (-DNAME=VALUE ...) into another .so (scripts/build_variant.py)."""
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in CU_HEADERS] + [os.path.join(ROOT, "include", "trimem_b200.h")]
+    LIB = out or globals()["LIB"]
     if not force and not _newer(LIB, deps):
         return ""
-    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     procs = []
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.basename(LIB) if out else "")
     os.makedirs(objdir, exist_ok=True)
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

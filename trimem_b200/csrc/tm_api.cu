@@ -113,7 +113,6 @@ int tm_mesh_create(int device, tm_mesh** out) {
     TM_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     TM_CUDA(cudaEventCreate(&m->ev0));
     TM_CUDA(cudaEventCreate(&m->ev1));
-    TM_CUDA(cudaMalloc(&m->partials, sizeof(double) * 6 * TM_MAX_PARTIAL_BLOCKS));
     TM_CUDA(cudaMalloc(&m->sums, sizeof(double) * 8));
     TM_CUDA(cudaMalloc(&m->ticket, sizeof(unsigned) * 4));
     TM_CUDA(cudaMemset(m->ticket, 0, sizeof(unsigned) * 4));
@@ -130,9 +129,9 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaStreamSynchronize(m->stream);
     tm_flips_release(m);
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
-    cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt);
+    cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt); cudaFree(m->ring8);
     cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
-    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad);
+    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     cudaFreeHost(m->h_sums);
@@ -150,11 +149,13 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
     TM_CUDA(cudaSetDevice(m->device));
     if (V != m->V) {
         if (dev_alloc(&m->v_he, V) || dev_alloc(&m->v_he_h, V) || dev_alloc(&m->d2h, V) || dev_alloc(&m->h2d, V) ||
-            dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) ||
+            dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) || dev_alloc(&m->ring8, V) ||
             dev_alloc(&m->pos, V) || dev_alloc(&m->xio3, 3 * (size_t)V) || dev_alloc(&m->xout3, 3 * (size_t)V) ||
             dev_alloc(&m->grad, 3 * (size_t)V))
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
+        if (m->frep) { cudaFree(m->frep); m->frep = nullptr; }
+        m->frep_epoch = 0;
         TM_CUDA(cudaMemsetAsync(m->pos, 0, sizeof(P4) * (size_t)V, m->stream));
         m->perm_valid = false;          // a new vertex set: the order is rebuilt from its first positions
         m->have_positions = false;
@@ -329,16 +330,18 @@ int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int whic
                    unsigned long long flush_bytes, float* ms_avg) {
     if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     TM_CHECK(iters > 0 && ms_avg, "bad arguments");
-    TM_CHECK(which >= 0 && which <= 2, "which must be 0 (full property sweep), 1 (gradient's property sweep) or 2 (gradient sweep)");
-    // the gradient sweep consumes rho and the reduced sums of a property sweep
-    if (tm_launch_props(m, view_of(nl), *p, false, false)) return 1;
+    TM_CHECK(which >= 0 && which <= 3, "which must be 0 (energy sweeps: ring properties + pairs + reduction), "
+             "1 (the gradient's property sweep + reduction), 2 (ring gradient sweep) or 3 (pair sweep alone)");
+    // the gradient sweep consumes rho, the reduced sums and the pair force of earlier sweeps
+    if (tm_launch_props(m, view_of(nl), *p, true, false)) return 1;
     double total = 0.0;
     for (int it = 0; it < iters; it++) {
         if (flush_bytes && tm_flush_l2(m, flush_bytes)) return 1;
         TM_CUDA(cudaEventRecord(m->ev0, m->stream));
         int rc = which == 0 ? tm_launch_props(m, view_of(nl), *p, true, false)
                : which == 1 ? tm_launch_props(m, view_of(nl), *p, false, false)
-                            : tm_launch_grad(m, view_of(nl), *p);
+               : which == 2 ? tm_launch_grad(m, view_of(nl), *p)
+                            : tm_launch_pairs(m, view_of(nl), *p);
         if (rc) return 1;
         TM_CUDA(cudaEventRecord(m->ev1, m->stream));
         TM_CUDA(cudaEventSynchronize(m->ev1));

@@ -34,15 +34,39 @@ extern unsigned long long g_tm_launches;
 constexpr int TM_RING_FACE  = 1 << 30;          // slot's outgoing half-edge has a face
 constexpr int TM_RING_OFACE = (int)0x80000000u;         // its opposite half-edge has a face
 constexpr int TM_RING_MASK  = (1 << 30) - 1;
-constexpr int TM_PROPS_THREADS = 128;
-constexpr int TM_GRAD_THREADS  = 128;
-constexpr int TM_MAX_PARTIAL_BLOCKS = 1 << 17;  // 16.7M vertices at 128 threads
+// fixed-width one-ring rows (R8): unused slots hold TM_RING_PAD; a vertex whose ring does not fit
+// (valence > 8) or is degenerate (valence < 3) has TM_RING_GENERIC in slot 0 and is evaluated
+// from the CSR row instead
+constexpr int TM_RING_PAD     = TM_RING_MASK;
+constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
+// launch shapes of the two sweeps (overridable with -D for timing experiments, scripts/build_variant.py)
+#ifndef TM_PROPS_NT
+#define TM_PROPS_NT 128
+#endif
+#ifndef TM_GRAD_NT
+#define TM_GRAD_NT 128
+#endif
+// resident blocks per SM the register allocation aims at (measured on B200 at 655k vertices,
+// profiles/r01: ring gradient 130 us at 176 regs, 99 us at 128 regs, 119 us at 96 regs)
+#ifndef TM_PROPS_MINB
+#define TM_PROPS_MINB 5
+#endif
+#ifndef TM_GRAD_MINB
+#define TM_GRAD_MINB 4
+#endif
+constexpr int TM_PROPS_THREADS = TM_PROPS_NT;
+constexpr int TM_GRAD_THREADS  = TM_GRAD_NT;
+constexpr int TM_REDUCE_BLOCKS = 128;           // second-stage blocks of the property reduction (upper bound)
 
 // ------------------------------------------------------------ device views --
 // One 32-byte record per vertex = one DRAM/L2 sector: position plus rho = c/a (curvature /
 // area ratio of the last property sweep), so the gather sweeps fetch everything they need
 // about a ring neighbour with a single 256-bit load.
 struct __align__(32) P4 { double x, y, z, w; };
+// One 32-byte record per vertex as well: the clockwise one-ring (neighbour id | face flags) of a
+// vertex of valence <= 8. A thread fetches its whole ring with one coalesced 256-bit load instead
+// of the dependent ring_off -> ring_v chain, and can then issue all position gathers at once.
+struct __align__(32) R8 { int v[8]; };
 
 // All device arrays use the DEVICE vertex numbering: vertices sorted by the Morton code of a
 // coarse grid cell (tm_layout.cu), so that the 32 vertices of a warp form a compact surface
@@ -57,6 +81,7 @@ struct MeshView {
     const int* v_he;
     const int* ring_off;   // V+1
     const int* ring_v;     // HE entries, flags in the two top bits
+    const R8* ring8;       // V fixed-width rows (see TM_RING_PAD / TM_RING_GENERIC)
     const P4* pos;         // V packed (x, y, z, rho) records, device vertex numbering
 };
 
@@ -83,6 +108,7 @@ struct tm_mesh {
     int V = 0, HE = 0;
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
+    R8* ring8 = nullptr;
     bool rings_valid = false;
     // host-numbered connectivity as uploaded (he_to_h, v_he_h) and the vertex permutation
     int *he_to_h = nullptr, *v_he_h = nullptr;
@@ -100,7 +126,11 @@ struct tm_mesh {
     double* xout3 = nullptr;     // V*3 staging in HOST numbering: results on their way out
     double* vprops = nullptr;    // V*6 (allocated on demand)
     double* grad = nullptr;      // V*3 device numbering
-    double* partials = nullptr;  // 6 * TM_MAX_PARTIAL_BLOCKS
+    double* frep = nullptr;      // V*3 pair force of the last pair sweep (allocated on demand)
+    unsigned long long frep_epoch = 0;     // pos_epoch, potential and list it was evaluated for
+    double frep_lc1 = 0; int frep_r = 0; const void* frep_list = nullptr;
+    double* partials = nullptr;  // 6 * (warps of the property sweep) + 6 * TM_REDUCE_BLOCKS
+    size_t partials_n = 0;
     double* sums = nullptr;      // 8
     unsigned* ticket = nullptr;
     double* h_sums = nullptr;    // pinned, 8
@@ -114,7 +144,7 @@ struct tm_mesh {
         MeshView v;
         v.V = V; v.HE = HE;
         v.he_to = he_to; v.he_next = he_next; v.he_face = he_face; v.v_he = v_he;
-        v.ring_off = ring_off; v.ring_v = ring_v; v.pos = pos;
+        v.ring_off = ring_off; v.ring_v = ring_v; v.ring8 = ring8; v.pos = pos;
         return v;
     }
 };
@@ -166,6 +196,7 @@ int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* tot
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p);  // tm_energy.cu
+int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); // tm_energy.cu (force only)
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
 
 // ------------------------------------------------------------ device maths --

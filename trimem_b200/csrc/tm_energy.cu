@@ -9,7 +9,7 @@
 //   EnergyManager::properties/energy/gradient    src/energy.cpp:63-124
 //
 // Formulation. One thread owns one vertex i and walks its
-// one-ring j_0..j_{d-1} (clockwise CSR row). With e_s = x_{j_s} - x_i,
+// one-ring j_0..j_{d-1} (clockwise). With e_s = x_{j_s} - x_i,
 //   n_s   = e_s x e_{s-1}            un-normalised normal of face (i, j_s, j_{s-1})
 //   p_s   = e_s . e_{s-1}
 //   theta_s = atan2(-|e_s| (e_{s+1} . n_s), n_s . n_{s+1})   dihedral of spoke s
@@ -18,195 +18,443 @@
 // ring slot and no other transcendental. The gradient is a gather: vertex i
 // only writes g_i (no fp64 atomics) and needs the ring positions plus
 // rho_v = c_v / a_v of itself and of its ring from the property sweep.
-// Global sums use warp shuffles, a fixed block tree and a fixed-order last-block
-// pass, so results are bit-reproducible run to run.
+//
+// Memory access. A thread fetches its whole ring as one 32-byte R8 row (coalesced
+// across the warp), then issues all <= 8 position gathers back to back before any
+// arithmetic: two dependent memory levels instead of three, and 6-8 loads in flight
+// per thread instead of one. The ring loop is fully unrolled over the 8 slots of the
+// row so the ring data sit in registers under static indices; vertices of valence
+// > 8 (or < 3) take the generic CSR walk. Neighbour-list rows are consumed four
+// entries at a time for the same reason.
+//
+// Kernels. The ring part (area, volume, curvature, tether; and their gradients) and the
+// pair part (surface repulsion over the neighbour list) have different shapes -- the first
+// is register-hungry straight-line fp64, the second a long gather loop -- so they are
+// separate kernels, each at the occupancy that suits it. k_pairs evaluates the pair
+// potential and, in the same pass, the pair force (they share the distance, the reciprocal
+// and the exponential); the force is kept per vertex and the gradient sweep adds it, so an
+// energy() followed by gradient() at the same positions evaluates every pair once.
+//
+// Reduction. Each warp reduces its six sums with shuffles and writes one partial
+// per quantity; no block barrier, fence or atomic in the sweep. A small second
+// kernel adds the warp partials in a fixed order (fixed chunks, fixed trees), so
+// results are bit-reproducible run to run.
 #include "tm_common.cuh"
 #include "tm_neigh.cuh"
 #include "tm_vertex.cuh"
 
 namespace {
 
-// ---- reductions ---------------------------------------------------------------
-template <int NT, int NQ>
-__device__ __forceinline__ void block_reduce(double (&v)[NQ], double* out /* NQ, thread 0 */) {
-    __shared__ double sm[NQ][NT / 32];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// ---- shared pieces -----------------------------------------------------------------
+__device__ __forceinline__ int row_valence(const R8& r) {
+    int d = 0;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
+    for (int k = 0; k < 8; k++) d += (r.v[k] != TM_RING_PAD) ? 1 : 0;
+    return d;
+}
+
+__device__ __forceinline__ R8 ldrow(const R8* __restrict__ rows, int i) {
+    R8 r;
+    const int4 a = __ldg(reinterpret_cast<const int4*>(rows + i));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(rows + i) + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+// Verlet rows, four entries per trip: indices, then all four records, then the arithmetic.
+// f(d = x_i - x_j, l2) for l2 < dmax2, in row order (fixed summation order).
+template <bool REC, class F>
+__device__ __forceinline__ void verlet_pairs(const P4* pos, const NlView& nl, int i, d3 xi, double dmax2, F f) {
+    const int b = nl.row_off[i], e = nl.row_off[i + 1];
+    for (int k = b; k < e; k += 4) {
+        int j[4];
+        j[0] = __ldg(nl.row_j + k);
+#pragma unroll
+        for (int u = 1; u < 4; u++) j[u] = (k + u < e) ? __ldg(nl.row_j + k + u) : j[0];
+        d3 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (REC) { const P4 r = ldrec(pos, j[u]); x[u] = mk3(r.x, r.y, r.z); }
+            else x[u] = ldpos(pos, j[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (k + u < e) {
+                const d3 dv = xi - x[u];
+                const double l2 = dot3(dv, dv);
+                if (l2 < dmax2) f(dv, l2);
+            }
+        }
+    }
+}
+
+// ---- K1: per-vertex properties ------------------------------------------------------
+// one ring slot of vertex_properties (mesh_properties.cpp:19-38): spoke e_cur, face
+// (i, j_s, j_{s-1}) with normal n_cur, next spoke / normal for the dihedral of the spoke
+template <bool FULL>
+__device__ __forceinline__ void props_slot(const DevParams& P, d3 xi, int word, d3 e_cur, d3 n_cur, d3 e_next,
+                                           d3 n_next, double& area, double& vol, double& curv, double& teth) {
+    if (word & TM_RING_FACE) {                // `not he.is_boundary()`
+        const double l = sqrt_nn(dot3(e_cur, e_cur));
+        const double a_f = 0.5 * sqrt_nn(dot3(n_cur, n_cur));
+        area += a_f;
+        vol += dot3(xi, n_cur);               // = (x_j x x_k) . x_i
+        if (word & TM_RING_OFACE) {           // dihedral is 0 on boundary edges
+            const double th = tm_math::atan2_fast(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
+            curv = fma(l, th, curv);
+        }
+        if (FULL) {
+            if (P.bond_type == TM_BOND_EDGE) { if (l > P.lc0 || l < P.lc1) teth += tether_edge(l, P); }
+            else { const double q = a_f / P.a0 - 1.0; teth += q * q; }
+        }
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void ring_props_fast(const P4* pos, const DevParams& P, const R8& row, int d, d3 xi,
+                                                double& area, double& vol, double& curv, double& teth) {
+    d3 e[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+        if (s < d) e[s] = ldpos(pos, row.v[s] & TM_RING_MASK) - xi;
+    d3 el = e[2];                              // e_{d-1}, d >= 3 on this path
+#pragma unroll
+    for (int s = 3; s < 8; s++)
+        if (s < d) el = e[s];
+    d3 n_cur = cross3(e[0], el);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < d) {
+            const d3 en = (s == 7 || s + 1 == d) ? e[0] : e[(s + 1) & 7];
+            const d3 n_next = cross3(en, e[s]);
+            props_slot<FULL>(P, xi, row.v[s], e[s], n_cur, en, n_next, area, vol, curv, teth);
+            n_cur = n_next;
+        }
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void ring_props_generic(const MeshView& mv, const DevParams& P, int i, d3 xi,
+                                                   double& area, double& vol, double& curv, double& teth) {
+    const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
+    if (d <= 0) return;
+    const int* ring = mv.ring_v + beg;
+    int w_cur = ring[0];
+    d3 e_cur = ldpos(mv.pos, w_cur & TM_RING_MASK) - xi;
+    d3 n_cur = cross3(e_cur, ldpos(mv.pos, ring[d - 1] & TM_RING_MASK) - xi);
+    for (int s = 0; s < d; s++) {
+        const int w_next = ring[s + 1 == d ? 0 : s + 1];
+        const d3 e_next = ldpos(mv.pos, w_next & TM_RING_MASK) - xi;
+        const d3 n_next = cross3(e_next, e_cur);
+        props_slot<FULL>(P, xi, w_cur, e_cur, n_cur, e_next, n_next, area, vol, curv, teth);
+        w_cur = w_next; e_cur = e_next; n_cur = n_next;
+    }
+}
+
+// FULL = also tether and repulsion (what energy()/properties() need); the property
+// sweep inside gradient() only needs area, volume, curvature and rho.
+template <bool FULL, bool WRITE_VPROPS>
+__global__ void __launch_bounds__(TM_PROPS_THREADS, TM_PROPS_MINB)
+k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
+        double* __restrict__ partials, int nwarps, int nq) {
+    const int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
+    if (i < mv.V) {
+        const R8 row = ldrow(mv.ring8, i);
+        const d3 xi = ldpos(mv.pos, i);
+        double area = 0, vol = 0, curv = 0, teth = 0;
+        if (row.v[0] == TM_RING_GENERIC) ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
+        else {
+            const int d = row_valence(row);
+            if (d > 0) ring_props_fast<FULL>(mv.pos, P, row, d, xi, area, vol, curv, teth);
+        }
+        area = area / 3.0;
+        vol = vol / 18.0;                          // /6 per face, /3 multiplicity
+        curv = curv / 4.0;                         // 0.5 l theta per half-edge, /2 multiplicity
+        if (FULL) teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
+        acc[0] = area; acc[1] = vol; acc[2] = curv;
+        acc[3] = 2.0 * curv * curv / area;
+        acc[4] = teth;
+        pos_rw[i].w = curv / area;                 // rho_i = c_i / a_i rides in the position record
+        if (WRITE_VPROPS) {
+            double* o = vprops + 6 * (size_t)i;
+#pragma unroll
+            for (int q = 0; q < 5; q++) o[q] = acc[q];
+        }
+    }
+    // one partial per warp and quantity, fixed shuffle tree; quantity 5 (repulsion) belongs to
+    // k_pairs and is written here (as 0) only when no pair sweep runs (nq == 6)
+    const int lane = threadIdx.x & 31, w = i >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        if (q >= nq) break;
+        double t = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && w < nwarps) partials[(size_t)q * nwarps + w] = t;
+    }
+}
+
+// ---- K1b: pair sweep: surface repulsion energy and force per vertex ------------------------
+// (mesh_repulsion.h:28-79 over NeighbourList::point_distances). force[i] = sum_j slope_ij (x_i - x_j);
+// the gradient sweep adds 2 kappa_r force[i] (mesh_properties.cpp:139-146).
+constexpr int PAIR_THREADS = 128;
+template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS>
+__global__ void __launch_bounds__(PAIR_THREADS)
+k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
+        double* __restrict__ partials, int nwarps) {
+    const int i = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    double rep = 0.0;
+    if (i < mv.V) {
+        const d3 xi = ldpos(mv.pos, i);
+        d3 gr = mk3(0, 0, 0);
+        auto pair = [&rep, &gr, lc1, rr](d3 dv, double l2) {
+            double sl;
+            const double phi = repulsion_pair<WITH_F>(l2, lc1, rr, sl);
+            if (WITH_E) rep += phi;
+            if (WITH_F) axpy3(gr, sl, dv);
+        };
+        if (nl.kind == TM_NLIST_VERLET) verlet_pairs<false>(mv.pos, nl, i, xi, lc1 * lc1, pair);
+        else for_each_pair_fast<false, false>(mv, nl, i, xi, lc1 * lc1, [&pair](int, d3 dv, double l2) { pair(dv, l2); });
+        if (WITH_F) {
+            double* o = force + 3 * (size_t)i;
+            o[0] = gr.x; o[1] = gr.y; o[2] = gr.z;
+        }
+        if (WRITE_VPROPS) vprops[6 * (size_t)i + 5] = rep;
+    }
+    if (WITH_E) {
+        const int lane = threadIdx.x & 31, w = i >> 5;
+        double t = rep;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && w < nwarps) partials[(size_t)5 * nwarps + w] = t;
+    }
+}
+
+// ---- K2: fixed-order sum of the warp partials ---------------------------------------------
+// grid of nb <= TM_REDUCE_BLOCKS blocks; block b owns the contiguous chunk [b*per, (b+1)*per) of
+// warp partials; the last block to finish adds the nb block sums in index order.
+constexpr int RT = 256;
+__device__ __forceinline__ void block_sum6(double (&v)[6], double* out /* 6, valid in thread 0 */) {
+    __shared__ double sm[6][RT / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
         double t = v[q];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (lane == 0) sm[q][w] = t;
     }
     __syncthreads();
-    if (w == 0) {
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            double t = lane < NT / 32 ? sm[q][lane] : 0.0;
-#pragma unroll
-            for (int o = NT / 64; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) out[q] = t;
+        for (int q = 0; q < 6; q++) {
+            double t = 0.0;
+            for (int k = 0; k < RT / 32; k++) t += sm[q][k];
+            out[q] = t;
         }
     }
     __syncthreads();
 }
 
-// ---- K1 + K2: per-vertex properties and their global sums ----------------------
-// FULL = also tether and repulsion (what energy()/properties() need); the property
-// sweep inside gradient() only needs area, volume, curvature and rho.
-template <bool FULL, bool WRITE_VPROPS>
-__global__ void __launch_bounds__(TM_PROPS_THREADS)
-k_props(MeshView mv, NlView nl, DevParams P, P4* pos_rw,
-        double* __restrict__ vprops, double* __restrict__ partials,
-        unsigned* __restrict__ ticket, double* __restrict__ sums) {
-    int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
-    double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
-    if (i < mv.V) {
-        const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
-        const int* ring = mv.ring_v + beg;
-        vertex_props<FULL, false>(mv, nl, P, i, d, [ring](int s) { return __ldg(ring + s); }, acc);
-        pos_rw[i].w = acc[2] / acc[0];        // rho_i = c_i / a_i rides in the position record
-        if (WRITE_VPROPS) {
-            double* o = vprops + 6 * (size_t)i;
+__global__ void __launch_bounds__(RT)
+k_reduce_props(const double* __restrict__ partials, int nwarps, int per, int nq, double* __restrict__ block_sums,
+               unsigned* __restrict__ ticket, double* __restrict__ sums) {
+    const int lo = blockIdx.x * per, hi = min(lo + per, nwarps);
+    double tot[6] = {0, 0, 0, 0, 0, 0};
+    // up to 4 independent rows of loads in flight per thread, accumulated in index order
+    for (int w0 = lo + threadIdx.x; w0 < hi; w0 += 4 * RT) {
+        double v[4][6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) o[q] = acc[q];
+        for (int u = 0; u < 4; u++) {
+            const int w = w0 + u * RT;
+#pragma unroll
+            for (int q = 0; q < 6; q++) v[u][q] = (w < hi && q < nq) ? __ldcg(partials + (size_t)q * nwarps + w) : 0.0;
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < 6; q++) tot[q] += v[u][q];
     }
-
-    // block partials -> last block sums all partials in a fixed order
-    __shared__ double bsum[6];
+    __shared__ double bs[6];
     __shared__ bool last;
-    block_reduce<TM_PROPS_THREADS, 6>(acc, bsum);
+    block_sum6(tot, bs);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int q = 0; q < 6; q++) partials[(size_t)q * gridDim.x + blockIdx.x] = bsum[q];
+        for (int q = 0; q < 6; q++) block_sums[q * TM_REDUCE_BLOCKS + blockIdx.x] = bs[q];
         __threadfence();
-        unsigned t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x - 1);
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     }
     __syncthreads();
-    if (last) {
+    if (last && threadIdx.x < 6 * 32) {
         __threadfence();
-        double tot[6] = {0, 0, 0, 0, 0, 0};
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += TM_PROPS_THREADS) {
+        // warp q adds the block sums of quantity q: lanes stride over the blocks, then a fixed tree
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double t = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(block_sums + q * TM_REDUCE_BLOCKS + b);
 #pragma unroll
-            for (int q = 0; q < 6; q++) tot[q] += __ldcg(partials + (size_t)q * gridDim.x + b);
-        }
-        block_reduce<TM_PROPS_THREADS, 6>(tot, bsum);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int q = 0; q < 6; q++) sums[q] = bsum[q];
-            *ticket = 0;
-        }
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) sums[q] = t;
+        if (threadIdx.x == 0) *ticket = 0;
     }
 }
 
 // ---- K3 + K4: gather gradient ----------------------------------------------------
+// chain-rule factors of the global penalties (kernel.h:27-71,124-137) and the constants of a sweep
+struct GradK {
+    double fA, fV, fC, kb, kt;
+};
+
+// ring state of one slot of the gradient walk: spoke e_s, |e_s|^2, rho of j_s and, with the
+// previous spoke, p_s = e_s . e_{s-1}, n_s = e_s x e_{s-1}, 1/|n_s|
+struct GSlot {
+    d3 e, n;
+    double l2, rho, p, in;
+};
+
+__device__ __forceinline__ void gslot_point(GSlot& t, d3 e, double rho) {
+    t.e = e; t.rho = rho; t.l2 = dot3(e, e);
+}
+__device__ __forceinline__ void gslot_pair(GSlot& t, const GSlot& before) {
+    t.p = dot3(t.e, before.e);
+    t.n = cross3(t.e, before.e);
+    t.in = rsqrt_pos(dot3(t.n, t.n));
+}
+
+// contribution of ring slot s (mesh_properties.cpp:73-134) to g_i
+__device__ __forceinline__ void grad_slot(const DevParams& P, const GradK& K, double rho_i, int word,
+                                          const GSlot& prv, const GSlot& cur, const GSlot& nxt,
+                                          d3& g, d3& nsum, d3& esum) {
+    if (!(word & TM_RING_FACE)) return;
+    const double il = rsqrt_pos(cur.l2);       // 1/l_s
+    const double l = cur.l2 * il;
+    const double inn_cur = cur.in * cur.in;
+    double cE = 0.0, cEp = 0.0, cN = 0.0, cNn = 0.0;
+
+    // spoke edge (i, j_s): owners i and j_s   (mesh_properties.cpp:88-98)
+    const double W = 0.5 * K.fC + K.kb * (rho_i + cur.rho);
+    if (word & TM_RING_OFACE) {
+        const double th = tm_math::atan2_fast(-l * dot3(nxt.e, cur.n), dot3(cur.n, nxt.n));
+        cE -= W * th * il;                                   // theta * dl/dx_i
+        cN += W * (cur.l2 - cur.p) * inn_cur;                // l * dtheta/dx_i
+        cNn += W * (cur.l2 - nxt.p) * (nxt.in * nxt.in);
+    }
+    // face (i, j_s, j_{s-1}): owners i, j_s, j_{s-1}   (:103-118)
+    double U = K.fA - (2.0 / 3.0) * K.kb * (rho_i * rho_i + cur.rho * cur.rho + prv.rho * prv.rho);
+    if (P.bond_type == TM_BOND_AREA) {
+        const double a_f = 0.5 * rcp_pos(cur.in);
+        U += K.kt * 2.0 * (a_f / P.a0 - 1.0) / P.a0;
+    }
+    const double h = 0.5 * U * cur.in;                       // dA_f/dx_i in the e basis
+    cEp += h * (cur.p - cur.l2);
+    cE -= h * (prv.l2 - cur.p);
+    // link edge (j_s, j_{s-1}) seen from its apex i: owners j_s, j_{s-1}   (:121-129)
+    const double Wl = 0.5 * K.fC + K.kb * (cur.rho + prv.rho);
+    cN -= Wl * (cur.l2 + prv.l2 - 2.0 * cur.p) * inn_cur;
+    // tether bond (:132-133)
+    if (P.bond_type == TM_BOND_EDGE) {
+        if (l > P.lc0 || l < P.lc1) cE -= K.kt * tether_edge_fac(l, P) * il;
+    }
+    axpy3(g, cE, cur.e);
+    axpy3(g, cEp, prv.e);
+    axpy3(g, cN, cur.n);
+    axpy3(g, cNn, nxt.n);
+    nsum = nsum + cur.n;
+    esum = esum + (prv.e - cur.e);
+}
+
+__device__ __forceinline__ void ring_grad_fast(const P4* pos, const DevParams& P, const GradK& K, const R8& row,
+                                               int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
+    d3 e[8];
+    double rho[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < d) {
+            const P4 q = ldrec(pos, row.v[s] & TM_RING_MASK);
+            e[s] = mk3(q.x, q.y, q.z) - xi;
+            rho[s] = q.w;
+        }
+    }
+    d3 el = e[2];
+    double rhol = rho[2];
+#pragma unroll
+    for (int s = 3; s < 8; s++)
+        if (s < d) { el = e[s]; rhol = rho[s]; }
+    GSlot prv, cur;
+    gslot_point(prv, el, rhol);
+    gslot_point(cur, e[0], rho[0]);
+    gslot_pair(cur, prv);
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < d) {
+            const bool wrap = (s == 7 || s + 1 == d);
+            GSlot nxt;
+            gslot_point(nxt, wrap ? e[0] : e[(s + 1) & 7], wrap ? rho[0] : rho[(s + 1) & 7]);
+            gslot_pair(nxt, cur);
+            grad_slot(P, K, rho_i, row.v[s], prv, cur, nxt, g, nsum, esum);
+            prv = cur;
+            cur = nxt;
+        }
+    }
+}
+
+__device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevParams& P, const GradK& K, int i,
+                                                  d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
+    const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
+    if (d <= 0) return;
+    const int* ring = mv.ring_v + beg;
+    auto point = [&](GSlot& t, int word) {
+        const P4 q = ldrec(mv.pos, word & TM_RING_MASK);
+        gslot_point(t, mk3(q.x, q.y, q.z) - xi, q.w);
+    };
+    GSlot prv, cur;
+    int w_cur = ring[0];
+    point(prv, ring[d - 1]);
+    point(cur, w_cur);
+    gslot_pair(cur, prv);
+    for (int s = 0; s < d; s++) {
+        const int w_next = ring[s + 1 == d ? 0 : s + 1];
+        GSlot nxt;
+        point(nxt, w_next);
+        gslot_pair(nxt, cur);
+        grad_slot(P, K, rho_i, w_cur, prv, cur, nxt, g, nsum, esum);
+        prv = cur; cur = nxt; w_cur = w_next;
+    }
+}
+
 // Reads only: every ring / list neighbour costs one 256-bit read-only load of its
 // (x, y, z, rho) record.
-__global__ void __launch_bounds__(TM_GRAD_THREADS)
-k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ sums, double* __restrict__ grad) {
-    int i = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
+__global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
+k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
+       double* __restrict__ grad) {
+    const int i = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
     if (i >= mv.V) return;
 
-    // chain-rule factors of the global penalties (kernel.h:27-71,124-137)
-    const double fA = 2.0 * P.kappa_a / P.ref_area * (sums[0] / P.ref_area - 1.0);
-    const double fV = 2.0 * P.kappa_v / P.ref_volume * (sums[1] / P.ref_volume - 1.0);
-    const double fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
-    const double kb = P.kappa_b, kt = P.kappa_t;
+    GradK K;
+    K.fA = 2.0 * P.kappa_a / P.ref_area * (sums[0] / P.ref_area - 1.0);
+    K.fV = 2.0 * P.kappa_v / P.ref_volume * (sums[1] / P.ref_volume - 1.0);
+    K.fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
+    K.kb = P.kappa_b; K.kt = P.kappa_t;
 
+    const R8 row = ldrow(mv.ring8, i);
     const P4 ri = ldrec(mv.pos, i);
     const d3 xi = mk3(ri.x, ri.y, ri.z);
     d3 g = mk3(0, 0, 0);
-    int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
-    if (d > 0) {
-        const int* ring = mv.ring_v + beg;
-        const double rho_i = ri.w;
-        d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
-        d3 esum = mk3(0, 0, 0);      // sum of (e_{s-1} - e_s) over faces (0 for closed fans)
-
-        int r_prev = __ldg(ring + d - 1), r_cur = __ldg(ring);
-        const P4 q_prev = ldrec(mv.pos, r_prev & TM_RING_MASK), q_cur = ldrec(mv.pos, r_cur & TM_RING_MASK);
-        d3 e_prev = mk3(q_prev.x, q_prev.y, q_prev.z) - xi;
-        d3 e_cur = mk3(q_cur.x, q_cur.y, q_cur.z) - xi;
-        double rho_prev = q_prev.w, rho_cur = q_cur.w;
-        double l2_prev = dot3(e_prev, e_prev), l2_cur = dot3(e_cur, e_cur);
-        double p_cur = dot3(e_cur, e_prev);
-        d3 n_cur = cross3(e_cur, e_prev);
-        double nn_cur = dot3(n_cur, n_cur);
-        double in_cur = rsqrt_pos(nn_cur);            // 1/|n_s|
-
-        for (int s = 0; s < d; s++) {
-            int sn = s + 1 == d ? 0 : s + 1;
-            int r_next = __ldg(ring + sn);
-            const P4 q_next = ldrec(mv.pos, r_next & TM_RING_MASK);
-            d3 e_next = mk3(q_next.x, q_next.y, q_next.z) - xi;
-            double rho_next = q_next.w;
-            double l2_next = dot3(e_next, e_next);
-            double p_next = dot3(e_next, e_cur);
-            d3 n_next = cross3(e_next, e_cur);
-            double nn_next = dot3(n_next, n_next);
-            double in_next = rsqrt_pos(nn_next);
-
-            if (r_cur & TM_RING_FACE) {
-                const double il = rsqrt_pos(l2_cur);   // 1/l_s
-                const double l = l2_cur * il;
-                const double inn_cur = in_cur * in_cur;
-                double cE = 0.0, cEp = 0.0, cN = 0.0, cNn = 0.0;
-
-                // spoke edge (i, j_s): owners i and j_s   (mesh_properties.cpp:88-98)
-                const double W = 0.5 * fC + kb * (rho_i + rho_cur);
-                if (r_cur & TM_RING_OFACE) {
-                    const double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
-                    cE -= W * th * il;                                   // theta * dl/dx_i
-                    cN += W * (l2_cur - p_cur) * inn_cur;                // l * dtheta/dx_i
-                    cNn += W * (l2_cur - p_next) * (in_next * in_next);
-                }
-                // face (i, j_s, j_{s-1}): owners i, j_s, j_{s-1}   (:103-118)
-                double U = fA - (2.0 / 3.0) * kb * (rho_i * rho_i + rho_cur * rho_cur + rho_prev * rho_prev);
-                if (P.bond_type == TM_BOND_AREA) {
-                    const double a_f = 0.5 * nn_cur * in_cur;
-                    U += kt * 2.0 * (a_f / P.a0 - 1.0) / P.a0;
-                }
-                const double h = 0.5 * U * in_cur;                       // dA_f/dx_i in the e basis
-                cEp += h * (p_cur - l2_cur);
-                cE -= h * (l2_prev - p_cur);
-                // link edge (j_s, j_{s-1}) seen from its apex i: owners j_s, j_{s-1}   (:121-129)
-                const double Wl = 0.5 * fC + kb * (rho_cur + rho_prev);
-                cN -= Wl * (l2_cur + l2_prev - 2.0 * p_cur) * inn_cur;
-                // tether bond (:132-133)
-                if (P.bond_type == TM_BOND_EDGE) {
-                    if (l > P.lc0 || l < P.lc1) cE -= kt * tether_edge_fac(l, P) * il;
-                }
-                axpy3(g, cE, e_cur);
-                axpy3(g, cEp, e_prev);
-                axpy3(g, cN, n_cur);
-                axpy3(g, cNn, n_next);
-                nsum = nsum + n_cur;
-                esum = esum + (e_prev - e_cur);
-            }
-            r_prev = r_cur; r_cur = r_next;
-            e_prev = e_cur; e_cur = e_next;
-            rho_prev = rho_cur; rho_cur = rho_next;
-            l2_prev = l2_cur; l2_cur = l2_next;
-            p_cur = p_next; n_cur = n_next; nn_cur = nn_next; in_cur = in_next;
-        }
-        // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
-        d3 vg = nsum + cross3(xi, esum);
-        axpy3(g, fV / 6.0, vg);
+    d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
+    d3 esum = mk3(0, 0, 0);      // sum of (e_{s-1} - e_s) over faces (0 for closed fans)
+    if (row.v[0] == TM_RING_GENERIC) ring_grad_generic(mv, P, K, i, xi, ri.w, g, nsum, esum);
+    else {
+        const int d = row_valence(row);
+        if (d > 0) ring_grad_fast(mv.pos, P, K, row, d, xi, ri.w, g, nsum, esum);
     }
+    // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
+    axpy3(g, K.fV / 6.0, nsum + cross3(xi, esum));
 
-    // repulsion (mesh_properties.cpp:139-146, mesh_repulsion.h:56-78)
-    if (nl.kind >= 0 && P.rep_lc1 > 0.0 && P.kappa_r != 0.0) {
-        d3 gr = mk3(0, 0, 0);
-        const double lc1 = P.rep_lc1;
-        const int rr = P.rep_r;
-        for_each_pair_fast<false, true>(mv, nl, i, xi, lc1 * lc1, [&gr, lc1, rr](int, d3 dv, double l2) {
-            double sl;
-            repulsion_pair<true>(l2, lc1, rr, sl);
-            axpy3(gr, sl, dv);
-        });
-        axpy3(g, 2.0 * P.kappa_r, gr);
+    // repulsion (mesh_properties.cpp:139-146): 2 kappa_r * pair force of k_pairs
+    if (force) {
+        const double* f = force + 3 * (size_t)i;
+        axpy3(g, 2.0 * P.kappa_r, mk3(__ldg(f), __ldg(f + 1), __ldg(f + 2)));
     }
 
     double* o = grad + 3 * (size_t)i;
@@ -215,34 +463,84 @@ k_grad(MeshView mv, NlView nl, DevParams P, const double* __restrict__ sums, dou
 
 }  // namespace
 
+// does the pair force stored in m->frep belong to the current positions, list and potential?
+static bool pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
+    return m->frep_epoch == m->pos_epoch && m->frep_lc1 == p.rep_lc1 && m->frep_r == p.rep_r &&
+           m->frep_list == (nl.kind == TM_NLIST_VERLET ? (const void*)nl.row_j : (const void*)nl.cell_items);
+}
+
+// pair sweep: energy partials (quantity 5) and/or per-vertex force
+static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
+                        int nwarps) {
+    if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
+    const int nb = (m->V + PAIR_THREADS - 1) / PAIR_THREADS;
+    MeshView mv = m->view();
+    if (write_vprops)
+        k_pairs<true, true, true><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps);
+    else if (with_e)
+        k_pairs<true, true, false><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, nullptr, m->partials, nwarps);
+    else
+        k_pairs<false, true, false><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, nullptr, m->partials, nwarps);
+    TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
+    m->frep_list = nl.kind == TM_NLIST_VERLET ? (const void*)nl.row_j : (const void*)nl.cell_items;
+    return 0;
+}
+
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
     if (tm_ensure_layout(m)) return 1;
-    int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
-    TM_CHECK(nb <= TM_MAX_PARTIAL_BLOCKS, "mesh too large for the reduction workspace (%d vertices)", m->V);
+    const int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
+    const int nwarps = (m->V + 31) / 32;
+    const size_t need = 6 * (size_t)nwarps + 6 * TM_REDUCE_BLOCKS;
+    if (m->partials_n < need) {
+        if (m->partials) cudaFree(m->partials);
+        m->partials = nullptr; m->partials_n = 0;
+        TM_CUDA(cudaMalloc(&m->partials, need * sizeof(double)));
+        m->partials_n = need;
+    }
+    double* block_sums = m->partials + 6 * (size_t)nwarps;
     DevParams P = tm_to_dev(p);
     MeshView mv = m->view();
+    // the repulsion sum is wanted whenever lc1 > 0, whatever kappa_r is (mesh_properties.cpp:46)
+    const bool pairs = full && nl.kind >= 0 && p.rep_lc1 > 0.0;
+    // quantities the ring sweep reduces: geometry + bending (4) for the gradient's sweep, all but
+    // the repulsion when a pair sweep follows, else all six (repulsion = 0)
+    const int nq = !full ? 4 : (pairs ? 5 : 6);
     if (write_vprops) {
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
-        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, m->vprops,
-                                                                    m->partials, m->ticket, m->sums);
+        TM_CUDA(cudaMemsetAsync(m->vprops, 0, sizeof(double) * 6 * (size_t)m->V, m->stream));
+        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq);
     } else if (full) {
-        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, nullptr,
-                                                                     m->partials, m->ticket, m->sums);
+        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq);
     } else {
-        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, nl, P, m->pos, nullptr,
-                                                                      m->partials, m->ticket, m->sums);
+        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq);
     }
+    TM_LAUNCHED();
+    if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps)) return 1;
+    int rb = (nwarps + 4 * RT - 1) / (4 * RT);
+    rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
+    const int per = (nwarps + rb - 1) / rb;
+    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, nwarps, per, full ? 6 : 4, block_sums, m->ticket, m->sums);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->geo_epoch = m->pos_epoch;        // sums[0..2] and rho now belong to the current positions
     return 0;
 }
 
+int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
+    if (tm_ensure_layout(m)) return 1;
+    if (!(nl.kind >= 0 && p.rep_lc1 > 0.0)) return 0;
+    return launch_pairs(m, nl, p, false, false, 0);
+}
+
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     if (tm_ensure_layout(m)) return 1;
+    const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
+    if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
     int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     DevParams P = tm_to_dev(p);
-    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), nl, P, m->sums, m->grad);
+    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, pairs ? m->frep : nullptr, m->grad);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     return 0;

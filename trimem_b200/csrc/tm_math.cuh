@@ -1,0 +1,78 @@
+// fp64 elementary functions of the sweeps, written for the B200 instruction mix.
+//
+// The reference calls libm: std::acos inside OpenMesh's calc_dihedral_angle /
+// calc_sector_angle (mesh_util.h:132,148-161), std::exp and std::pow in the tether
+// and repulsion potentials (mesh_tether.h:46-71, mesh_repulsion.h:51,69). CUDA's own
+// exp()/atan2() materialise every polynomial coefficient with two UMOVs per use and
+// carry slow-path branches (atan2: ~35 DFMA inside ~200 SASS instructions; exp: 14
+// DFMA inside ~60), and the sweeps turned out issue-bound on exactly that overhead
+// (profiles/r01c). These versions keep the coefficients in the constant bank, where a
+// DFMA reads them as a direct operand, and are branch-free.
+//
+// Accuracy: <= ~2 ulp over the argument ranges the sweeps produce (tests/test_gpu_math.py
+// compares against numpy over dense samples); the parity bar of the path is 1e-10 relative.
+#pragma once
+#include "tm_common.cuh"
+
+#ifdef __CUDACC__
+namespace tm_math {
+
+// 1/k!, k = 13 .. 2
+static __constant__ double EXP_C[12] = {
+    1.6059043836821613e-10, 2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07,
+    2.7557319223985893e-06, 2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03,
+    8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01, 5.0e-01};
+
+// (-1)^n / (2n+1), n = 8 .. 1   (atan r = r + r^3 * P(r^2))
+static __constant__ double ATAN_C[8] = {
+    5.8823529411764705e-02, -6.6666666666666666e-02, 7.6923076923076927e-02, -9.0909090909090912e-02,
+    1.1111111111111111e-01, -1.4285714285714285e-01, 2.0e-01, -3.3333333333333331e-01};
+
+// exp(t) for t <= 0 (t = l/(l - lc1) of the flat-bottom potentials). Returns 0 below -708
+// (the true value is < 3.4e-308 there).
+__device__ __forceinline__ double exp_nonpos(double t) {
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: round-to-nearest integer
+    double kd = fma(t, 1.4426950408889634, MAGIC);
+    const int k = __double2loint(kd);                        // k <= 0
+    kd -= MAGIC;
+    double r = fma(kd, -6.93147180369123816490e-01, t);      // ln2 hi (32 trailing zero bits)
+    r = fma(kd, -1.90821492927058770002e-10, r);             // ln2 lo
+    double p = EXP_C[0];
+#pragma unroll
+    for (int i = 1; i < 12; i++) p = fma(p, r, EXP_C[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    // p * 2^k through the exponent field (p in [0.70, 1.42], k >= -1021 keeps it normal)
+    const double s = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return t < -708.0 ? 0.0 : s;
+}
+
+// atan2(y, x), all quadrants, y == x == 0 -> 0.
+//   q = min(|x|,|y|)/max(|x|,|y|) in [0,1];  c = q rounded to a multiple of 1/4;
+//   atan q = atan c + atan((q - c)/(1 + q c)),  |(q - c)/(1 + q c)| <= 1/8  -> odd series to r^17.
+__device__ __forceinline__ double atan2_fast(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const double q = mn * rcp_pos(mx);
+    const double M = 1688849860263936.0;                     // 1.5 * 2^50: ulp = 1/4
+    const double t = q + M;
+    const int k = __double2loint(t) & 7;                     // 0 .. 4
+    const double c = t - M;
+    const double r = (q - c) * rcp_pos(fma(q, c, 1.0));
+    const double s = r * r;
+    double p = ATAN_C[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) p = fma(p, s, ATAN_C[i]);
+    double a = fma(r * s, p, r);
+    const double ak = k == 0 ? 0.0 : k == 1 ? 0.24497866312686414 : k == 2 ? 0.46364760900080615
+                    : k == 3 ? 0.6435011087932844 : 0.7853981633974483;
+    a += ak;
+    a = swap ? 1.5707963267948966 - a : a;
+    a = __double2hiint(x) < 0 ? 3.141592653589793 - a : a;
+    a = mx > 0.0 ? a : 0.0;
+    return copysign(a, y);
+}
+
+}  // namespace tm_math
+#endif

@@ -29,19 +29,28 @@ __global__ void k_ring_count(int V, const int* __restrict__ v_he,
 
 __global__ void k_ring_fill(int V, const int* __restrict__ v_he, const int* __restrict__ he_next,
                             const int* __restrict__ he_to, const int* __restrict__ he_face,
-                            const int* __restrict__ off, int* __restrict__ ring_v) {
+                            const int* __restrict__ off, int* __restrict__ ring_v, R8* __restrict__ ring8) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
+    R8 row;
+#pragma unroll
+    for (int k = 0; k < 8; k++) row.v[k] = TM_RING_PAD;
     int h0 = v_he[i];
-    if (h0 < 0) return;
-    int o = off[i], end = off[i + 1], h = h0;
-    do {
-        int v = he_to[h];
-        if (he_face[h] >= 0) v |= TM_RING_FACE;
-        if (he_face[h ^ 1] >= 0) v |= TM_RING_OFACE;
-        ring_v[o++] = v;
-        h = he_next[h ^ 1];
-    } while (h != h0 && o < end);
+    int o = off[i], end = off[i + 1], h = h0, n = 0;
+    if (h0 >= 0) {
+        do {
+            int v = he_to[h];
+            if (he_face[h] >= 0) v |= TM_RING_FACE;
+            if (he_face[h ^ 1] >= 0) v |= TM_RING_OFACE;
+            ring_v[o++] = v;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (k == n) row.v[k] = v;
+            ++n;
+            h = he_next[h ^ 1];
+        } while (h != h0 && o < end);
+    }
+    if (n > 8 || (n > 0 && n < 3)) row.v[0] = TM_RING_GENERIC;
+    ring8[i] = row;
 }
 
 // --- three-phase exclusive scan over int (sizes here are <= 64M elements) ---
@@ -157,7 +166,7 @@ int tm_ensure_rings(tm_mesh* m) {
     TM_CHECK(total <= m->HE, "one-ring walk visited %lld half-edges but the mesh has %d "
              "(non-manifold vertex or corrupt connectivity)", total, m->HE);
     k_ring_fill<<<nb, 256, 0, m->stream>>>(m->V, m->v_he, m->he_next, m->he_to, m->he_face,
-                                          m->ring_off, m->ring_v); TM_LAUNCHED();
+                                          m->ring_off, m->ring_v, m->ring8); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->rings_valid = true;
     return 0;

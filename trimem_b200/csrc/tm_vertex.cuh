@@ -7,6 +7,7 @@
 #pragma once
 #include "tm_common.cuh"
 #include "tm_neigh.cuh"
+#include "tm_math.cuh"
 
 struct DevParams {
     double kappa_b, kappa_a, kappa_v, kappa_c, kappa_t, kappa_r;
@@ -40,7 +41,7 @@ __device__ __forceinline__ double powi(double x, int r) {
 // FlatBottomEdgePenalty::vertex_property (mesh_tether.h:40-54)
 __device__ __forceinline__ double tether_edge(double l, const DevParams& P) {
     if (l > P.lc0) return powi((double)P.bond_r, P.bond_r + 1) * powi(l - P.lc0, P.bond_r);
-    if (l < P.lc1) return exp(l / (l - P.lc1)) / powi(l, P.bond_r);
+    if (l < P.lc1) return tm_math::exp_nonpos(l / (l - P.lc1)) / powi(l, P.bond_r);
     return 0.0;
 }
 // slope factor of FlatBottomEdgePenalty::vertex_property_grad (mesh_tether.h:62-76)
@@ -52,7 +53,7 @@ __device__ __forceinline__ double tether_edge_fac(double l, const DevParams& P) 
         double lmc = l - P.lc1;
         fac -= P.lc1 / (lmc * lmc) + P.bond_r / l;
         fac /= lr;
-        fac *= exp(l / lmc);
+        fac *= tm_math::exp_nonpos(l / lmc);
     }
     return fac;
 }
@@ -80,7 +81,7 @@ __device__ __forceinline__ double repulsion_pair(double l2, double lc1, int r, d
     sl = 0.0;
     if (!(l < lc1)) return 0.0;            // the rounded length decides, as in the reference
     const double w = rcp_pos(l - lc1);     // 1/(l - lc1) < 0
-    const double ex = exp(l * w);
+    const double ex = tm_math::exp_nonpos(l * w);
     const double ilr = r == 2 ? il * il : powi(il, r);
     const double phi = ex * ilr;
     if (WITH_SLOPE) sl = -fma(lc1 * w, w, (double)r * il) * (phi * il);
@@ -103,22 +104,22 @@ __device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& n
     const d3 xi = ldpos(mv.pos, i);
     double area = 0, vol = 0, curv = 0, teth = 0;
     if (d > 0) {
-        d3 e_prev = ldpos(mv.pos, ring(d - 1) & TM_RING_MASK) - xi;
-        int r_cur = ring(0);
-        d3 e_cur = ldpos(mv.pos, r_cur & TM_RING_MASK) - xi;
-        d3 n_cur = cross3(e_cur, e_prev);
-        for (int s = 0; s < d; s++) {
+        // ring state of one slot: spoke e_s, face normal n_s = e_s x e_{s-1}, ring word
+        struct Slot { d3 e, n; int r; };
+        // one ring slot; `cur` is read, `nxt` is produced. The caller alternates two Slot objects
+        // so the rotation cur <- nxt costs no register moves.
+        auto step = [&](const Slot& cur, Slot& nxt, int s) {
             const int sn = s + 1 == d ? 0 : s + 1;
-            const int r_next = ring(sn);
-            const d3 e_next = ldpos(mv.pos, r_next & TM_RING_MASK) - xi;
-            const d3 n_next = cross3(e_next, e_cur);
-            if (r_cur & TM_RING_FACE) {           // `not he.is_boundary()`
-                const double l = sqrt_nn(dot3(e_cur, e_cur));
-                const double a_f = 0.5 * sqrt_nn(dot3(n_cur, n_cur));
+            nxt.r = ring(sn);
+            nxt.e = ldpos(mv.pos, nxt.r & TM_RING_MASK) - xi;
+            nxt.n = cross3(nxt.e, cur.e);
+            if (cur.r & TM_RING_FACE) {           // `not he.is_boundary()`
+                const double l = sqrt_nn(dot3(cur.e, cur.e));
+                const double a_f = 0.5 * sqrt_nn(dot3(cur.n, cur.n));
                 area += a_f;
-                vol += dot3(xi, n_cur);           // = (x_j x x_k) . x_i
-                if (r_cur & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
-                    const double th = atan2(-l * dot3(e_next, n_cur), dot3(n_cur, n_next));
+                vol += dot3(xi, cur.n);           // = (x_j x x_k) . x_i
+                if (cur.r & TM_RING_OFACE) {      // dihedral is 0 on boundary edges
+                    const double th = tm_math::atan2_fast(-l * dot3(nxt.e, cur.n), dot3(cur.n, nxt.n));
                     curv = fma(l, th, curv);
                 }
                 if (FULL) {
@@ -126,7 +127,14 @@ __device__ __forceinline__ void vertex_props(const MeshView& mv, const NlView& n
                     else { const double q = a_f / P.a0 - 1.0; teth += q * q; }
                 }
             }
-            e_prev = e_cur; e_cur = e_next; n_cur = n_next; r_cur = r_next;
+        };
+        Slot a, b;
+        a.r = ring(0);
+        a.e = ldpos(mv.pos, a.r & TM_RING_MASK) - xi;
+        a.n = cross3(a.e, ldpos(mv.pos, ring(d - 1) & TM_RING_MASK) - xi);
+        for (int s = 0; s < d; s += 2) {
+            step(a, b, s);
+            if (s + 1 < d) step(b, a, s + 1);
         }
     }
     area = area / 3.0;
