@@ -15,6 +15,63 @@ void tm_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- device block cache -------------------------------------------------------------
+#include <map>
+#include <mutex>
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks[16];    // per device, keyed by size
+    std::map<void*, size_t> live[16];
+    size_t cached_bytes[16] = {0};
+};
+Pool g_pool;
+constexpr size_t POOL_MAX_CACHED = (size_t)8 << 30;
+}  // namespace
+
+void* tm_pool_alloc(int device, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    const int d = device & 15;
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        auto it = g_pool.free_blocks[d].find(bytes);
+        if (it != g_pool.free_blocks[d].end()) {
+            void* p = it->second;
+            g_pool.free_blocks[d].erase(it);
+            g_pool.cached_bytes[d] -= bytes;
+            g_pool.live[d][p] = bytes;
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        // release the cache and retry once
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        for (auto& kv : g_pool.free_blocks[d]) cudaFree(kv.second);
+        g_pool.free_blocks[d].clear();
+        g_pool.cached_bytes[d] = 0;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_pool.live[d][p] = bytes;
+    return p;
+}
+
+void tm_pool_free(int device, void* p) {
+    if (!p) return;
+    const int d = device & 15;
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    auto it = g_pool.live[d].find(p);
+    if (it == g_pool.live[d].end()) { cudaFree(p); return; }
+    const size_t bytes = it->second;
+    g_pool.live[d].erase(it);
+    if (g_pool.cached_bytes[d] + bytes > POOL_MAX_CACHED) { cudaFree(p); return; }
+    g_pool.free_blocks[d].emplace(bytes, p);
+    g_pool.cached_bytes[d] += bytes;
+}
+
 namespace {
 
 template <class T>
@@ -131,7 +188,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
     cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt); cudaFree(m->ring8);
     cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
-    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep);
+    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); cudaFree(m->ex2_v);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     cudaFreeHost(m->h_sums);
@@ -155,6 +212,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
         if (m->frep) { cudaFree(m->frep); m->frep = nullptr; }
+        if (m->ex2_off) { cudaFree(m->ex2_off); m->ex2_off = nullptr; }
         m->frep_epoch = 0;
         TM_CUDA(cudaMemsetAsync(m->pos, 0, sizeof(P4) * (size_t)V, m->stream));
         m->perm_valid = false;          // a new vertex set: the order is rebuilt from its first positions
@@ -178,6 +236,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
     m->raw_stale = false;
     m->rings_valid = false;
     m->pos_epoch++;
+    m->topo_epoch++;
     return 0;
 }
 

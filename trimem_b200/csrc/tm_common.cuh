@@ -95,9 +95,14 @@ struct NlView {
     int strides[3];
     const int* cell_start; // ncell+1
     const int* cell_items; // V, ascending vertex id inside a cell
-    // verlet rows
-    const int* row_off;    // V+1
-    const int* row_j;      // directed entries, ascending inside a row
+    // verlet rows, fixed width, sliced by warp: entry k of vertex i is
+    // row_j[((i >> 5) * row_cap + k) * 32 + (i & 31)], k < row_cnt[i]. The 32 threads of a warp
+    // read 32 consecutive ints per step and a warp's whole slice is one contiguous block
+    // (row_cap * 128 bytes), so the sweep stays inside a page or two.
+    const int* row_cnt;    // V
+    const int* row_j;      // ceil(V/32) * row_cap * 32
+    int row_cap;
+    unsigned long long serial;   // identity of the list (pair-force cache)
 };
 
 // ----------------------------------------------------------------- handles --
@@ -128,7 +133,11 @@ struct tm_mesh {
     double* grad = nullptr;      // V*3 device numbering
     double* frep = nullptr;      // V*3 pair force of the last pair sweep (allocated on demand)
     unsigned long long frep_epoch = 0;     // pos_epoch, potential and list it was evaluated for
-    double frep_lc1 = 0; int frep_r = 0; const void* frep_list = nullptr;
+    double frep_lc1 = 0; int frep_r = 0; unsigned long long frep_list = 0;
+    // sorted, de-duplicated two-ring rows (verlet exclusion level 2), rebuilt when the topology changed
+    int *ex2_off = nullptr, *ex2_v = nullptr;
+    unsigned long long topo_epoch = 1, ex2_epoch = 0;
+    int verlet_cap_hint = 0;     // row width that fitted the last verlet build of this mesh
     double* partials = nullptr;  // 6 * (warps of the property sweep) + 6 * TM_REDUCE_BLOCKS
     size_t partials_n = 0;
     double* sums = nullptr;      // 8
@@ -158,7 +167,9 @@ struct tm_nlist {
     int shape[3] = {1, 1, 1}, strides[3] = {1, 1, 1};
     long long ncell = 0;
     int *cell_start = nullptr, *cell_items = nullptr;
-    int *row_off = nullptr, *row_j = nullptr;
+    int *row_cnt = nullptr, *row_j = nullptr;
+    int row_cap = 0;
+    unsigned long long serial = 0;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
     long long n_entries = 0;
     unsigned long long layout_epoch = 0;   // vertex numbering the list was built in
@@ -170,10 +181,16 @@ struct tm_nlist {
             v.shape[k] = shape[k]; v.strides[k] = strides[k];
         }
         v.cell_start = cell_start; v.cell_items = cell_items;
-        v.row_off = row_off; v.row_j = row_j;
+        v.row_cnt = row_cnt; v.row_j = row_j; v.row_cap = row_cap; v.serial = serial;
         return v;
     }
 };
+
+// first entry of vertex i's row; consecutive entries are 32 ints apart
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t tm_row_base(int i, int row_cap) { return ((size_t)(i >> 5) * row_cap) * 32 + (i & 31); }
 
 inline NlView tm_no_nlist() {
     NlView v;
@@ -192,6 +209,11 @@ int tm_bbox(tm_mesh* m, const double* x, int stride, int V, double out[6]);   //
 int tm_sort_segments(tm_mesh* m, long long nseg, const int* start, int* items);   // tm_layout.cu
 int tm_check_nlist(const tm_mesh* m, const tm_nlist* nl);        // tm_layout.cu
 int tm_ensure_rings(tm_mesh* m);                                 // tm_rings.cu
+int tm_ensure_ring2(tm_mesh* m);                                 // tm_rings.cu
+// size-keyed cache of device blocks (neighbour lists are rebuilt every few steps: no cudaMalloc /
+// cudaFree, and hence no device-wide sync, in steady state)                      tm_api.cu
+void* tm_pool_alloc(int device, size_t bytes);
+void tm_pool_free(int device, void* p);
 int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* total);  // tm_rings.cu
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu

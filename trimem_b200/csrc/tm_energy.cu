@@ -25,7 +25,7 @@
 // per thread instead of one. The ring loop is fully unrolled over the 8 slots of the
 // row so the ring data sit in registers under static indices; vertices of valence
 // > 8 (or < 3) take the generic CSR walk. Neighbour-list rows are consumed four
-// entries at a time for the same reason.
+// entries at a time for the same reason, from fixed-width column-major rows (coalesced index loads).
 //
 // Kernels. The ring part (area, volume, curvature, tether; and their gradients) and the
 // pair part (surface repulsion over the neighbour list) have different shapes -- the first
@@ -66,12 +66,13 @@ __device__ __forceinline__ R8 ldrow(const R8* __restrict__ rows, int i) {
 // f(d = x_i - x_j, l2) for l2 < dmax2, in row order (fixed summation order).
 template <bool REC, class F>
 __device__ __forceinline__ void verlet_pairs(const P4* pos, const NlView& nl, int i, d3 xi, double dmax2, F f) {
-    const int b = nl.row_off[i], e = nl.row_off[i + 1];
-    for (int k = b; k < e; k += 4) {
+    const int e = nl.row_cnt[i];
+    const int* col = nl.row_j + tm_row_base(i, nl.row_cap);
+    for (int k = 0; k < e; k += 4) {
         int j[4];
-        j[0] = __ldg(nl.row_j + k);
+        j[0] = __ldg(col + k * 32);
 #pragma unroll
-        for (int u = 1; u < 4; u++) j[u] = (k + u < e) ? __ldg(nl.row_j + k + u) : j[0];
+        for (int u = 1; u < 4; u++) j[u] = (k + u < e) ? __ldg(col + (k + u) * 32) : j[0];
         d3 x[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -466,7 +467,7 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
 // does the pair force stored in m->frep belong to the current positions, list and potential?
 static bool pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     return m->frep_epoch == m->pos_epoch && m->frep_lc1 == p.rep_lc1 && m->frep_r == p.rep_r &&
-           m->frep_list == (nl.kind == TM_NLIST_VERLET ? (const void*)nl.row_j : (const void*)nl.cell_items);
+           m->frep_list == nl.serial;
 }
 
 // pair sweep: energy partials (quantity 5) and/or per-vertex force
@@ -484,7 +485,7 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
-    m->frep_list = nl.kind == TM_NLIST_VERLET ? (const void*)nl.row_j : (const void*)nl.cell_items;
+    m->frep_list = nl.serial;
     return 0;
 }
 

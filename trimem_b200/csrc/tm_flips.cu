@@ -428,6 +428,7 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     m->rings_valid = false;                 // connectivity changed: the ring table is rebuilt lazily,
     m->raw_stale = true;                    // the host-numbered copies on request,
     m->pos_epoch++;                         // and cached per-vertex properties are void
+    m->topo_epoch++;
     TM_CHECK(hc[3] == 0, "flip sweep met a vertex of valence > %d", MAXV);
     if (flipped && hc[1] > 0)
         TM_CUDA(cudaMemcpy(flipped, ws->flips, sizeof(int) * hc[1], cudaMemcpyDeviceToHost));
@@ -475,6 +476,7 @@ int tm_mesh_flip(tm_mesh* m, int edge) {
     m->rings_valid = false;
     m->raw_stale = true;
     m->pos_epoch++;
+    m->topo_epoch++;
     return 0;
 }
 

@@ -255,6 +255,7 @@ int tm_ensure_layout(tm_mesh* m) {
         m->raw_stale = false;
         m->rings_valid = false;
         m->pos_epoch++;
+        m->topo_epoch++;
     }
     if (m->stage_pending) {
         k_import_positions<<<vb, NT, 0, m->stream>>>(V, m->xio3, m->d2h, m->pos); TM_LAUNCHED();

@@ -53,9 +53,9 @@ template <bool LIVE, class F>
 __device__ __forceinline__ void for_each_neighbour_t(const MeshView& mv, const NlView& nl, int i,
                                                      d3 xi, double dmax, F f) {
     if (nl.kind == TM_NLIST_VERLET) {
-        int b = nl.row_off[i], e = nl.row_off[i + 1];
-        for (int k = b; k < e; k++) {
-            int j = __ldg(nl.row_j + k);
+        const int n = nl.row_cnt[i];
+        for (int k = 0; k < n; k++) {
+            int j = __ldg(nl.row_j + tm_row_base(i, nl.row_cap) + k * 32);
             d3 d = sub_nofma(xi, ldpos(mv.pos, j));
             double l = dist_nofma(d);
             if (l < dmax) f(j, d, l);
@@ -111,18 +111,18 @@ template <bool LIVE, bool REC, class F>
 __device__ __forceinline__ void for_each_pair_fast(const MeshView& mv, const NlView& nl, int i,
                                                    d3 xi, double dmax2, F f) {
     if (nl.kind == TM_NLIST_VERLET) {
-        const int b = nl.row_off[i], e = nl.row_off[i + 1];
-        if (b >= e) return;
+        const int e = nl.row_cnt[i];
+        if (e <= 0) return;
         // software pipeline of depth 1: the next neighbour's record is in flight while the
         // current pair is evaluated
-        int jn = __ldg(nl.row_j + b);
+        int jn = __ldg(nl.row_j + tm_row_base(i, nl.row_cap));
         d3 xn;
         if (REC) { const P4 r = ldrec(mv.pos, jn); xn = mk3(r.x, r.y, r.z); } else xn = ldpos(mv.pos, jn);
-        for (int k = b; k < e; k++) {
+        for (int k = 0; k < e; k++) {
             const int j = jn;
             const d3 xj = xn;
             if (k + 1 < e) {
-                jn = __ldg(nl.row_j + k + 1);
+                jn = __ldg(nl.row_j + tm_row_base(i, nl.row_cap) + (k + 1) * 32);
                 if (REC) { const P4 r = ldrec(mv.pos, jn); xn = mk3(r.x, r.y, r.z); } else xn = ldpos(mv.pos, jn);
             }
             const d3 d = xi - xj;

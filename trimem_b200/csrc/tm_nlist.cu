@@ -1,5 +1,6 @@
 // Neighbour lists on the device: cell grid (one-pass counting sort on the cell
-// key) and Verlet rows (count -> scan -> fill pair search over 27 cells).
+// key) and Verlet rows (single-pass pair search over 27 cells into fixed-width,
+// column-major rows; exclusion by binary search in sorted two-ring rows).
 //
 // Replaces, in the reference (all serial CPU code there):
 //   make_nlist                        src/nlists/nlist.cpp:10-53
@@ -90,21 +91,112 @@ __device__ __forceinline__ void for_each_cell_pair(const MeshView& mv, const NlV
     }
 }
 
-__global__ void k_verlet_count(MeshView mv, NlView nl, const int* __restrict__ cell_of, double rlist,
-                               int* __restrict__ cnt) {
+// ---- verlet build ---------------------------------------------------------------------
+// The list is the symmetrised distance_matrix(rlist) of a cell list built from the same
+// positions (verlet_list.h:18-35): all pairs with dist <= rlist that are not topologically
+// excluded. The pair SET does not depend on the cell geometry (any grid with cells >= rlist
+// finds the same pairs), so the build uses its own tight grid; distances use the reference's
+// non-FMA arithmetic so that the <= decision is bit-identical.
+struct VGrid {
+    double lo[3], inv[3];
+    int n[3];
+};
+__device__ __forceinline__ void vcell(const VGrid& g, d3 p, int c[3]) {
+    c[0] = min(g.n[0] - 1, max(0, (int)((p.x - g.lo[0]) * g.inv[0])));
+    c[1] = min(g.n[1] - 1, max(0, (int)((p.y - g.lo[1]) * g.inv[1])));
+    c[2] = min(g.n[2] - 1, max(0, (int)((p.z - g.lo[2]) * g.inv[2])));
+}
+__global__ void k_vcell_count(VGrid g, const P4* __restrict__ pos, int V, int* __restrict__ cell_of,
+                              int* __restrict__ count) {
     int i = blockIdx.x * NT + threadIdx.x;
-    if (i >= mv.V) return;
-    int n = 0;
-    for_each_cell_pair<true>(mv, nl, i, cell_of[i], rlist, [&](int, double) { ++n; });
-    cnt[i] = n;
+    if (i >= V) return;
+    int c[3];
+    vcell(g, ldpos(pos, i), c);
+    const int id = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+    cell_of[i] = id;
+    atomicAdd(count + id, 1);
 }
 
-__global__ void k_verlet_fill(MeshView mv, NlView nl, const int* __restrict__ cell_of, double rlist,
-                              const int* __restrict__ row_off, int* __restrict__ row_j) {
-    int i = blockIdx.x * NT + threadIdx.x;
-    if (i >= mv.V) return;
-    int o = row_off[i];
-    for_each_cell_pair<true>(mv, nl, i, cell_of[i], rlist, [&](int j, double) { row_j[o++] = j; });
+// is j in the sorted row [b, e)?
+__device__ __forceinline__ bool in_sorted(const int* __restrict__ v, int b, int e, int j) {
+    while (b < e) {
+        const int mid = (b + e) >> 1;
+        const int x = __ldg(v + mid);
+        if (x == j) return true;
+        if (x < j) b = mid + 1; else e = mid;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128)
+k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
+                const int* __restrict__ ex2_off, const int* __restrict__ ex2_v, int excl, double rlist,
+                int cap, int* __restrict__ row_j, int* __restrict__ row_cnt, int* __restrict__ maxcnt) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    int n = 0;
+    if (i < mv.V) {
+        const d3 xi = ldpos(mv.pos, i);
+        int c[3];
+        vcell(g, xi, c);
+        int xb = 0, xe = 0;
+        if (excl == 2) { xb = ex2_off[i]; xe = ex2_off[i + 1]; }
+        else if (excl == 1) { xb = mv.ring_off[i]; xe = mv.ring_off[i + 1]; }
+        for (int dz = -1; dz < 2; dz++) {
+            const int cz = c[2] + dz;
+            if (cz < 0 || cz >= g.n[2]) continue;
+            for (int dy = -1; dy < 2; dy++) {
+                const int cy = c[1] + dy;
+                if (cy < 0 || cy >= g.n[1]) continue;
+                // the three x-neighbours are consecutive cells: one contiguous range of items
+                const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, g.n[0] - 1);
+                const int base = (cz * g.n[1] + cy) * g.n[0];
+                const int kb = __ldg(cell_start + base + x0), ke = __ldg(cell_start + base + x1 + 1);
+                for (int k = kb; k < ke; k++) {
+                    const int j = __ldg(cell_items + k);
+                    if (j == i) continue;
+                    const double l = dist_nofma(sub_nofma(xi, ldpos(mv.pos, j)));
+                    if (!(l <= rlist)) continue;
+                    bool ex = false;
+                    if (excl == 2) ex = in_sorted(ex2_v, xb, xe, j);
+                    else if (excl == 1) {
+                        for (int s = xb; s < xe; s++) ex |= ((mv.ring_v[s] & TM_RING_MASK) == j);
+                    }
+                    if (ex) continue;
+                    if (n < cap) row_j[tm_row_base(i, cap) + n * 32] = j;
+                    ++n;
+                }
+            }
+        }
+        row_cnt[i] = n < cap ? n : cap;
+    }
+    // widest row of the build: the host re-runs with wider rows if it did not fit
+    int w = n;
+    for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(maxcnt, w);
+}
+
+// ascending ids inside every row (column-major rows: the warp's accesses are coalesced).
+// Ascending device ids = ascending along the space-filling order, which keeps the position
+// gathers of the pair sweep on few cache lines.
+__global__ void k_sort_rows(int V, int cap, const int* __restrict__ row_cnt, int* __restrict__ row_j) {
+    const int i = blockIdx.x * NT + threadIdx.x;
+    if (i >= V) return;
+    const int n = row_cnt[i];
+    int* col = row_j + tm_row_base(i, cap);
+    for (int a = 1; a < n; a++) {
+        const int v = col[a * 32];
+        int q = a - 1;
+        while (q >= 0 && col[q * 32] > v) { col[(q + 1) * 32] = col[q * 32]; --q; }
+        col[(q + 1) * 32] = v;
+    }
+}
+
+// number of directed entries: sum of row_cnt (fixed-order, integers)
+__global__ void k_sum_int(const int* __restrict__ v, int n, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) s += (unsigned long long)v[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
 // distance_matrix of a cell list: pairs i<j with dist <= rdist (cell_list.h:221-312)
@@ -140,8 +232,8 @@ __global__ void k_verlet_dm_count(MeshView mv, NlView nl, double dmax, int* __re
     if (i >= mv.V) return;
     d3 xi = ldpos(mv.pos, i);
     int n = 0;
-    for (int k = nl.row_off[i]; k < nl.row_off[i + 1]; k++)
-        if (dist_nofma(sub_nofma(xi, ldpos(mv.pos, nl.row_j[k]))) < dmax) ++n;
+    for (int k = 0; k < nl.row_cnt[i]; k++)
+        if (dist_nofma(sub_nofma(xi, ldpos(mv.pos, nl.row_j[tm_row_base(i, nl.row_cap) + k * 32]))) < dmax) ++n;
     cnt[i] = n;
 }
 
@@ -151,8 +243,8 @@ __global__ void k_verlet_dm_fill(MeshView mv, NlView nl, double dmax, const int*
     if (i >= mv.V) return;
     d3 xi = ldpos(mv.pos, i);
     int o = off[i];
-    for (int k = nl.row_off[i]; k < nl.row_off[i + 1]; k++) {
-        int j = nl.row_j[k];
+    for (int k = 0; k < nl.row_cnt[i]; k++) {
+        int j = nl.row_j[tm_row_base(i, nl.row_cap) + k * 32];
         double l = dist_nofma(sub_nofma(xi, ldpos(mv.pos, j)));
         if (l < dmax) { dist[o] = l; idx[o] = i; jdx[o] = j; ++o; }
     }
@@ -170,6 +262,15 @@ __global__ void k_point_distances(MeshView mv, NlView nl, int pid, double dmax, 
     });
     *n_out = n;
 }
+
+template <class T>
+struct PoolBuf {
+    T* p = nullptr;
+    int dev;
+    explicit PoolBuf(int d) : dev(d) {}
+    ~PoolBuf() { tm_pool_free(dev, p); }
+    int alloc(size_t n) { p = (T*)tm_pool_alloc(dev, (n ? n : 1) * sizeof(T)); return p ? 0 : 1; }
+};
 
 template <class T>
 struct DevBuf {
@@ -200,13 +301,13 @@ int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
              "(rlist=%g is tiny compared with the bounding box)", nl->shape[0], nl->shape[1], nl->shape[2], nl->rlist);
     nl->ncell = ncell;
 
-    TM_CUDA(cudaMalloc(&nl->cell_start, sizeof(int) * (size_t)(ncell + 1)));
-    TM_CUDA(cudaMalloc(&nl->cell_items, sizeof(int) * (size_t)V));
-    DevBuf<int> count;
-    if (count.alloc((size_t)ncell + 1)) return 1;
-    int* cell_of = nullptr;
-    TM_CUDA(cudaMalloc(&cell_of, sizeof(int) * (size_t)V));
+    nl->cell_start = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)(ncell + 1));
+    nl->cell_items = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)V);
+    PoolBuf<int> count(m->device);
+    int* cell_of = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)V);
     *cell_of_out = cell_of;
+    TM_CHECK(nl->cell_start && nl->cell_items && cell_of && !count.alloc((size_t)ncell + 1),
+             "out of device memory for a cell grid of %lld cells", ncell);
     TM_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)(ncell + 1), m->stream));
     Grid g;
     for (int k = 0; k < 3; k++) {
@@ -221,6 +322,82 @@ int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
     if (tm_sort_segments(m, ncell, nl->cell_start, nl->cell_items)) return 1;
     TM_CUDA(cudaGetLastError());
     TM_CUDA(cudaStreamSynchronize(m->stream));   // `count` is released on return
+    return 0;
+}
+
+// Verlet rows: tight grid -> counting sort of the vertices by cell -> single search pass.
+int build_verlet(tm_mesh* m, tm_nlist* nl) {
+    const int V = m->V, vb = (V + NT - 1) / NT, dev = m->device;
+    if (nl->excl == 2 && tm_ensure_ring2(m)) return 1;
+    double hb[6];
+    if (tm_bbox(m, reinterpret_cast<const double*>(m->pos), 4, V, hb)) return 1;
+    VGrid g;
+    long long ncell = 1;
+    for (int k = 0; k < 3; k++) {
+        const double dim = hb[3 + k] - hb[k];
+        int nk = (int)(dim / nl->rlist);
+        if (nk < 1) nk = 1;
+        g.lo[k] = hb[k];
+        g.n[k] = nk;
+        g.inv[k] = dim > 0.0 ? nk / dim : 0.0;      // cell edge dim/nk >= rlist
+        ncell *= nk;
+    }
+    {   // what tm_nlist_info reports is the geometry of the reference's temporary cell list
+        // (cell_list.h:45-65), whatever grid the search itself uses
+        const double init_min[3] = {DBL_MAX, 0.0, 0.0}, init_max[3] = {-1.0, 0.0, 0.0};
+        for (int k = 0; k < 3; k++) {
+            nl->box_min[k] = hb[k] < init_min[k] ? hb[k] : init_min[k];
+            nl->box_max[k] = hb[3 + k] > init_max[k] ? hb[3 + k] : init_max[k];
+            const double dim = nl->box_max[k] - nl->box_min[k] + nl->box_eps;
+            const int nk = (int)(dim / nl->rlist);
+            nl->cell[k] = (nk > 0) ? dim / nk : dim;
+            nl->shape[k] = (nk > 0) ? nk : 1;
+        }
+    }
+    TM_CHECK(ncell < (1LL << 30), "cell grid of %d x %d x %d cells is too large for the dense cell table "
+             "(rlist=%g is tiny compared with the bounding box)", g.n[0], g.n[1], g.n[2], nl->rlist);
+    nl->ncell = ncell;
+    nl->strides[0] = 1; nl->strides[1] = nl->shape[0]; nl->strides[2] = nl->shape[0] * nl->shape[1];
+
+    PoolBuf<int> count(dev), start(dev), items(dev), cell_of(dev), maxcnt(dev);
+    TM_CHECK(!count.alloc((size_t)ncell + 1) && !start.alloc((size_t)ncell + 1) && !items.alloc(V) &&
+             !cell_of.alloc(V) && !maxcnt.alloc(4), "out of device memory for a cell grid of %lld cells", ncell);
+    TM_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)(ncell + 1), m->stream));
+    TM_CUDA(cudaMemsetAsync(maxcnt.p, 0, sizeof(int) * 4, m->stream));
+    k_vcell_count<<<vb, NT, 0, m->stream>>>(g, m->pos, V, cell_of.p, count.p); TM_LAUNCHED();
+    if (tm_exclusive_scan(m, count.p, start.p, (int)ncell, nullptr)) return 1;
+    TM_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)(ncell + 1), m->stream));
+    k_cell_fill<<<vb, NT, 0, m->stream>>>(V, cell_of.p, start.p, count.p, items.p); TM_LAUNCHED();
+    if (tm_sort_segments(m, ncell, start.p, items.p)) return 1;       // deterministic order inside a cell
+
+    nl->row_cnt = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)V);
+    TM_CHECK(nl->row_cnt, "out of device memory for verlet rows");
+    int cap = m->verlet_cap_hint > 0 ? m->verlet_cap_hint : 32;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        nl->row_cap = cap;
+        nl->row_j = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)cap * 32 * ((V + 31) / 32));
+        TM_CHECK(nl->row_j, "out of device memory for verlet rows of width %d", cap);
+        k_verlet_search<<<(V + 127) / 128, 128, 0, m->stream>>>(m->view(), g, start.p, items.p, m->ex2_off, m->ex2_v,
+                                                                nl->excl, nl->rlist, cap, nl->row_j,
+                                                                nl->row_cnt, maxcnt.p);
+        TM_LAUNCHED();
+        TM_CUDA(cudaGetLastError());
+        int widest = 0;
+        TM_CUDA(cudaMemcpyAsync(&widest, maxcnt.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+        TM_CUDA(cudaStreamSynchronize(m->stream));
+        if (widest <= cap) {
+            // next build of this mesh starts from the width that fitted (plus slack)
+            m->verlet_cap_hint = ((widest + widest / 4 + 7) / 8) * 8;
+            if (m->verlet_cap_hint < 8) m->verlet_cap_hint = 8;
+            break;
+        }
+        TM_CHECK(attempt < 2, "verlet rows of %d entries did not fit", widest);
+        tm_pool_free(dev, nl->row_j); nl->row_j = nullptr;
+        cap = ((widest + 7) / 8) * 8;
+    }
+    k_sort_rows<<<vb, NT, 0, m->stream>>>(V, nl->row_cap, nl->row_cnt, nl->row_j); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    nl->n_entries = -1;                 // counted on demand (tm_nlist_info)
     return 0;
 }
 
@@ -243,39 +420,16 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
     nl->device = m->device;
     nl->kind = kind; nl->excl = exclusion_level; nl->rlist = rlist; nl->box_eps = box_eps; nl->V = m->V;
     nl->layout_epoch = m->layout_epoch;
-    int* cell_of = nullptr;
-    int rc = build_cells(m, nl, &cell_of);
-    if (rc == 0 && kind == TM_NLIST_VERLET) {
-        // the verlet list is the symmetrised distance_matrix(rlist) of a temporary cell list
-        // (verlet_list.h:18-35): count -> scan -> fill, rows ascending
-        NlView cv = nl->view();
-        cv.kind = TM_NLIST_CELL;
-        int vb = (m->V + NT - 1) / NT;
-        long long total = 0;
-        rc = (cudaMalloc(&nl->row_off, sizeof(int) * ((size_t)m->V + 1)) != cudaSuccess);
-        if (rc) tm_set_error("out of device memory for verlet rows");
-        if (!rc) {
-            k_verlet_count<<<vb, NT, 0, m->stream>>>(m->view(), cv, cell_of, rlist, nl->row_off); TM_LAUNCHED();
-            rc = tm_exclusive_scan(m, nl->row_off, nl->row_off, m->V, &total);
-        }
-        if (!rc) {
-            nl->n_entries = total;
-            rc = (cudaMalloc(&nl->row_j, sizeof(int) * (size_t)(total > 0 ? total : 1)) != cudaSuccess);
-            if (rc) tm_set_error("out of device memory for %lld verlet entries", total);
-        }
-        if (!rc) {
-            k_verlet_fill<<<vb, NT, 0, m->stream>>>(m->view(), cv, cell_of, rlist, nl->row_off, nl->row_j); TM_LAUNCHED();
-            rc = tm_sort_segments(m, m->V, nl->row_off, nl->row_j);
-            if (!rc) rc = (cudaStreamSynchronize(m->stream) != cudaSuccess);
-            if (rc) tm_set_error("verlet build failed: %s", cudaGetErrorString(cudaGetLastError()));
-        }
-        // a verlet list does not keep the grid
-        cudaFree(nl->cell_start); nl->cell_start = nullptr;
-        cudaFree(nl->cell_items); nl->cell_items = nullptr;
-        cudaFree(cell_of); cell_of = nullptr;
+    static unsigned long long g_serial = 0;
+    nl->serial = ++g_serial;
+    if (kind == TM_NLIST_VERLET) {
+        if (build_verlet(m, nl)) { tm_nlist_destroy(nl); return 1; }
+        *out = nl;
+        return 0;
     }
-    if (rc) { cudaFree(cell_of); tm_nlist_destroy(nl); return 1; }
-    if (kind == TM_NLIST_CELL) nl->cell_of = cell_of;   // build-time cells, for distance_matrix
+    int* cell_of = nullptr;
+    if (build_cells(m, nl, &cell_of)) { tm_pool_free(m->device, cell_of); tm_nlist_destroy(nl); return 1; }
+    nl->cell_of = cell_of;   // build-time cells, for distance_matrix
     *out = nl;
     return 0;
 }
@@ -283,14 +437,27 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
 int tm_nlist_destroy(tm_nlist* nl) {
     if (!nl) return 0;
     cudaSetDevice(nl->device);
-    cudaFree(nl->cell_start); cudaFree(nl->cell_items); cudaFree(nl->row_off); cudaFree(nl->row_j);
-    cudaFree(nl->cell_of);
+    tm_pool_free(nl->device, nl->cell_start); tm_pool_free(nl->device, nl->cell_items);
+    tm_pool_free(nl->device, nl->row_cnt); tm_pool_free(nl->device, nl->row_j);
+    tm_pool_free(nl->device, nl->cell_of);
     delete nl;
     return 0;
 }
 
 int tm_nlist_info(tm_nlist* nl, long long* n_entries, int shape[3], double box[6], double cell[3]) {
     TM_CHECK(nl != nullptr, "null neighbour list");
+    if (n_entries && nl->n_entries < 0 && nl->kind == TM_NLIST_VERLET) {
+        TM_CUDA(cudaSetDevice(nl->device));
+        unsigned long long* d = (unsigned long long*)tm_pool_alloc(nl->device, 8);
+        TM_CHECK(d, "out of device memory");
+        unsigned long long h = 0;
+        cudaMemset(d, 0, 8);
+        k_sum_int<<<256, NT>>>(nl->row_cnt, nl->V, d); TM_LAUNCHED();
+        cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+        tm_pool_free(nl->device, d);
+        TM_CHECK(e == cudaSuccess, "tm_nlist_info failed: %s", cudaGetErrorString(e));
+        nl->n_entries = (long long)h;
+    }
     if (n_entries) *n_entries = nl->n_entries;
     for (int k = 0; k < 3; k++) {
         if (shape) shape[k] = nl->shape[k];

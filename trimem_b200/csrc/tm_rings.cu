@@ -53,6 +53,55 @@ __global__ void k_ring_fill(int V, const int* __restrict__ v_he, const int* __re
     ring8[i] = row;
 }
 
+// --- sorted two-ring rows ------------------------------------------------------------------
+// all vertices within two rings of i (i itself excluded), ascending and de-duplicated: the
+// exclusion set of level 2 (cell_list.h:181-199), looked up by binary search in the verlet build
+constexpr int RING2_CAP = 160;
+__device__ int collect_ring2(int i, const int* __restrict__ ring_off, const int* __restrict__ ring_v, int* buf) {
+    int n = 0;
+    for (int s = ring_off[i]; s < ring_off[i + 1]; s++) {
+        const int v = ring_v[s] & TM_RING_MASK;
+        if (n < RING2_CAP) buf[n] = v;
+        ++n;
+        for (int t = ring_off[v]; t < ring_off[v + 1]; t++) {
+            const int w = ring_v[t] & TM_RING_MASK;
+            if (w == i) continue;
+            if (n < RING2_CAP) buf[n] = w;
+            ++n;
+        }
+    }
+    if (n > RING2_CAP) return -1;
+    for (int a = 1; a < n; a++) {
+        int v = buf[a], q = a - 1;
+        while (q >= 0 && buf[q] > v) { buf[q + 1] = buf[q]; --q; }
+        buf[q + 1] = v;
+    }
+    int m = 0;
+    for (int a = 0; a < n; a++)
+        if (m == 0 || buf[m - 1] != buf[a]) buf[m++] = buf[a];
+    return m;
+}
+
+__global__ void k_ring2_count(int V, const int* __restrict__ ring_off, const int* __restrict__ ring_v,
+                              int* __restrict__ cnt, int* __restrict__ err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    int buf[RING2_CAP];
+    int n = collect_ring2(i, ring_off, ring_v, buf);
+    if (n < 0) { *err = 1; n = 0; }
+    cnt[i] = n;
+}
+
+__global__ void k_ring2_fill(int V, const int* __restrict__ ring_off, const int* __restrict__ ring_v,
+                             const int* __restrict__ off, int* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    int buf[RING2_CAP];
+    const int n = collect_ring2(i, ring_off, ring_v, buf);
+    int* o = out + off[i];
+    for (int a = 0; a < n; a++) o[a] = buf[a];
+}
+
 // --- three-phase exclusive scan over int (sizes here are <= 64M elements) ---
 __device__ __forceinline__ int warp_incl_scan(int v) {
     int lane = threadIdx.x & 31;
@@ -169,5 +218,27 @@ int tm_ensure_rings(tm_mesh* m) {
                                           m->ring_off, m->ring_v, m->ring8); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->rings_valid = true;
+    return 0;
+}
+
+
+int tm_ensure_ring2(tm_mesh* m) {
+    if (tm_ensure_rings(m)) return 1;
+    if (m->ex2_off && m->ex2_epoch == m->topo_epoch) return 0;
+    const int V = m->V, nb = (V + 127) / 128;
+    if (!m->ex2_off) TM_CUDA(cudaMalloc(&m->ex2_off, sizeof(int) * ((size_t)V + 2)));
+    int* err = m->ex2_off + V + 1;
+    TM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), m->stream));
+    k_ring2_count<<<nb, 128, 0, m->stream>>>(V, m->ring_off, m->ring_v, m->ex2_off, err); TM_LAUNCHED();
+    int herr = 0;
+    TM_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    long long total = 0;
+    if (tm_exclusive_scan(m, m->ex2_off, m->ex2_off, V, &total)) return 1;   // syncs the stream
+    TM_CHECK(herr == 0, "a vertex has more than %d vertices within two rings", RING2_CAP);
+    if (m->ex2_v) { cudaFree(m->ex2_v); m->ex2_v = nullptr; }
+    TM_CUDA(cudaMalloc(&m->ex2_v, sizeof(int) * (size_t)(total > 0 ? total : 1)));
+    k_ring2_fill<<<nb, 128, 0, m->stream>>>(V, m->ring_off, m->ring_v, m->ex2_off, m->ex2_v); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    m->ex2_epoch = m->topo_epoch;
     return 0;
 }
