@@ -40,47 +40,66 @@ def env_int(name, default):
         return default
 
 
+_POLLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+while True:
+    try:
+        print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+              nv.nvmlDeviceGetCurrentClocksThrottleReasons(h), flush=True)
+    except Exception as exc:
+        print("ERR", repr(exc), flush=True)
+        break
+    time.sleep(0.005)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md). NVML is
+    polled every 5 ms from a separate PROCESS: the timed loops are ~10-100 ms long (too short for
+    `nvidia-smi -lms`), and a sampling thread in this process would fight the e2e loop for the GIL."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.proc = gpu, None
+
+    @staticmethod
+    def _nvml_index(gpu):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if gpu < len(ids) and ids[gpu].strip().isdigit():
+                return int(ids[gpu])
+        return gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLLER, str(self._nvml_index(self.gpu))],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc.stdout.readline()            # first sample = the poller is up
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml poller unavailable"]}
         self.proc.terminate()
         try:
-            self.proc.wait(timeout=2)
+            out, _ = self.proc.communicate(timeout=3)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+            out, _ = self.proc.communicate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            if len(r) < 9:
+        for line in out.splitlines():
+            f = line.split()
+            if len(f) != 3 or f[0] == "ERR":
                 continue
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if r[col].lower().startswith("active"):
+            sm.append(float(f[0])); mx.append(float(f[1]))
+            for name, bit in self.REASONS:
+                if int(f[2]) & bit:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
@@ -222,10 +241,11 @@ def main():
         total_ms += cm.timer_stop()
     barrier()
     launches = cabi.lib().tm_launch_count() - launches0
-    clocks = sampler.stop()
 
-    # dominant kernel: gather gradient sweep, timed alone, L2 flushed before every launch
-    k_ms = [cm.time_kernel(nl, p, w, max(10, min(args.steps, 50)), FLUSH_BYTES) for w in (0, 1, 2)]
+    # sweep sets timed alone, L2 flushed before every launch: energy() sweeps (ring properties +
+    # pair sweep + reduction), the gradient's own property sweep, the ring gradient kernel
+    # (dominant single kernel), the pair sweep
+    k_ms = [cm.time_kernel(nl, p, w, max(10, min(args.steps, 50)), FLUSH_BYTES) for w in (0, 1, 2, 3)]
     # verlet-list rebuild (update_repulsion), device resident
     reb = []
     for _ in range(3):
@@ -249,6 +269,7 @@ def main():
         e_last, g_last = eg_api(k)
     barrier()
     e2e_s = time.time() - t0
+    clocks = sampler.stop()       # covers the device-resident loop, the per-kernel timings and the e2e loop
 
     # parity spot check of the timed configuration against itself through both boundaries
     e_dev, _ = cm.energy(nl, p)
@@ -277,7 +298,9 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         ms_step = total_ms / args.steps
         value = world * args.steps / (total_ms / 1e3)
-        alg_grad = workload.bytes_grad_sweep(P, True) * V          # bytes per launch of the gradient sweep
+        # k_grad: SURVEY 8(d) gradient sweep 2 without the list (84 B/vertex) + the stored pair force it
+        # reads instead (24 B/vertex); DESIGN.md section 4
+        alg_grad = (workload.bytes_grad_sweep(0.0, False) + 24.0) * V
         achieved = alg_grad / (k_ms[2] * 1e-3) / 1e9
         alg_eg = workload.bytes_eg(P, True) * V
         line = {
@@ -292,12 +315,13 @@ def main():
                     "h2d_bytes_per_step": 2 * V * 24, "d2h_bytes_per_step": V * 24 + 2 * 48,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_grad (gather gradient sweep incl. repulsion)",
+            "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_grad, "ms_per_launch": k_ms[2],
                          "eg_algorithmic_bytes": alg_eg, "eg_frac_of_peak": alg_eg / (ms_step * 1e-3) / 1e9 / peak,
-                         "kernel_ms": {"props_full": k_ms[0], "props_for_gradient": k_ms[1], "grad": k_ms[2]}},
+                         "kernel_ms": {"energy_sweeps": k_ms[0], "props_for_gradient": k_ms[1], "ring_grad": k_ms[2],
+                                       "pair_sweep": k_ms[3]}},
             "cpu_baseline": cpu,
             "mvertex_evals_per_s": value * V / 1e6,
             "verlet_rebuild_ms": float(np.median(reb)),

@@ -200,24 +200,109 @@ k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
 // ---- K1b: pair sweep: surface repulsion energy and force per vertex ------------------------
 // (mesh_repulsion.h:28-79 over NeighbourList::point_distances). force[i] = sum_j slope_ij (x_i - x_j);
 // the gradient sweep adds 2 kappa_r force[i] (mesh_properties.cpp:139-146).
-constexpr int PAIR_THREADS = 128;
-template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS>
-__global__ void __launch_bounds__(PAIR_THREADS)
+//
+// The inner loop is written for instruction count (the kernel is fp64-issue-bound): branch-free
+// evaluation with the inactive lanes masked at the end (a warp executes an instruction whenever
+// one lane needs it, so skipping buys nothing and the reconvergence bookkeeping costs), the
+// exponential's coefficients and all loop invariants in registers, one 256-bit read-only load
+// per neighbour.
+struct PairConst {
+    double lc1, lc1sq, rd;      // cut-off, its square, (double) r
+    double ec[12];              // exp polynomial (tm_math::EXP_C)
+};
+
+// phi = exp(l/(l-lc1)) / l^r and slope = -(lc1/(l-lc1)^2 + r/l) / l^(r+1) * exp(l/(l-lc1)) for l2 < lc1^2,
+// both 0 for inactive entries. R2: r == 2 (the default exponent) without the power loop.
+template <bool R2>
+__device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2, bool active, double& phi, double& sl) {
+    const double l2s = active ? l2 : C.lc1sq * 0.25;          // any harmless in-range value
+    const double il = rsqrt_pos(l2s);
+    const double l = l2s * il;
+    double dl = l - C.lc1;                                    // < 0; guard the rounding corner l2 < lc1^2 <= l^2
+    dl = dl < -1.0e-300 ? dl : -1.0e-300;
+    const double w = rcp_pos(dl);
+    // exp(l * w), argument <= 0 (tm_math::exp_nonpos with the coefficients in registers)
+    const double t = l * w;
+    const double MAGIC = 6755399441055744.0;
+    double kd = fma(t, 1.4426950408889634, MAGIC);
+    const int k = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -6.93147180369123816490e-01, t);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = C.ec[0];
+#pragma unroll
+    for (int q = 1; q < 12; q++) p = fma(p, r, C.ec[q]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double ex = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    ex = (active && t >= -708.0) ? ex : 0.0;
+    const double ilr = R2 ? il * il : powi(il, rr);
+    phi = ex * ilr;
+    sl = -fma(C.lc1 * w, w, C.rd * il) * (phi * il);
+}
+
+#ifndef TM_PAIR_NT
+#define TM_PAIR_NT 128
+#endif
+#ifndef TM_PAIR_MINB
+#define TM_PAIR_MINB 4
+#endif
+#ifndef TM_PAIR_BATCH
+#define TM_PAIR_BATCH 4
+#endif
+constexpr int PAIR_THREADS = TM_PAIR_NT;
+constexpr int PB = TM_PAIR_BATCH;
+template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2>
+__global__ void __launch_bounds__(PAIR_THREADS, TM_PAIR_MINB)
 k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
         double* __restrict__ partials, int nwarps) {
     const int i = blockIdx.x * PAIR_THREADS + threadIdx.x;
     double rep = 0.0;
     if (i < mv.V) {
-        const d3 xi = ldpos(mv.pos, i);
+        PairConst C;
+        C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
+#pragma unroll
+        for (int q = 0; q < 12; q++) C.ec[q] = tm_math::EXP_C[q];
+        const P4 ri = ldrec(mv.pos, i);
+        const d3 xi = mk3(ri.x, ri.y, ri.z);
         d3 gr = mk3(0, 0, 0);
-        auto pair = [&rep, &gr, lc1, rr](d3 dv, double l2) {
-            double sl;
-            const double phi = repulsion_pair<WITH_F>(l2, lc1, rr, sl);
-            if (WITH_E) rep += phi;
-            if (WITH_F) axpy3(gr, sl, dv);
-        };
-        if (nl.kind == TM_NLIST_VERLET) verlet_pairs<false>(mv.pos, nl, i, xi, lc1 * lc1, pair);
-        else for_each_pair_fast<false, false>(mv, nl, i, xi, lc1 * lc1, [&pair](int, d3 dv, double l2) { pair(dv, l2); });
+        if (nl.kind == TM_NLIST_VERLET) {
+            const int e = nl.row_cnt[i];
+            const int* col = nl.row_j + tm_row_base(i, nl.row_cap);
+            for (int k = 0; k < e; k += PB) {
+                int j[PB];
+                j[0] = __ldg(col + k * 32);
+#pragma unroll
+                for (int u = 1; u < PB; u++) j[u] = (k + u < e) ? __ldg(col + (k + u) * 32) : j[0];
+                P4 x[PB];
+#pragma unroll
+                for (int u = 0; u < PB; u++) x[u] = ldrec(mv.pos, j[u]);
+#pragma unroll
+                for (int u = 0; u < PB; u++) {
+                    const d3 dv = xi - mk3(x[u].x, x[u].y, x[u].z);
+                    const double l2 = dot3(dv, dv);
+                    double phi, sl;
+#ifdef TM_PAIR_BRANCHY
+                    if ((k + u < e) && (l2 < C.lc1sq)) {
+                        pair_eval<R2>(C, rr, l2, true, phi, sl);
+                        if (WITH_E) rep += phi;
+                        if (WITH_F) axpy3(gr, sl, dv);
+                    }
+#else
+                    pair_eval<R2>(C, rr, l2, (k + u < e) && (l2 < C.lc1sq), phi, sl);
+                    if (WITH_E) rep += phi;
+                    if (WITH_F) axpy3(gr, sl, dv);
+#endif
+                }
+            }
+        } else {
+            for_each_pair_fast<false, true>(mv, nl, i, xi, C.lc1sq, [&](int, d3 dv, double l2) {
+                double phi, sl;
+                pair_eval<R2>(C, rr, l2, true, phi, sl);
+                if (WITH_E) rep += phi;
+                if (WITH_F) axpy3(gr, sl, dv);
+            });
+        }
         if (WITH_F) {
             double* o = force + 3 * (size_t)i;
             o[0] = gr.x; o[1] = gr.y; o[2] = gr.z;
@@ -476,12 +561,13 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
     const int nb = (m->V + PAIR_THREADS - 1) / PAIR_THREADS;
     MeshView mv = m->view();
-    if (write_vprops)
-        k_pairs<true, true, true><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps);
-    else if (with_e)
-        k_pairs<true, true, false><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, nullptr, m->partials, nwarps);
-    else
-        k_pairs<false, true, false><<<nb, PAIR_THREADS, 0, m->stream>>>(mv, nl, p.rep_lc1, p.rep_r, m->frep, nullptr, m->partials, nwarps);
+#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, 0, m->stream>>>( \
+        mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps)
+    const bool r2 = p.rep_r == 2;
+    if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
+    else if (with_e)  { if (r2) TM_PAIRS(true, true, false, true); else TM_PAIRS(true, true, false, false); }
+    else              { if (r2) TM_PAIRS(false, true, false, true); else TM_PAIRS(false, true, false, false); }
+#undef TM_PAIRS
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;

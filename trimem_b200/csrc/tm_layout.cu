@@ -134,14 +134,27 @@ __global__ void k_gather_int(int n, const int* __restrict__ in, const int* __res
     if (k < n) out[k] = in[map[k]];
 }
 
+// changed (optional): set to 1 when any coordinate differs bitwise from the record it replaces.
 __global__ void k_import_positions(int V, const double* __restrict__ x3, const int* __restrict__ d2h,
-                                   P4* __restrict__ pos) {
+                                   P4* __restrict__ pos, int* __restrict__ changed) {
     int d = blockIdx.x * NT + threadIdx.x;
-    if (d >= V) return;
-    const double* s = x3 + 3 * (size_t)d2h[d];
-    // rho (.w) is left alone: it belongs to the last property sweep
-    *reinterpret_cast<double2*>(pos + d) = make_double2(s[0], s[1]);
-    pos[d].z = s[2];
+    bool diff = false;
+    if (d < V) {
+        const double* s = x3 + 3 * (size_t)d2h[d];
+        const double sx = s[0], sy = s[1], sz = s[2];
+        if (changed) {
+            const d3 old = ldpos(pos, d);
+            diff = __double_as_longlong(old.x) != __double_as_longlong(sx) ||
+                   __double_as_longlong(old.y) != __double_as_longlong(sy) ||
+                   __double_as_longlong(old.z) != __double_as_longlong(sz);
+        }
+        // rho (.w) is left alone: it belongs to the last property sweep
+        if (!changed || diff) {
+            *reinterpret_cast<double2*>(pos + d) = make_double2(sx, sy);
+            pos[d].z = sz;
+        }
+    }
+    if (changed && __any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) *changed = 1;
 }
 
 __global__ void k_export_positions(int V, const P4* __restrict__ pos, const int* __restrict__ d2h,
@@ -258,10 +271,25 @@ int tm_ensure_layout(tm_mesh* m) {
         m->topo_epoch++;
     }
     if (m->stage_pending) {
-        k_import_positions<<<vb, NT, 0, m->stream>>>(V, m->xio3, m->d2h, m->pos); TM_LAUNCHED();
+        // Positions cross the C ABI on every evaluation (the caller may have written through
+        // TriMesh.points()). When results cached for the current positions exist (the sums / rho
+        // of a property sweep, the pair force), compare while importing: an unchanged upload --
+        // energy() then gradient() at one position, the usual pair -- keeps them valid.
+        const bool have_cache = m->geo_epoch == m->pos_epoch || m->frep_epoch == m->pos_epoch;
+        if (have_cache) {
+            int* flag = reinterpret_cast<int*>(m->ticket) + 2;
+            TM_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), m->stream));
+            k_import_positions<<<vb, NT, 0, m->stream>>>(V, m->xio3, m->d2h, m->pos, flag); TM_LAUNCHED();
+            int changed = 1;
+            TM_CUDA(cudaMemcpyAsync(&changed, flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+            TM_CUDA(cudaStreamSynchronize(m->stream));
+            if (changed) m->pos_epoch++;
+        } else {
+            k_import_positions<<<vb, NT, 0, m->stream>>>(V, m->xio3, m->d2h, m->pos, nullptr); TM_LAUNCHED();
+            m->pos_epoch++;
+        }
         TM_CUDA(cudaGetLastError());
         m->stage_pending = false;
-        m->pos_epoch++;
     }
     return tm_ensure_rings(m);
 }
