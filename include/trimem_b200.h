@@ -177,6 +177,63 @@ int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* 
 int tm_mesh_is_flip_ok(tm_mesh* m, int edge, int* ok);
 int tm_mesh_flip(tm_mesh* m, int edge);
 
+/* ---- velocity-Verlet trajectory, device resident   ---------------
+ * Replaces _vv_integration (src/trimem/mc/hmc.py:14-26) and the two Hamiltonian
+ * evaluations of HMC._step (hmc.py:129-155): positions, momenta and gradients stay
+ * in HBM for the n_steps steps; the neighbour list is fixed during a trajectory, as
+ * in the reference (update_repulsion runs in the per-move callback,
+ * mc/evaluators.py:181-182). Momenta are (V,3) in the caller's vertex numbering.   */
+int tm_mesh_set_momenta(tm_mesh* m, const double* p);
+int tm_mesh_get_momenta(tm_mesh* m, double* p);
+/* x, p <- n_steps velocity-Verlet steps from the mesh's current device positions and
+ * momenta, force = -gradient of the functional `params` describes; asynchronous.
+ * with_energies != 0 also evaluates U(x0), U(xN) (the full sweeps replace the
+ * geometry-only ones at both ends; nothing is evaluated twice) and the kinetic
+ * energies 0.5 p.p / mass.                                                          */
+int tm_vv_integrate_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double mass, double dt,
+                          int n_steps, int with_energies);
+/* waits; stats = { U(x0), K(p0), U(xN), K(pN) }, props0/props1 (optional) the reduced
+ * properties at both ends. On a partitioned mesh K is the owned vertices' share.     */
+int tm_vv_stats(tm_mesh* m, const tm_energy_params* p, double stats[4], double props0[6], double props1[6]);
+/* the synchronous whole: upload p0, integrate, download x (optional), p (optional),
+ * stats (optional; NULL skips the energy sweeps)                                     */
+int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const double* p0, double mass,
+                    double dt, int n_steps, double* x_out, double* p_out, double stats[4]);
+
+/* ---- one mesh partitioned across devices  (BASELINE.json config 4) ----
+ * No reference counterpart (its sweeps are OpenMP loops in one address space,
+ * src/kernel.h:243-262). Every rank holds the whole mesh, owns a contiguous slice of
+ * the (Morton-ordered) vertices, evaluates / integrates / reports only those, reads
+ * halo positions straight from the owners' memory over NVLink and adds the ranks'
+ * reduced sums in rank order (csrc/tm_part.cu). Every rank must make the same
+ * sequence of evaluation calls. After tm_part_create:
+ *   tm_energy / tm_properties      global sums, identical bits on every rank
+ *   tm_gradient / tm_fetch_gradient, tm_mesh_get_momenta
+ *                                  rows of the owned vertices, zeros elsewhere
+ *   tm_mesh_get_positions, tm_nlist_create
+ *                                  first bring every rank's whole array up to date
+ *   flips, per-vertex queries      operate on the whole replicated mesh            */
+int tm_part_create(tm_mesh* m, int rank, int nranks);
+int tm_part_info(tm_mesh* m, int* rank, int* nranks, int* first_slot, int* n_owned, int* n_ghost_ring1, int* n_pull);
+/* peers in other processes: 128 opaque bytes (two cudaIpcMemHandle_t) to pass around */
+int tm_part_export(tm_mesh* m, unsigned char handle[128]);
+int tm_part_attach_ipc(tm_mesh* m, int peer_rank, const unsigned char handle[128]);
+/* peers in this process (other device, or the same one in tests)                    */
+int tm_part_attach_local(tm_mesh* m, int peer_rank, tm_mesh* peer);
+/* local: halo lists and every on-demand buffer, so that no allocation happens
+ * between the collective calls that follow                                          */
+int tm_part_prepare(tm_mesh* m, tm_nlist* nl);
+/* collective: the whole position array of every rank becomes current                */
+int tm_part_sync_positions(tm_mesh* m);
+/* collective: out[q] = sum over ranks of in[q], added in rank order (the path the
+ * property sums take; tests)                                                        */
+int tm_part_allsum6(tm_mesh* m, const double in[6], double out[6]);
+/* diagnostics: the rank's sequencing block {pos_seq, sums_seq, error, host-side pos_seq,
+ * host-side sums_seq, ack[0..16)}                                                    */
+int tm_part_debug(tm_mesh* m, unsigned long long out[21]);
+/* syncs the mesh's stream and reports an exchange time-out, if any                  */
+int tm_part_check(tm_mesh* m);
+
 #ifdef __cplusplus
 }
 #endif

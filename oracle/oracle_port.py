@@ -258,6 +258,31 @@ class EnergyManager:
         return flags, ener, props
 
 
+def vv_integration(mesh, estore, p0, mass, dt, n_steps):
+    """Restatement of _vv_integration (src/trimem/mc/hmc.py:14-26) with force = -gradient evaluated
+    the way mc/evaluators.py:104-107,139-156 does (positions written into the mesh, then
+    EnergyManager.gradient). Returns (x, p, [U(x0), K(p0), U(xN), K(pN)]); the mesh is restored."""
+    x0 = mesh.points().copy()
+
+    def force(x):
+        np.copyto(mesh.points(), x)
+        return -estore.gradient(mesh)
+
+    u0 = estore.energy(mesh)
+    x, p = x0, np.asarray(p0, dtype=np.float64)
+    a = force(x)
+    for _ in range(n_steps):
+        x = x + (p * dt + 0.5 * a * dt**2) / mass
+        an = force(x)
+        p = p + 0.5 * (a + an) * dt
+        a = an
+    np.copyto(mesh.points(), x)
+    u1 = estore.energy(mesh)
+    np.copyto(mesh.points(), x0)
+    stats = np.array([u0, 0.5 * p0.ravel().dot(p0.ravel()) / mass, u1, 0.5 * p.ravel().dot(p.ravel()) / mass])
+    return x, p, stats
+
+
 def params_from(core_params):
     """Flat dict from a trimem.core-style EnergyParams object (reference or product module)."""
     ep = core_params

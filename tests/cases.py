@@ -92,3 +92,20 @@ def flip_inputs(name):
     n_edges = 3 * len(v) - 6
     rng = np.random.default_rng(seed)
     return case, rng.integers(0, n_edges, n).astype(np.int32), rng.random(n)
+
+
+# velocity-Verlet trajectories (reference: _vv_integration, src/trimem/mc/hmc.py:14-26):
+# name -> (case, momentum seed, momentum scale, mass, time step, steps)
+VV_CASES = {
+    "vv_ico4_config1": ("ico4_config1", 11, 1.0, 1.0, 2.5e-5, 10),
+    "vv_ico4_stress_verlet2": ("ico4_stress_verlet2", 12, 1.0, 1.0, 2.5e-5, 10),
+    "vv_ico4_stress_cell2": ("ico4_stress_cell2", 13, 2.0, 2.0, 2.0e-5, 6),
+    "vv_ico3_area": ("ico3_area", 14, 1.0, 1.0, 1.0e-3, 8),
+}
+
+
+def vv_inputs(name):
+    case, seed, scale, mass, dt, n = VV_CASES[name]
+    v, _ = mesh_of(case)
+    p0 = scale * np.random.default_rng(seed).normal(size=v.shape)
+    return case, p0, mass, dt, n

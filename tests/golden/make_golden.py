@@ -178,6 +178,44 @@ def flip_cases():
         save(name, **out)
 
 
+def reference_hmc_module():
+    """The reference's own Python integrator (src/trimem/mc/hmc.py), imported from where it lies
+    with the oracle build of trimem.core behind its `from .. import core`."""
+    import importlib.util
+    import types
+    pkg = types.ModuleType("trimem.mc")
+    pkg.__path__ = ["/root/reference/src/trimem/mc"]
+    sys.modules["trimem.mc"] = pkg
+    spec = importlib.util.spec_from_file_location("trimem.mc.hmc", "/root/reference/src/trimem/mc/hmc.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["trimem.mc.hmc"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def trajectory_cases():
+    hmc = reference_hmc_module()
+    for name in cases.VV_CASES:
+        case, p0, mass, dt, n = cases.vv_inputs(name)
+        mesh, es = cases.build(ref, case)
+        x0 = mesh.points().copy()
+
+        def force(x):                      # mc/evaluators.py:104-107,139-156: mesh.x = x ; -estore.gradient
+            np.copyto(mesh.points(), x)
+            return -es.gradient(mesh)
+
+        def nlog_prob(x):
+            np.copyto(mesh.points(), x)
+            return es.energy(mesh)
+
+        u0 = nlog_prob(x0)
+        xn, pn = hmc._vv_integration(x0, p0, force, mass, dt, n)
+        u1 = nlog_prob(xn)
+        k0 = 0.5 * p0.ravel().dot(p0.ravel()) / mass
+        k1 = 0.5 * pn.ravel().dot(pn.ravel()) / mass
+        save(name, x=xn, p=pn, stats=np.array([u0, k0, u1, k1]), moved=np.array([np.abs(xn - x0).max()]))
+
+
 def thread_spread():
     """The reference's own 1-vs-N-thread spread on the headline case (its noise floor)."""
     import subprocess
@@ -194,7 +232,7 @@ def thread_spread():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread"]
+    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory"]
     if "topology" in which: topology_cases()
     if "analytic" in which: analytic_cases()
     if "primitives" in which: primitive_cases()
@@ -202,3 +240,4 @@ if __name__ == "__main__":
     if "flips" in which: flip_cases()
     if "energy" in which: energy_cases()
     if "spread" in which: thread_spread()
+    if "trajectory" in which: trajectory_cases()

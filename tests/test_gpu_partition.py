@@ -1,0 +1,159 @@
+"""One mesh partitioned across ranks (tm_part_*): every rank owns a slice of the
+vertices, reads halo positions from the owners' arrays and adds the ranks' reduced sums in rank
+order. Here the ranks are mesh handles of ONE process on ONE device (peer pointers attached
+directly); tests/test_gpu_partition_ipc.py runs the same path with one process per rank over
+cudaIpc handles. Parity: sums / energy 1e-10 relative against the reference's golden values,
+gradient rows 1e-10 norm-wise, trajectories against the reference's integrator as in
+test_gpu_trajectory.py; all ranks must agree on the global sums bit for bit."""
+import numpy as np
+import pytest
+
+import cases
+from trimem_b200 import cabi, workload
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def nrm(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+class Ranks:
+    def __init__(self, core, case, nranks, n_search=None, x=None):
+        self.mesh, self.es = cases.build(core, case)
+        self.v = self.mesh.points().copy() if x is None else x
+        arrs = self.mesh.halfedge_arrays()[:4]
+        rp = self.es.eparams.repulse_params
+        kind = cabi.NLIST_CELL if rp.n_search == "cell-list" else cabi.NLIST_VERLET
+        self.par = workload.abi_params(self.es)
+        self.cm = [cabi.Mesh(*arrs, xyz=self.v) for _ in range(nranks)]
+        for r, m in enumerate(self.cm):
+            m.part_create(r, nranks)
+        for r, m in enumerate(self.cm):
+            for q, o in enumerate(self.cm):
+                if q != r:
+                    m.part_attach_local(q, o)
+        self.nl = [cabi.NList(m, kind, rp.rlist, rp.exclusion_level) for m in self.cm]
+        for m, nl in zip(self.cm, self.nl):
+            m.part_prepare(nl)          # all local allocation before any collective call
+        self.n = nranks
+
+    def each(self, fn):
+        """fn(mesh, nlist) on every rank, one host thread per rank (as one process per rank would):
+        collective calls wait for their peers on the device, so the ranks' launches must not be
+        serialised behind each other on the host."""
+        import threading
+        out, err = [None] * self.n, [None] * self.n
+
+        def run(r):
+            try:
+                out[r] = fn(self.cm[r], self.nl[r])
+            except BaseException as exc:      # noqa: BLE001  (re-raised in the caller's thread)
+                err[r] = exc
+        th = [threading.Thread(target=run, args=(r,)) for r in range(self.n)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+
+@pytest.mark.parametrize("case,nranks", [("ico4_stress_verlet2", 2), ("ico4_stress_verlet2", 3), ("ico4_stress_cell2", 2),
+                                         ("ico4_config1", 4), ("ico4_area_stress", 2), ("ico6_stress_verlet2", 8)])
+def test_energy_gradient_partitioned(gpu_core, case, nranks):
+    gold = cases.load_golden(case)
+    R = Ranks(gpu_core, case, nranks)
+    info = [m.part_info() for m in R.cm]
+    V = R.cm[0].V
+    assert sum(i["count"] for i in info) == V and info[0]["first"] == 0
+    assert all(i["first"] % 32 == 0 for i in info)
+    assert all(0 < i["n_ghost1"] <= i["n_pull"] < V for i in info)
+    # asynchronous on every rank, then fetch: nothing may block on a peer that has not been launched
+    R.each(lambda m, nl: m.energy_async(nl, R.par))
+    res = R.each(lambda m, nl: m.fetch_energy(R.par))
+    for e, props in res:
+        assert e == res[0][0] and np.array_equal(props, res[0][1])      # identical bits on every rank
+    e, props = res[0]
+    for q in range(6):
+        if gold["props"][q] == 0.0:
+            assert props[q] == 0.0
+        else:
+            assert abs(props[q] - gold["props"][q]) <= TOL * abs(gold["props"][q])
+    assert abs(e - float(gold["energy"])) <= TOL * abs(float(gold["energy"]))
+    R.each(lambda m, nl: m.gradient_async(nl, R.par))
+    gs = R.each(lambda m, nl: m.fetch_gradient())
+    # each rank reports the rows it owns and zeros elsewhere; the rows are disjoint
+    owned = [np.any(g != 0.0, axis=1) for g in gs]
+    assert np.all(np.sum(owned, axis=0) == 1)
+    g = np.sum(gs, axis=0)
+    if "grad" in gold:
+        assert nrm(g, gold["grad"]) < TOL
+    else:
+        rows = gold["rows"]
+        assert nrm(g[rows], gold["grad_rows"]) < TOL
+        assert abs(np.linalg.norm(g) - float(gold["grad_norm"])) <= TOL * float(gold["grad_norm"])
+
+
+@pytest.mark.parametrize("name,nranks", [("vv_ico4_stress_verlet2", 2), ("vv_ico4_stress_verlet2", 3),
+                                         ("vv_ico4_stress_cell2", 2), ("vv_ico4_config1", 4)])
+def test_trajectory_partitioned(gpu_core, name, nranks):
+    gold = cases.load_golden(name)
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    R = Ranks(gpu_core, case, nranks)
+    R.each(lambda m, nl: m.set_momenta(p0))
+    R.each(lambda m, nl: m.vv_integrate_async(nl, R.par, mass, dt, n, with_energies=True))
+    stats = R.each(lambda m, nl: m.vv_stats(R.par)[0])
+    ps = R.each(lambda m, nl: m.momenta())
+    xs = R.each(lambda m, nl: m.positions())            # collective: whole arrays become current
+    for x in xs:
+        assert np.array_equal(x, xs[0])
+    assert nrm(xs[0] - R.v, gold["x"] - R.v) < 1e-9
+    assert nrm(np.sum(ps, axis=0), gold["p"]) < 1e-9
+    st = np.array(stats)
+    assert np.all(st[:, 0] == st[0, 0]) and np.all(st[:, 2] == st[0, 2])
+    k0, k1 = st[:, 1].sum(), st[:, 3].sum()             # kinetic energy: each rank's owned share
+    want = gold["stats"]
+    assert abs(st[0, 0] - want[0]) <= TOL * abs(want[0]) and abs(k0 - want[1]) <= TOL * abs(want[1])
+    assert abs(st[0, 2] - want[2]) <= 10 * TOL * abs(want[2]) and abs(k1 - want[3]) <= 10 * TOL * abs(want[3])
+
+
+def test_rebuild_after_trajectory_and_allsum(gpu_core):
+    """A neighbour list rebuilt after a partitioned trajectory sees every rank's current positions
+    (tm_nlist_create pulls the far field first), and equals the list a single device builds."""
+    name = "vv_ico4_stress_verlet2"
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    R = Ranks(gpu_core, case, 2)
+    # the sums path itself: rank-ordered addition, same bits everywhere
+    vec = [np.arange(6) * 0.1 + r for r in range(2)]
+    res = R.each(lambda m, nl: m.part_allsum6(vec[m.part_info()["rank"]]))
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], vec[0] + vec[1])
+    R.each(lambda m, nl: m.set_momenta(p0))
+    R.each(lambda m, nl: m.vv_integrate_async(nl, R.par, mass, dt, n, with_energies=False))
+    rp = R.es.eparams.repulse_params
+    new = R.each(lambda m, nl: cabi.NList(m, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level))
+    # single-device list at the same end point
+    gold = cases.load_golden(name)
+    x_end = R.cm[0].positions()
+    arrs = R.mesh.halfedge_arrays()[:4]
+    one = cabi.Mesh(*arrs, xyz=x_end)
+    nl1 = cabi.NList(one, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    d1 = nl1.distance_matrix(rp.rlist)
+    for r in range(2):
+        d = new[r].distance_matrix(rp.rlist)
+        assert np.array_equal(d[1], d1[1]) and np.array_equal(d[2], d1[2])
+    assert nrm(x_end - R.v, gold["x"] - R.v) < 1e-9
+
+
+def test_partition_errors(gpu_core):
+    mesh, es = cases.build(gpu_core, "ico3_edge")
+    arrs = mesh.halfedge_arrays()[:4]
+    cm = cabi.Mesh(*arrs, xyz=mesh.points().copy())
+    with pytest.raises(cabi.TMError):
+        cm.part_create(2, 2)
+    cm.part_create(0, 2)
+    with pytest.raises(cabi.TMError):
+        cm.part_create(0, 2)
+    with pytest.raises(cabi.TMError, match="not every peer is attached"):
+        cm.energy_async(None, workload.abi_params(es))

@@ -1,0 +1,111 @@
+"""Device-resident velocity-Verlet trajectory (tm_vv_integrate, core.vv_integrate) against the
+reference's own Python integrator: the golden vectors were produced by running
+src/trimem/mc/hmc.py::_vv_integration on the reference build (tests/golden/make_golden.py
+trajectory_cases). Tolerances: the force agrees to 1e-10 norm-wise per evaluation (BASELINE.json);
+over the 6-10 steps of a case the end point's DISPLACEMENT and the momenta are held to 1e-9
+norm-wise, the energies to 1e-10 relative."""
+import numpy as np
+import pytest
+
+import cases
+from trimem_b200 import cabi, workload
+
+pytestmark = pytest.mark.gpu
+TOL_TRAJ = 1e-9
+TOL_E = 1e-10
+
+
+def nrm(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("name", list(cases.VV_CASES))
+def test_pybind_vv_integrate_vs_reference(gpu_core, name):
+    gold = cases.load_golden(name)
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    mesh, es = cases.build(gpu_core, case)
+    x0 = mesh.points().copy()
+    x, p, st = gpu_core.vv_integrate(mesh, es, p0, mass, dt, n)
+    assert np.array_equal(mesh.points(), x0)                 # the mesh itself is left alone
+    assert nrm(x - x0, gold["x"] - x0) < TOL_TRAJ
+    assert nrm(p, gold["p"]) < TOL_TRAJ
+    assert np.all(np.abs(st - gold["stats"]) <= TOL_E * np.abs(gold["stats"]) * np.array([1, 1, 10, 10]))
+    # the same trajectory driven from Python through energy()/gradient(), as the reference does it
+    def force(xx):
+        np.copyto(mesh.points(), xx)
+        return -es.gradient(mesh)
+    xr, pr, a = x0, p0, force(x0)
+    for _ in range(n):
+        xr = xr + (pr * dt + 0.5 * a * dt**2) / mass
+        an = force(xr)
+        pr = pr + 0.5 * (a + an) * dt
+        a = an
+    np.copyto(mesh.points(), x0)
+    # equal gradients -> bit-identical update arithmetic
+    assert np.array_equal(x, xr) and np.array_equal(p, pr)
+
+
+def test_c_abi_async_trajectory_and_port(gpu_core, port):
+    """Through the C ABI with the momenta resident on the device, against the oracle port."""
+    name = "vv_ico4_stress_verlet2"
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    v, f = cases.mesh_of(case)
+    pm = port.TriMesh(v, f)
+    pe = port.EnergyManager(pm, port.workload_params(pm, **cases.CASES[case][2]))
+    xr, pr, sr = port.vv_integration(pm, pe, p0, mass, dt, n)
+    mesh, es = cases.build(gpu_core, case)
+    he_to, he_next, he_face, v_he, _ = mesh.halfedge_arrays()
+    cm = cabi.Mesh(he_to, he_next, he_face, v_he, xyz=v)
+    rp = es.eparams.repulse_params
+    nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    par = workload.abi_params(es)
+    cm.set_momenta(p0)
+    assert np.array_equal(cm.momenta(), p0)
+    # in two legs: 4 steps, then the remaining ones (the state stays on the device in between)
+    cm.vv_integrate_async(nl, par, mass, dt, 4, with_energies=True)
+    st_a, _, _ = cm.vv_stats(par)
+    cm.vv_integrate_async(nl, par, mass, dt, n - 4, with_energies=True)
+    st_b, props0, props1 = cm.vv_stats(par)
+    x, p = cm.positions(), cm.momenta()
+    assert nrm(x - v, xr - v) < TOL_TRAJ and nrm(p, pr) < TOL_TRAJ
+    assert abs(st_a[0] - sr[0]) <= TOL_E * abs(sr[0]) and abs(st_a[1] - sr[1]) <= TOL_E * abs(sr[1])
+    assert abs(st_b[2] - sr[2]) <= 10 * TOL_E * abs(sr[2]) and abs(st_b[3] - sr[3]) <= 10 * TOL_E * abs(sr[3])
+    assert st_a[2] == st_b[0] and st_a[3] == st_b[1]        # leg 2 starts where leg 1 ended, same bits
+    # the energy the trajectory reports at its end is the energy of its end point
+    e, props = cm.energy(nl, par)
+    assert e == st_b[2] and np.array_equal(props, props1)
+
+
+@pytest.mark.parametrize("subdiv,n,dt", [(6, 10, 1.0e-6), (8, 5, 1.0e-7)])
+def test_reversibility_and_energy_conservation(gpu_core, subdiv, n, dt):
+    """Size-independent properties at BASELINE sizes: velocity Verlet is time reversible (integrate,
+    flip the momenta, integrate again -> the start) and conserves H = U + K to O(dt^2)."""
+    mesh, es, x0 = workload.make_case(gpu_core, subdiv, repulsion="stress", n_search="verlet-list")
+    V = mesh.n_vertices()
+    p0 = np.random.default_rng(5).normal(size=(V, 3))
+    mass = 1.0          # (the stress potential is stiff: the reference itself diverges at dt = 5e-6 here)
+    x1, p1, st = gpu_core.vv_integrate(mesh, es, p0, mass, dt, n)
+    h0, h1 = st[0] + st[1], st[2] + st[3]
+    assert abs(h1 - h0) < 2e-3 * abs(h0)
+    assert np.abs(x1 - x0).max() > 0
+    np.copyto(mesh.points(), x1)
+    x2, p2, st2 = gpu_core.vv_integrate(mesh, es, -p1, mass, dt, n)
+    assert np.linalg.norm(x2 - x0) < 1e-9 * np.linalg.norm(x1 - x0)
+    assert nrm(-p2, p0) < 1e-9
+    assert abs(st2[2] - st[0]) <= 1e-10 * abs(st[0])
+    # zero steps: nothing moves, energies of the start point
+    np.copyto(mesh.points(), x0)
+    x3, p3, st3 = gpu_core.vv_integrate(mesh, es, p0, mass, dt, 0)
+    assert np.array_equal(x3, x0) and np.array_equal(p3, p0) and st3[0] == st3[2] and st3[1] == st3[3]
+    assert abs(st3[0] - es.energy(mesh)) <= 1e-12 * abs(st3[0])
+
+
+def test_argument_errors(gpu_core):
+    mesh, es = cases.build(gpu_core, "ico3_edge")
+    p0 = np.zeros((mesh.n_vertices(), 3))
+    with pytest.raises(RuntimeError):
+        gpu_core.vv_integrate(mesh, es, p0[:-1], 1.0, 1e-4, 2)
+    with pytest.raises(RuntimeError):
+        gpu_core.vv_integrate(mesh, es, p0, 0.0, 1e-4, 2)
+    with pytest.raises(RuntimeError):
+        gpu_core.vv_integrate(mesh, es, p0, 1.0, 1e-4, -1)

@@ -185,3 +185,20 @@ def test_port_matches_reference_build_live(port, refmod):
     assert rel(eo.energy(mo), ea.energy(ma)) < TOL
     ga, go = ea.gradient(ma), eo.gradient(mo)
     assert np.linalg.norm(ga - go) / np.linalg.norm(ga) < TOL
+
+
+@pytest.mark.parametrize("name", list(cases.VV_CASES))
+def test_port_trajectory_vs_reference_integrator(port, name):
+    """oracle_port.vv_integration (restatement of src/trimem/mc/hmc.py:14-26) against the reference's
+    own _vv_integration run on the reference build (tests/golden/make_golden.py trajectory_cases)."""
+    gold = cases.load_golden(name)
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    v, f = cases.mesh_of(case)
+    pm = port.TriMesh(v, f)
+    pe = port.EnergyManager(pm, port.workload_params(pm, **cases.CASES[case][2]))
+    x, p, st = port.vv_integration(pm, pe, p0, mass, dt, n)
+    assert float(gold["moved"][0]) > 1e-4                    # the trajectory goes somewhere
+    assert np.linalg.norm((x - v) - (gold["x"] - v)) <= 1e-10 * np.linalg.norm(gold["x"] - v)
+    assert np.linalg.norm(p - gold["p"]) <= 1e-10 * np.linalg.norm(gold["p"])
+    assert np.all(np.abs(st - gold["stats"]) <= 1e-10 * np.abs(gold["stats"]))
+    assert np.array_equal(pm.points(), v)

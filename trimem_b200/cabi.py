@@ -94,6 +94,21 @@ def lib():
     L.tm_edge_vertex_properties.argtypes = [vp, vp, pp, C.c_int, _dp]
     L.tm_mesh_is_flip_ok.argtypes = [vp, C.c_int, _ip]
     L.tm_mesh_flip.argtypes = [vp, C.c_int]
+    L.tm_mesh_set_momenta.argtypes = [vp, _dp]
+    L.tm_mesh_get_momenta.argtypes = [vp, _dp]
+    L.tm_vv_integrate_async.argtypes = [vp, vp, pp, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.tm_vv_stats.argtypes = [vp, pp, _dp, _dp, _dp]
+    L.tm_vv_integrate.argtypes = [vp, vp, pp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+    L.tm_part_create.argtypes = [vp, C.c_int, C.c_int]
+    L.tm_part_info.argtypes = [vp, _ip, _ip, _ip, _ip, _ip, _ip]
+    L.tm_part_export.argtypes = [vp, C.c_char_p]
+    L.tm_part_attach_ipc.argtypes = [vp, C.c_int, C.c_char_p]
+    L.tm_part_attach_local.argtypes = [vp, C.c_int, vp]
+    L.tm_part_prepare.argtypes = [vp, vp]
+    L.tm_part_sync_positions.argtypes = [vp]
+    L.tm_part_allsum6.argtypes = [vp, _dp, _dp]
+    L.tm_part_check.argtypes = [vp]
+    L.tm_part_debug.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 
@@ -249,6 +264,90 @@ class Mesh:
 
     def flip(self, edge):
         _chk(lib().tm_mesh_flip(self.h, edge))
+
+    # ---- velocity-Verlet trajectory (device resident) ----
+    def set_momenta(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        assert p.shape == (self.V, 3)
+        _chk(lib().tm_mesh_set_momenta(self.h, _d(p)))
+
+    def momenta(self):
+        p = np.zeros((self.V, 3))
+        _chk(lib().tm_mesh_get_momenta(self.h, _d(p)))
+        return p
+
+    def vv_integrate_async(self, nl, p, mass, dt, n_steps, with_energies=False):
+        _chk(lib().tm_vv_integrate_async(self.h, nl.h if nl else None, C.byref(p), mass, dt, n_steps,
+                                         1 if with_energies else 0))
+
+    def vv_stats(self, p):
+        st, p0, p1 = np.empty(4), np.empty(6), np.empty(6)
+        _chk(lib().tm_vv_stats(self.h, C.byref(p), _d(st), _d(p0), _d(p1)))
+        return st, p0, p1
+
+    def vv_integrate(self, nl, p, p0, mass, dt, n_steps, stats=True):
+        """-> (x_new, p_new, [U0, K0, U1, K1] or None): n_steps of hmc.py's _vv_integration from the
+        mesh's current positions."""
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        assert p0.shape == (self.V, 3)
+        x, pn = np.zeros((self.V, 3)), np.zeros((self.V, 3))
+        st = np.empty(4) if stats else None
+        _chk(lib().tm_vv_integrate(self.h, nl.h if nl else None, C.byref(p), _d(p0), mass, dt, n_steps,
+                                   _d(x), _d(pn), _d(st) if stats else None))
+        return x, pn, st
+
+    # ---- one mesh partitioned across devices ----
+    def part_create(self, rank, nranks):
+        _chk(lib().tm_part_create(self.h, rank, nranks))
+
+    def part_info(self):
+        v = [C.c_int() for _ in range(6)]
+        _chk(lib().tm_part_info(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("rank", "nranks", "first", "count", "n_ghost1", "n_pull"), [x.value for x in v]))
+
+    def part_export(self):
+        buf = C.create_string_buffer(128)
+        _chk(lib().tm_part_export(self.h, buf))
+        return buf.raw
+
+    def part_attach_ipc(self, peer, handle):
+        assert len(handle) == 128
+        _chk(lib().tm_part_attach_ipc(self.h, peer, handle))
+
+    def part_attach_local(self, peer, other):
+        _chk(lib().tm_part_attach_local(self.h, peer, other.h))
+
+    def part_prepare(self, nl):
+        _chk(lib().tm_part_prepare(self.h, nl.h if nl else None))
+
+    def part_sync_positions(self):
+        _chk(lib().tm_part_sync_positions(self.h))
+
+    def part_allsum6(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty(6)
+        _chk(lib().tm_part_allsum6(self.h, _d(v), _d(out)))
+        return out
+
+    def part_debug(self):
+        out = (C.c_ulonglong * 21)()
+        _chk(lib().tm_part_debug(self.h, out))
+        v = list(out)
+        return dict(pos_seq=v[0], sums_seq=v[1], error=v[2], host_pos_seq=v[3], host_sums_seq=v[4], ack=v[5:])
+
+    def part_check(self):
+        _chk(lib().tm_part_check(self.h))
+
+    def fetch_energy(self, p):
+        e = C.c_double()
+        props = np.empty(6)
+        _chk(lib().tm_fetch_energy(self.h, C.byref(p), C.byref(e), _d(props)))
+        return e.value, props
+
+    def fetch_gradient(self):
+        g = np.zeros((self.V, 3))
+        _chk(lib().tm_fetch_gradient(self.h, _d(g)))
+        return g
 
 
 class NList:

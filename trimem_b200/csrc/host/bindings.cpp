@@ -350,6 +350,23 @@ PYBIND11_MODULE(core, m) {
           py::arg("mesh"), py::arg("estore"), py::arg("gradient"), py::arg("epsilon") = 1.0e-6,
           "Finite difference gradient of energy.");
 
+    // ---- device-resident trajectory (extension; replaces the Python loop of mc/hmc.py:14-26) -----------
+    m.def("vv_integrate",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, py::array_t<double, py::array::c_style | py::array::forcecast> p0,
+             double mass, double dt, int n_steps) {
+              const int n = mesh.n_vertices();
+              if (p0.size() != (py::ssize_t)3 * n)
+                  throw std::runtime_error("momenta must have 3 * n_vertices entries");
+              py::array_t<double> x = pinned_array(n, 3), pn = pinned_array(n, 3);
+              py::array_t<double> st(4);
+              vv_integrate(mesh, estore, p0.data(), mass, dt, n_steps, x.mutable_data(), pn.mutable_data(),
+                           st.mutable_data());
+              return py::make_tuple(x, pn, st);
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("p"), py::arg("mass"), py::arg("time_step"), py::arg("n_steps"),
+          "Velocity-Verlet integration of n_steps from mesh.points() with momenta p, force = -estore.gradient;\n"
+          "returns (x_new, p_new, [U(x0), K(p0), U(x_new), K(p_new)]). mesh.points() is not modified.");
+
     // ---- B200 extensions ----------------------------------------------------------------------------------
     m.def("device_count", []() { return tm_device_count(); });
     m.def("set_device", &set_default_device, py::arg("device"));

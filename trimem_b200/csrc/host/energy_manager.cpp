@@ -219,6 +219,14 @@ int flip_parallel_batches(HalfedgeMesh& mesh, EnergyManager& estore, double flip
     return flip_sweep(mesh, estore, flip_ratio, seed, TM_FLIP_BATCH);
 }
 
+// ------------------------------------------------------------------ trajectory --
+void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, double mass, double dt,
+                  int n_steps, double* x_out, double* p_out, double* stats) {
+    tm_energy_params p = estore.abi_params();
+    if (tm_vv_integrate(mesh.device(), estore.nlist_handle(), &p, p0, mass, dt, n_steps, x_out, p_out, stats))
+        fail();
+}
+
 // --------------------------------------------------------------- setup reductions --
 double area(HalfedgeMesh& mesh) {
     double a = 0, l = 0;

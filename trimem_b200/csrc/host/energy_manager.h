@@ -104,6 +104,14 @@ public:
 int flip_serial(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
 int flip_parallel_batches(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
 
+// ---- velocity-Verlet trajectory (src/trimem/mc/hmc.py:14-26, device resident) ------------
+// n_steps of _vv_integration from the mesh's current points() and the momenta p0 (n_vertices x 3);
+// x_out / p_out (n_vertices x 3) receive the end point, stats (optional) = {U(x0), K(p0), U(xN), K(pN)}.
+// The mesh's points() are left untouched, like the reference's evaluator-driven integration leaves
+// the decision to the Metropolis test.
+void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, double mass, double dt,
+                  int n_steps, double* x_out, double* p_out, double* stats);
+
 // ---- setup-time reductions (src/util.h) ------------------------------------------------
 double area(HalfedgeMesh& mesh);
 double edges_length(HalfedgeMesh& mesh);

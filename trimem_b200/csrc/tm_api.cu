@@ -72,6 +72,18 @@ void tm_pool_free(int device, void* p) {
     g_pool.cached_bytes[d] += bytes;
 }
 
+// trimem_energy (kernel.h:110-122) from the six reduced properties
+double tm_energy_from_props(const tm_energy_params& p, const double s[6]) {
+    double e = 0.0, d;
+    d = s[0] / p.ref_area - 1.0;      e += p.kappa_a * d * d;
+    d = s[1] / p.ref_volume - 1.0;    e += p.kappa_v * d * d;
+    d = s[2] / p.ref_curvature - 1.0; e += p.kappa_c * d * d;
+    e += p.kappa_t * s[4];
+    e += p.kappa_r * s[5];
+    e += p.kappa_b * s[3];
+    return e;
+}
+
 namespace {
 
 template <class T>
@@ -82,17 +94,7 @@ int dev_alloc(T** p, size_t n) {
     return 0;
 }
 
-// trimem_energy (kernel.h:110-122) from the six reduced properties
-double energy_from_props(const tm_energy_params& p, const double s[6]) {
-    double e = 0.0, d;
-    d = s[0] / p.ref_area - 1.0;      e += p.kappa_a * d * d;
-    d = s[1] / p.ref_volume - 1.0;    e += p.kappa_v * d * d;
-    d = s[2] / p.ref_curvature - 1.0; e += p.kappa_c * d * d;
-    e += p.kappa_t * s[4];
-    e += p.kappa_r * s[5];
-    e += p.kappa_b * s[3];
-    return e;
-}
+double energy_from_props(const tm_energy_params& p, const double s[6]) { return tm_energy_from_props(p, s); }
 
 // every compute entry: device selected, vertex order / device connectivity / staged positions
 // / one-ring table brought up to date (tm_layout.cu)
@@ -113,10 +115,11 @@ int check_params(const tm_energy_params* p) {
 NlView view_of(tm_nlist* nl) { return nl ? nl->view() : tm_no_nlist(); }
 
 int fetch_sums(tm_mesh* m, double out[6]) {
+    if (tm_part_quiesce(m)) return 1;
     TM_CUDA(cudaMemcpyAsync(m->h_sums, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     for (int q = 0; q < 6; q++) out[q] = m->h_sums[q];
-    return 0;
+    return tm_part_poll_error(m);
 }
 
 }  // namespace
@@ -191,6 +194,9 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); cudaFree(m->ex2_v);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
+    tm_part_release(m);
+    cudaFree(m->mom); cudaFree(m->grad_prev); cudaFree(m->dot_part); cudaFree(m->d_stats);
+    if (m->h_stats) cudaFreeHost(m->h_stats);
     cudaFreeHost(m->h_sums);
     cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
     cudaStreamDestroy(m->stream);
@@ -204,6 +210,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
     TM_CHECK(V > 0 && HE >= 0 && (HE % 2) == 0, "bad mesh sizes: %d vertices, %d half-edges", V, HE);
     TM_CHECK(V < TM_RING_FACE, "too many vertices (%d)", V);
     TM_CUDA(cudaSetDevice(m->device));
+    TM_CHECK(!(m->part && V != m->V), "a partitioned mesh cannot change its vertex count");
     if (V != m->V) {
         if (dev_alloc(&m->v_he, V) || dev_alloc(&m->v_he_h, V) || dev_alloc(&m->d2h, V) || dev_alloc(&m->h2d, V) ||
             dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) || dev_alloc(&m->ring8, V) ||
@@ -211,6 +218,9 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
             dev_alloc(&m->grad, 3 * (size_t)V))
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
+        if (m->mom) { cudaFree(m->mom); m->mom = nullptr; }
+        if (m->grad_prev) { cudaFree(m->grad_prev); m->grad_prev = nullptr; }
+        m->grad_epoch = 0;
         if (m->frep) { cudaFree(m->frep); m->frep = nullptr; }
         if (m->ex2_off) { cudaFree(m->ex2_off); m->ex2_off = nullptr; }
         m->frep_epoch = 0;
@@ -288,7 +298,8 @@ int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
 int tm_mesh_get_positions(tm_mesh* m, double* xyz) {
     if (check_mesh(m)) return 1;
     TM_CHECK(xyz != nullptr, "null positions");
-    if (tm_export_positions(m)) return 1;
+    if (tm_part_make_current(m)) return 1;
+    if (tm_export_positions(m) || tm_part_quiesce(m)) return 1;
     TM_CUDA(cudaMemcpyAsync(xyz, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
@@ -326,16 +337,16 @@ int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, doubl
 int tm_fetch_gradient(tm_mesh* m, double* grad) {
     if (check_mesh(m)) return 1;
     TM_CHECK(grad != nullptr, "null gradient buffer");
-    if (tm_export_gradient(m)) return 1;           // device order -> host vertex numbering
-    TM_CUDA(cudaMemcpyAsync(grad, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    // device order -> host vertex numbering; a partitioned mesh delivers the rows it owns, zeros elsewhere
+    if (tm_export_vec3_owned(m, m->grad, grad)) return 1;
     TM_CUDA(cudaStreamSynchronize(m->stream));
-    return 0;
+    return tm_part_poll_error(m);
 }
 
 int tm_sync(tm_mesh* m) {
     if (check_mesh(m, false)) return 1;
     TM_CUDA(cudaStreamSynchronize(m->stream));
-    return 0;
+    return tm_part_poll_error(m);
 }
 
 int tm_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double out[6]) {
@@ -364,10 +375,76 @@ int tm_energy(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* energ
 int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* grad, double props[6]) {
     if (tm_gradient_async(m, nl, p)) return 1;
     if (props) {
+        if (tm_part_quiesce(m)) return 1;
         TM_CUDA(cudaMemcpyAsync(m->h_sums, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     }
     if (tm_fetch_gradient(m, grad)) return 1;
     if (props) for (int q = 0; q < 6; q++) props[q] = m->h_sums[q];
+    return 0;
+}
+
+// ---------------------------------------------------- velocity-Verlet trajectory --
+int tm_mesh_set_momenta(tm_mesh* m, const double* p) {
+    if (check_mesh(m)) return 1;
+    TM_CHECK(p != nullptr, "null momenta");
+    if (tm_import_momenta(m, p)) return 1;
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_mesh_get_momenta(tm_mesh* m, double* p) {
+    if (check_mesh(m)) return 1;
+    TM_CHECK(p != nullptr, "null momenta");
+    TM_CHECK(m->mom != nullptr, "mesh has no momenta (call tm_mesh_set_momenta first)");
+    if (tm_export_vec3_owned(m, m->mom, p)) return 1;
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_vv_integrate_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double mass, double dt,
+                          int n_steps, int with_energies) {
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
+    TM_CHECK(n_steps >= 0, "negative number of integration steps");
+    TM_CHECK(mass > 0.0, "mass must be positive");
+    TM_CHECK(m->mom != nullptr, "mesh has no momenta (call tm_mesh_set_momenta first)");
+    return tm_vv_run(m, view_of(nl), *p, mass, dt, n_steps, with_energies != 0);
+}
+
+int tm_vv_stats(tm_mesh* m, const tm_energy_params* p, double stats[4], double props0[6], double props1[6]) {
+    if (check_mesh(m, false) || check_params(p)) return 1;
+    TM_CHECK(m->h_stats != nullptr && m->d_stats != nullptr, "no trajectory has been run on this mesh");
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    TM_CUDA(cudaMemcpyAsync(m->h_stats, m->d_stats, 16 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    TM_CUDA(cudaStreamSynchronize(m->stream));
+    if (tm_part_poll_error(m)) return 1;
+    if (stats) {
+        stats[0] = tm_energy_from_props(*p, m->h_stats);
+        stats[1] = m->h_stats[12];
+        stats[2] = tm_energy_from_props(*p, m->h_stats + 6);
+        stats[3] = m->h_stats[13];
+    }
+    if (props0) for (int q = 0; q < 6; q++) props0[q] = m->h_stats[q];
+    if (props1) for (int q = 0; q < 6; q++) props1[q] = m->h_stats[6 + q];
+    return 0;
+}
+
+int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const double* p0, double mass, double dt,
+                    int n_steps, double* x_out, double* p_out, double stats[4]) {
+    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
+    TM_CHECK(p0 != nullptr, "null momenta");
+    TM_CHECK(n_steps >= 0, "negative number of integration steps");
+    TM_CHECK(mass > 0.0, "mass must be positive");
+    if (tm_import_momenta(m, p0)) return 1;
+    if (tm_vv_run(m, view_of(nl), *p, mass, dt, n_steps, stats != nullptr)) return 1;
+    if (p_out && tm_export_vec3_owned(m, m->mom, p_out)) return 1;
+    if (x_out) {
+        if (tm_part_make_current(m)) return 1;
+        // xout3 is reused: the momentum copy above is ordered before this export on the stream
+        if (tm_export_positions(m) || tm_part_quiesce(m)) return 1;
+        TM_CUDA(cudaMemcpyAsync(x_out, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (stats) return tm_vv_stats(m, p, stats, nullptr, nullptr);
+    TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }
 

@@ -85,6 +85,14 @@ struct MeshView {
     const P4* pos;         // V packed (x, y, z, rho) records, device vertex numbering
 };
 
+// Vertices one sweep launch covers: device slots [first, first + count), or the explicit list
+// vlist[0..count) (ghost sweeps of a partitioned mesh, tm_part.cu). `first` is a multiple of 32,
+// so a warp's partial of a partitioned sweep is the same sum as in the single-device sweep.
+struct SweepRange {
+    int first, count;
+    const int* vlist;
+};
+
 struct NlView {
     int kind;              // -1: none, TM_NLIST_CELL, TM_NLIST_VERLET
     int excl;
@@ -131,6 +139,15 @@ struct tm_mesh {
     double* xout3 = nullptr;     // V*3 staging in HOST numbering: results on their way out
     double* vprops = nullptr;    // V*6 (allocated on demand)
     double* grad = nullptr;      // V*3 device numbering
+    // velocity-Verlet trajectory state (tm_integrate.cu; allocated on demand)
+    double* grad_prev = nullptr; // V*3 gradient at the previous trajectory point (ping-pong with grad)
+    double* mom = nullptr;       // V*3 momenta, device numbering
+    unsigned long long grad_epoch = 0;     // pos_epoch the content of `grad` was evaluated at
+    double* h_stats = nullptr;   // pinned, 16: energies / reduced properties a trajectory reports
+    double* dot_part = nullptr;  // block partials of the kinetic-energy reduction
+    double* d_stats = nullptr;   // 16: what h_stats receives, collected on the device during a trajectory
+    // vertex-partitioned evaluation across devices (tm_part.cu); nullptr = whole mesh on this device
+    struct tm_part* part = nullptr;
     double* frep = nullptr;      // V*3 pair force of the last pair sweep (allocated on demand)
     unsigned long long frep_epoch = 0;     // pos_epoch, potential and list it was evaluated for
     double frep_lc1 = 0; int frep_r = 0; unsigned long long frep_list = 0;
@@ -220,6 +237,32 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p);  // tm_energy.cu
 int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); // tm_energy.cu (force only)
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
+double tm_energy_from_props(const tm_energy_params& p, const double s[6]);    // tm_api.cu (kernel.h:110-122)
+int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
+              bool with_energies);                               // tm_integrate.cu
+int tm_import_momenta(tm_mesh* m, const double* p_host);         // tm_integrate.cu
+int tm_export_vec3_owned(tm_mesh* m, const double* dev, double* host);   // tm_integrate.cu (async copy)
+// vertices this device sweeps (whole mesh, or the owned slice of a partitioned mesh)   tm_part.cu
+SweepRange tm_owned_range(const tm_mesh* m);
+// partitioned mesh: ring-1 ghost property sweep list (rho of non-owned ring neighbours), exchange
+// of the locally reduced sums; no-ops returning 0 on an unpartitioned mesh                tm_part.cu
+SweepRange tm_ghost_range(const tm_mesh* m);
+double* tm_part_local_sums(tm_mesh* m);          // where k_reduce_props writes (m->sums if unpartitioned)
+int tm_part_exchange_sums(tm_mesh* m, int nq);   // publish local sums, add all ranks' in rank order -> m->sums
+int tm_part_positions_updated(tm_mesh* m);       // after a device-side update of the owned positions: halo pull
+int tm_part_before_update(tm_mesh* m);           // peers must have pulled the previous positions
+int tm_part_release(tm_mesh* m);
+// CUDA loads kernels lazily, and the first launch of a kernel may synchronise the context. A rank
+// whose stream waits (on the device) for a peer living in the SAME context would then hold up the
+// very launch it waits for, so a partitioned mesh loads every kernel of the path up front.
+int tm_preload_energy();      // tm_energy.cu
+int tm_preload_integrate();   // tm_integrate.cu
+int tm_preload_layout();      // tm_layout.cu
+#define TM_PRELOAD(k) do { cudaFuncAttributes a__; TM_CUDA(cudaFuncGetAttributes(&a__, k)); } while (0)
+int tm_part_refresh(tm_mesh* m, const NlView& nl);   // halo lists for the current connectivity / list (local)
+int tm_part_make_current(tm_mesh* m);            // full position exchange if the far field is stale
+int tm_part_quiesce(tm_mesh* m);                 // partitioned: drain the stream before enqueuing a copy
+int tm_part_poll_error(tm_mesh* m);              // syncs; reports an exchange time-out
 
 // ------------------------------------------------------------ device maths --
 #ifdef __CUDACC__

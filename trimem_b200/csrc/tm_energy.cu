@@ -158,10 +158,11 @@ __device__ __forceinline__ void ring_props_generic(const MeshView& mv, const Dev
 template <bool FULL, bool WRITE_VPROPS>
 __global__ void __launch_bounds__(TM_PROPS_THREADS, TM_PROPS_MINB)
 k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
-        double* __restrict__ partials, int nwarps, int nq) {
-    const int i = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
+        double* __restrict__ partials, int nwarps, int nq, SweepRange R) {
+    const int t = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
+    const int i = R.vlist ? (t < R.count ? R.vlist[t] : 0) : R.first + t;
     double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
-    if (i < mv.V) {
+    if (t < R.count) {
         const R8 row = ldrow(mv.ring8, i);
         const d3 xi = ldpos(mv.pos, i);
         double area = 0, vol = 0, curv = 0, teth = 0;
@@ -186,14 +187,14 @@ k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
     }
     // one partial per warp and quantity, fixed shuffle tree; quantity 5 (repulsion) belongs to
     // k_pairs and is written here (as 0) only when no pair sweep runs (nq == 6)
-    const int lane = threadIdx.x & 31, w = i >> 5;
+    const int lane = threadIdx.x & 31, w = t >> 5;
 #pragma unroll
     for (int q = 0; q < 6; q++) {
         if (q >= nq) break;
-        double t = acc[q];
+        double s = acc[q];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0 && w < nwarps) partials[(size_t)q * nwarps + w] = t;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && w < nwarps) partials[(size_t)q * nwarps + w] = s;
     }
 }
 
@@ -255,10 +256,11 @@ constexpr int PB = TM_PAIR_BATCH;
 template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2>
 __global__ void __launch_bounds__(PAIR_THREADS, TM_PAIR_MINB)
 k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
-        double* __restrict__ partials, int nwarps) {
-    const int i = blockIdx.x * PAIR_THREADS + threadIdx.x;
+        double* __restrict__ partials, int nwarps, SweepRange R) {
+    const int t = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    const int i = R.first + t;
     double rep = 0.0;
-    if (i < mv.V) {
+    if (t < R.count) {
         PairConst C;
         C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
 #pragma unroll
@@ -310,11 +312,11 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
         if (WRITE_VPROPS) vprops[6 * (size_t)i + 5] = rep;
     }
     if (WITH_E) {
-        const int lane = threadIdx.x & 31, w = i >> 5;
-        double t = rep;
+        const int lane = threadIdx.x & 31, w = t >> 5;
+        double s = rep;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0 && w < nwarps) partials[(size_t)5 * nwarps + w] = t;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && w < nwarps) partials[(size_t)5 * nwarps + w] = s;
     }
 }
 
@@ -513,9 +515,10 @@ __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevP
 // (x, y, z, rho) record.
 __global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
 k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
-       double* __restrict__ grad) {
-    const int i = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
-    if (i >= mv.V) return;
+       double* __restrict__ grad, SweepRange R) {
+    const int t = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
+    if (t >= R.count) return;
+    const int i = R.first + t;
 
     GradK K;
     K.fA = 2.0 * P.kappa_a / P.ref_area * (sums[0] / P.ref_area - 1.0);
@@ -559,10 +562,11 @@ static bool pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
                         int nwarps) {
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
-    const int nb = (m->V + PAIR_THREADS - 1) / PAIR_THREADS;
+    const SweepRange R = tm_owned_range(m);
+    const int nb = (R.count + PAIR_THREADS - 1) / PAIR_THREADS;
     MeshView mv = m->view();
 #define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, 0, m->stream>>>( \
-        mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps)
+        mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
     else if (with_e)  { if (r2) TM_PAIRS(true, true, false, true); else TM_PAIRS(true, true, false, false); }
@@ -576,9 +580,10 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
 }
 
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
-    if (tm_ensure_layout(m)) return 1;
-    const int nb = (m->V + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
-    const int nwarps = (m->V + 31) / 32;
+    if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
+    const SweepRange R = tm_owned_range(m);
+    const int nb = (R.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
+    const int nwarps = (R.count + 31) / 32;
     const size_t need = 6 * (size_t)nwarps + 6 * TM_REDUCE_BLOCKS;
     if (m->partials_n < need) {
         if (m->partials) cudaFree(m->partials);
@@ -597,20 +602,30 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     if (write_vprops) {
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
         TM_CUDA(cudaMemsetAsync(m->vprops, 0, sizeof(double) * 6 * (size_t)m->V, m->stream));
-        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq);
+        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq, R);
     } else if (full) {
-        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq);
+        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
     } else {
-        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq);
+        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
     }
     TM_LAUNCHED();
+    // partitioned mesh: rho of the non-owned ring neighbours of owned vertices (the gradient
+    // sweep reads it) from a second, list-driven launch that reduces nothing
+    const SweepRange G = tm_ghost_range(m);
+    if (G.count > 0) {
+        k_props<false, false><<<(G.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS, TM_PROPS_THREADS, 0, m->stream>>>(
+            mv, P, m->pos, nullptr, m->partials, 0, 0, G);
+        TM_LAUNCHED();
+    }
     if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps)) return 1;
     int rb = (nwarps + 4 * RT - 1) / (4 * RT);
     rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
     const int per = (nwarps + rb - 1) / rb;
-    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, nwarps, per, full ? 6 : 4, block_sums, m->ticket, m->sums);
+    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, nwarps, per, full ? 6 : 4, block_sums, m->ticket,
+                                            tm_part_local_sums(m));
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
+    if (tm_part_exchange_sums(m, full ? 6 : 4)) return 1;
     m->geo_epoch = m->pos_epoch;        // sums[0..2] and rho now belong to the current positions
     return 0;
 }
@@ -622,13 +637,24 @@ int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
 }
 
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
-    if (tm_ensure_layout(m)) return 1;
+    if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
     if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
-    int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
+    const SweepRange R = tm_owned_range(m);
+    int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     DevParams P = tm_to_dev(p);
-    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, pairs ? m->frep : nullptr, m->grad);
+    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, pairs ? m->frep : nullptr, m->grad, R);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
+    m->grad_epoch = m->pos_epoch;
+    return 0;
+}
+
+int tm_preload_energy() {
+    TM_PRELOAD((k_props<true, true>)); TM_PRELOAD((k_props<true, false>)); TM_PRELOAD((k_props<false, false>));
+    TM_PRELOAD((k_pairs<true, true, true, true>)); TM_PRELOAD((k_pairs<true, true, true, false>));
+    TM_PRELOAD((k_pairs<true, true, false, true>)); TM_PRELOAD((k_pairs<true, true, false, false>));
+    TM_PRELOAD((k_pairs<false, true, false, true>)); TM_PRELOAD((k_pairs<false, true, false, false>));
+    TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad);
     return 0;
 }

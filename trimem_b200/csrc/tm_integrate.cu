@@ -1,0 +1,225 @@
+// Device-resident velocity-Verlet trajectory of hybrid Monte Carlo.
+//
+// Replaces, in the reference's Python driver, _vv_integration (src/trimem/mc/hmc.py:14-26)
+// and the two Hamiltonian evaluations around it (hmc.py:133-155):
+//
+//     a = force(x)                              force = -EnergyManager.gradient
+//     for i in range(N):
+//         x  = x + (p*dt + 0.5*a*dt**2) / m
+//         an = force(x)
+//         p  = p + 0.5*(a + an)*dt
+//         a  = an
+//
+// There every force() call crosses the pybind boundary (positions up, gradient down, ~10
+// numpy temporaries of V*3 doubles per step). Here x, p and both gradients stay in HBM for the
+// N steps; per step the device runs the gradient sweeps (tm_energy.cu) and ONE update kernel
+// that applies the momentum update of step i and the position update of step i+1 together.
+// The two gradients ping-pong between m->grad and m->grad_prev, so a = -g_old and an = -g_new
+// are read where they were written. The update is evaluated in numpy's operation order with
+// explicitly rounded multiplies/adds (no FMA contraction): given equal gradients it is
+// bit-identical to the reference expression.
+//
+// Energies. HMC needs U(x0) and U(xN) (nlog_prob, hmc.py:129-131). U(x0) comes from the
+// full property sweep that also feeds the first gradient; at xN the last gradient evaluation
+// runs the full sweeps (tether + pair energies) instead of the geometry-only ones, so the
+// trajectory costs N+1 sweep sets in total, none repeated. The kinetic terms 0.5 p.p/m are
+// reduced on the device in a fixed order.
+#include <utility>
+
+#include "tm_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+template <bool KICK, bool DRIFT>
+__global__ void __launch_bounds__(NT)
+k_vv_update(SweepRange R, P4* pos, double* __restrict__ mom, const double* __restrict__ g_old,
+            const double* __restrict__ g_new, double dt, double dt2, double mass) {
+    const int t = blockIdx.x * NT + threadIdx.x;
+    if (t >= R.count) return;
+    const size_t i = (size_t)(R.first + t);
+    double p[3], an[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        p[k] = mom[3 * i + k];
+        an[k] = -g_new[3 * i + k];
+    }
+    if (KICK) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double a = -g_old[3 * i + k];
+            // p + 0.5*(a + an)*dt
+            p[k] = __dadd_rn(p[k], __dmul_rn(__dmul_rn(0.5, __dadd_rn(a, an[k])), dt));
+            mom[3 * i + k] = p[k];
+        }
+    }
+    if (DRIFT) {
+        const d3 x = ldpos(pos, (int)i);
+        double xn[3] = {x.x, x.y, x.z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // x + (p*dt + 0.5*a*dt**2)/m
+            const double num = __dadd_rn(__dmul_rn(p[k], dt), __dmul_rn(__dmul_rn(0.5, an[k]), dt2));
+            xn[k] = __dadd_rn(xn[k], __ddiv_rn(num, mass));
+        }
+        *reinterpret_cast<double2*>(pos + i) = make_double2(xn[0], xn[1]);
+        pos[i].z = xn[2];
+    }
+}
+
+// p.p over the swept vertices: fixed grid, fixed strides, fixed trees -> bit-reproducible
+constexpr int DOT_BLOCKS = 296;
+__global__ void __launch_bounds__(NT)
+k_dot_partial(SweepRange R, const double* __restrict__ v, double* __restrict__ part) {
+    double s = 0.0;
+    for (int t = blockIdx.x * NT + threadIdx.x; t < R.count; t += DOT_BLOCKS * NT) {
+        const double* q = v + 3 * (size_t)(R.first + t);
+        s += fma(q[0], q[0], fma(q[1], q[1], q[2] * q[2]));
+    }
+    __shared__ double sm[NT / 32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < NT / 32; k++) tot += sm[k];
+        part[blockIdx.x] = tot;
+    }
+}
+
+__global__ void k_dot_final(const double* __restrict__ part, double scale, double* __restrict__ out) {
+    // one warp: lanes stride over the block partials, then a fixed tree
+    double s = 0.0;
+    for (int b = threadIdx.x; b < DOT_BLOCKS; b += 32) s += part[b];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = scale * s;
+}
+
+// The energies a trajectory reports are collected in a device block and fetched once, after the
+// trajectory: a device-to-host copy enqueued between the sweeps would sit in the copy engine's
+// in-order queue, where it can hold back another rank's copy when several ranks share a device.
+__global__ void k_store(double* __restrict__ dst, const double* __restrict__ src, int n) {
+    if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// host-numbered (V,3) array <-> device-numbered
+__global__ void k_import_vec3(int V, const double* __restrict__ in, const int* __restrict__ d2h,
+                              double* __restrict__ out) {
+    int d = blockIdx.x * NT + threadIdx.x;
+    if (d >= V) return;
+    const double* s = in + 3 * (size_t)d2h[d];
+    double* o = out + 3 * (size_t)d;
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}
+
+// rows of the swept range only (a partitioned mesh exports what it owns)
+__global__ void k_export_vec3_range(SweepRange R, const double* __restrict__ in, const int* __restrict__ d2h,
+                                    double* __restrict__ out) {
+    const int t = blockIdx.x * NT + threadIdx.x;
+    if (t >= R.count) return;
+    const int d = R.first + t;
+    const double* s = in + 3 * (size_t)d;
+    double* o = out + 3 * (size_t)d2h[d];
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}
+
+int ensure_state(tm_mesh* m) {
+    const size_t n = 3 * (size_t)m->V;
+    if (!m->mom) {
+        TM_CUDA(cudaMalloc(&m->mom, n * sizeof(double)));
+        TM_CUDA(cudaMemsetAsync(m->mom, 0, n * sizeof(double), m->stream));
+    }
+    if (!m->grad_prev) {
+        TM_CUDA(cudaMalloc(&m->grad_prev, n * sizeof(double)));
+        TM_CUDA(cudaMemsetAsync(m->grad_prev, 0, n * sizeof(double), m->stream));
+    }
+    if (!m->h_stats) TM_CUDA(cudaHostAlloc(&m->h_stats, 16 * sizeof(double), cudaHostAllocDefault));
+    if (!m->dot_part) TM_CUDA(cudaMalloc(&m->dot_part, DOT_BLOCKS * sizeof(double)));
+    if (!m->d_stats) TM_CUDA(cudaMalloc(&m->d_stats, 16 * sizeof(double)));
+    return 0;
+}
+
+int kinetic(tm_mesh* m, double mass, double* out_dev) {
+    double* part = m->dot_part;
+    k_dot_partial<<<DOT_BLOCKS, NT, 0, m->stream>>>(tm_owned_range(m), m->mom, part); TM_LAUNCHED();
+    k_dot_final<<<1, 32, 0, m->stream>>>(part, 0.5 / mass, out_dev); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
+              bool with_energies) {
+    if (ensure_state(m) || tm_part_refresh(m, nl)) return 1;
+    const double dt2 = dt * dt;
+    if (with_energies) {
+        // U(x0): full sweeps; their sums, rho and pair force feed the first gradient
+        if (tm_launch_props(m, nl, p, true, false)) return 1;
+        k_store<<<1, 32, 0, m->stream>>>(m->d_stats, m->sums, 6); TM_LAUNCHED();
+        if (kinetic(m, mass, m->d_stats + 12)) return 1;
+    }
+    // a = force(x0). The ring gradient is always re-evaluated (it depends on every parameter);
+    // the property sweep and the pair force are reused when they belong to x0.
+    if (m->geo_epoch != m->pos_epoch && tm_launch_props(m, nl, p, false, false)) return 1;
+    if (tm_launch_grad(m, nl, p)) return 1;
+    const SweepRange R = tm_owned_range(m);
+    const int nb = (R.count + NT - 1) / NT;
+    if (n_steps > 0) {
+        if (tm_part_before_update(m)) return 1;
+        k_vv_update<false, true><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad, m->grad, dt, dt2, mass);
+        TM_LAUNCHED();
+    }
+    for (int n = 1; n <= n_steps; n++) {
+        m->pos_epoch++;
+        if (tm_part_positions_updated(m)) return 1;
+        std::swap(m->grad, m->grad_prev);          // a = -grad_prev, an = -grad (about to be evaluated)
+        const bool last = n == n_steps;
+        if (tm_launch_props(m, nl, p, last && with_energies, false)) return 1;
+        if (tm_launch_grad(m, nl, p)) return 1;
+        if (last) {
+            k_vv_update<true, false><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad_prev, m->grad, dt, dt2, mass);
+        } else {
+            if (tm_part_before_update(m)) return 1;
+            k_vv_update<true, true><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad_prev, m->grad, dt, dt2, mass);
+        }
+        TM_LAUNCHED();
+    }
+    TM_CUDA(cudaGetLastError());
+    if (with_energies) {
+        if (n_steps == 0 && tm_launch_props(m, nl, p, true, false)) return 1;
+        k_store<<<1, 32, 0, m->stream>>>(m->d_stats + 6, m->sums, 6); TM_LAUNCHED();
+        if (kinetic(m, mass, m->d_stats + 13)) return 1;
+        TM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int tm_import_momenta(tm_mesh* m, const double* p_host) {
+    if (ensure_state(m)) return 1;
+    // through the host-numbered staging block, on the mesh's stream (positions staged there have
+    // been imported by the caller's tm_ensure_layout)
+    TM_CHECK(!m->stage_pending, "internal: staged positions not imported");
+    TM_CUDA(cudaMemcpyAsync(m->xio3, p_host, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
+    k_import_vec3<<<(m->V + NT - 1) / NT, NT, 0, m->stream>>>(m->V, m->xio3, m->d2h, m->mom); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tm_export_vec3_owned(tm_mesh* m, const double* dev, double* host) {
+    const SweepRange R = tm_owned_range(m);
+    if (R.count < m->V) TM_CUDA(cudaMemsetAsync(m->xout3, 0, sizeof(double) * 3 * (size_t)m->V, m->stream));
+    k_export_vec3_range<<<(R.count + NT - 1) / NT, NT, 0, m->stream>>>(R, dev, m->d2h, m->xout3); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    if (tm_part_quiesce(m)) return 1;
+    TM_CUDA(cudaMemcpyAsync(host, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));
+    return 0;
+}
+
+int tm_preload_integrate() {
+    TM_PRELOAD((k_vv_update<false, true>)); TM_PRELOAD((k_vv_update<true, false>)); TM_PRELOAD((k_vv_update<true, true>));
+    TM_PRELOAD(k_dot_partial); TM_PRELOAD(k_dot_final); TM_PRELOAD(k_store);
+    TM_PRELOAD(k_import_vec3); TM_PRELOAD(k_export_vec3_range);
+    return 0;
+}

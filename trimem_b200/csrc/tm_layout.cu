@@ -314,6 +314,11 @@ int tm_check_nlist(const tm_mesh* m, const tm_nlist* nl) {
     return 0;
 }
 
+int tm_preload_layout() {
+    TM_PRELOAD(k_import_positions); TM_PRELOAD(k_export_positions); TM_PRELOAD(k_export_vec3);
+    return 0;
+}
+
 extern "C" {
 
 // Recompute the vertex order from the current positions (extension; e.g. after long runs in

@@ -415,6 +415,8 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
     TM_CHECK(rlist > 0.0, "rlist must be positive (got %g)", rlist);
     TM_CUDA(cudaSetDevice(m->device));
     if (tm_ensure_layout(m)) return 1;
+    // partitioned mesh: the list is built from every rank's current positions (collective)
+    if (tm_part_make_current(m)) return 1;
 
     tm_nlist* nl = new tm_nlist();
     nl->device = m->device;
