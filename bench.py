@@ -148,6 +148,87 @@ def time_reference(subdiv, steps, warmup, threads=None):
             "setup_s": setup, "energy": float(e), "grad_norm": float(np.linalg.norm(g))}
 
 
+def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist, torch):
+    """BASELINE config 4: ONE mesh (subdiv --part-subdiv) whose vertices are partitioned across the ranks
+    (csrc/tm_part.cu): E+G evals/s and leapfrog steps/s of the whole mesh, strong scaling. At one rank the
+    same mesh is evaluated unpartitioned (the base of the scaling curve)."""
+    from trimem_b200 import meshgen, partition
+    t0 = time.time()
+    v, f = meshgen.jittered_icosphere(args.part_subdiv)
+    mesh = core.TriMesh(v, f)
+    ep = workload.energy_params(core, mesh, repulsion="stress", n_search="verlet-list")
+    estore = core.EnergyManager(mesh, ep)            # whole mesh on this device: reference sums + a parity value
+    e_single = estore.energy(mesh)
+    par = workload.abi_params(estore)
+    rp = ep.repulse_params
+    arrs = mesh.halfedge_arrays()[:4]
+    V = mesh.n_vertices()
+    cm = cabi.Mesh(*arrs, xyz=v, device=local)
+    make_nl = lambda m: cabi.NList(m, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    if world > 1:
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        nl = partition.setup(cm, rank, world, allgather, make_nl)
+        info = cm.part_info()
+    else:
+        nl = make_nl(cm)
+        info = {"rank": 0, "nranks": 1, "first": 0, "count": V, "n_ghost1": 0, "n_pull": 0}
+    setup_s = time.time() - t0
+    steps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        cm.energy_async(nl, par); cm.gradient_async(nl, par)
+    cm.sync()
+    barrier()
+    eg_ms = 0.0
+    for _ in range(steps):
+        cm.flush_l2(FLUSH_BYTES)
+        cm.timer_start()
+        cm.energy_async(nl, par); cm.gradient_async(nl, par)
+        eg_ms += cm.timer_stop()
+    barrier()
+    e_part, _ = cm.fetch_energy(par)
+    # leapfrog
+    L = max(1, args.leapfrog_steps)
+    cm.set_momenta(np.random.default_rng(7).normal(size=v.shape))
+    cm.vv_integrate_async(nl, par, 1.0, 2.0e-8, 2)
+    cm.sync()
+    barrier()
+    n_traj = 3
+    lf_ms = 0.0
+    for _ in range(n_traj):
+        cm.flush_l2(FLUSH_BYTES)
+        cm.timer_start()
+        cm.vv_integrate_async(nl, par, 1.0, 2.0e-8, L)
+        lf_ms += cm.timer_stop()
+    cm.sync()
+    barrier()
+    # list rebuild on current positions (collective: pulls the far field first)
+    t1 = time.time()
+    nl2 = make_nl(cm); cm.sync()
+    rebuild_ms = 1e3 * (time.time() - t1)
+    t = torch.tensor([eg_ms, lf_ms, rebuild_ms], dtype=torch.float64, device="cuda")
+    halo = torch.tensor([info["n_ghost1"], info["n_pull"], info["count"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo, op=dist.ReduceOp.MAX)
+    eg_ms, lf_ms, rebuild_ms = float(t[0]), float(t[1]), float(t[2])
+    nl2.close(); nl.close(); cm.close()
+    return {"workload": f"ONE icosphere subdiv={args.part_subdiv} ({V} vertices), tether + stress repulsion, verlet-list excl 2, "
+                        f"vertices partitioned over {world} rank(s)" + ("" if world > 1 else " (unpartitioned base of the scaling curve)"),
+            "scaling": "strong", "n_vertices": V, "ranks": world,
+            "ms_per_eg": eg_ms / steps, "evals_per_s": steps / (eg_ms / 1e3),
+            "mvertex_evals_per_s": steps / (eg_ms / 1e3) * V / 1e6,
+            "leapfrog_ms_per_step": lf_ms / n_traj / L, "mvertex_steps_per_s": n_traj * L / (lf_ms / 1e3) * V / 1e6,
+            "verlet_rebuild_ms": rebuild_ms,
+            "max_owned": int(halo[2]), "max_ghost_ring1": int(halo[0]), "max_pulled_per_update": int(halo[1]),
+            "energy_rel_diff_vs_whole_mesh_on_one_device": abs(e_part - e_single) / abs(e_single),
+            "exchange": "halo positions pulled over NVLink from the owners' arrays (cudaIpc), six sums added in rank order; "
+                        "device-side sequencing, no NCCL / host on the data path" if world > 1 else "none",
+            "setup_s": setup_s}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +238,11 @@ def main():
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 = 655,362 vertices, the headline)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="E+G evaluations of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--part-subdiv", type=int, default=10,
+                    help="icosphere subdivisions of the ONE mesh partitioned across the ranks (BASELINE config 4: 10 = "
+                         "10,485,762 vertices); also evaluated unpartitioned at --gpus 1 as the strong-scaling base")
+    ap.add_argument("--no-partition", action="store_true", help="skip the partitioned-mesh measurement")
+    ap.add_argument("--leapfrog-steps", type=int, default=10, help="velocity-Verlet steps per timed trajectory")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -255,30 +341,65 @@ def main():
 
     # ---- e2e through the public API with host buffers (H2D of positions, D2H of the gradient)
     xs = [x0 + 1e-6 * np.random.default_rng(s).normal(size=x0.shape) for s in range(2)]
+    phase = [0.0, 0.0, 0.0]
     def eg_api(k):
+        t_a = time.perf_counter()
         np.copyto(mesh.points(), xs[k % 2])
+        t_b = time.perf_counter()
         e = estore.energy(mesh)
+        t_c = time.perf_counter()
         g = estore.gradient(mesh)
+        t_d = time.perf_counter()
+        phase[0] += t_b - t_a; phase[1] += t_c - t_b; phase[2] += t_d - t_c
         return e, g
     for k in range(3):
         eg_api(k)
     e2e_steps = max(5, min(args.steps, 30))
     barrier()
+    phase[:] = [0.0, 0.0, 0.0]
     t0 = time.time()
     for k in range(e2e_steps):
         e_last, g_last = eg_api(k)
     barrier()
     e2e_s = time.time() - t0
-    clocks = sampler.stop()       # covers the device-resident loop, the per-kernel timings and the e2e loop
+    e2e_phase_ms = [1e3 * t / e2e_steps for t in phase]
+
+    # ---- device-resident velocity-Verlet trajectory (tm_vv_integrate_async; hmc.py:14-26): L steps per
+    # timed trajectory = L+1 gradient evaluations + L fused update kernels, state never leaves HBM
+    L = max(1, args.leapfrog_steps)
+    lf_dt = 1.0e-7                      # stable for the stiff stress potential at this resolution
+    cm.set_positions(x0)
+    cm.set_momenta(np.random.default_rng(100 + rank).normal(size=x0.shape))
+    cm.vv_integrate_async(nl, p, 1.0, lf_dt, 2)
+    cm.sync()
+    n_traj = max(3, min(10, args.steps // 5))
+    barrier()
+    lf_ms = 0.0
+    for _ in range(n_traj):
+        cm.flush_l2(FLUSH_BYTES)
+        cm.timer_start()
+        cm.vv_integrate_async(nl, p, 1.0, lf_dt, L)
+        lf_ms += cm.timer_stop()
+    barrier()
+    clocks = sampler.stop()       # covers the device-resident loops, the per-kernel timings and the e2e loop
+    lf_stats = None
+    cm.vv_integrate_async(nl, p, 1.0, lf_dt, L, True)
+    st = cm.vv_stats(p)[0]
+    lf_stats = {"H0": st[0] + st[1], "H1": st[2] + st[3]}
+    cm.set_positions(x0)
+
+    part = None
+    if not args.no_partition:
+        part = partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist if world > 1 else None, torch)
 
     # parity spot check of the timed configuration against itself through both boundaries
     e_dev, _ = cm.energy(nl, p)
 
     # max over ranks
-    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s, lf_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s = float(t[0]), float(t[1])
+    total_ms, e2e_s, lf_ms = float(t[0]), float(t[1]), float(t[2])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,7 +434,15 @@ def main():
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": "evals/s",
                     "h2d_bytes_per_step": 2 * V * 24, "d2h_bytes_per_step": V * 24 + 2 * 48,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "phase_ms": {"np.copyto(mesh.points(), x)": e2e_phase_ms[0], "estore.energy(mesh)": e2e_phase_ms[1],
+                                 "estore.gradient(mesh)": e2e_phase_ms[2]}},
+            "leapfrog": {"what": f"device-resident velocity-Verlet trajectory of {L} steps (tm_vv_integrate_async): "
+                                 f"{L + 1} gradient evaluations + {L} fused update kernels, L2 flushed before each trajectory",
+                         "ms_per_step": lf_ms / n_traj / L, "steps_per_s": world * n_traj * L / (lf_ms / 1e3),
+                         "mvertex_steps_per_s": world * n_traj * L / (lf_ms / 1e3) * V / 1e6,
+                         "trajectories": n_traj, "hamiltonian": lf_stats},
+            "partitioned": part,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

