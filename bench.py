@@ -191,20 +191,38 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
     e_part, _ = cm.fetch_energy(par)
     # leapfrog
     L = max(1, args.leapfrog_steps)
-    cm.set_momenta(np.random.default_rng(7).normal(size=v.shape))
-    cm.vv_integrate_async(nl, par, 1.0, 2.0e-8, 2)
+    lf_dt = 2.0e-8 * (655362.0 / V)
+    p_host = np.random.default_rng(7).normal(size=v.shape)
+
+    def lf_reset():
+        cm.set_positions(v)
+        cm.set_momenta(p_host)
+        cm.sync()
+    lf_reset()
+    cm.vv_integrate_async(nl, par, 1.0, lf_dt, 2)
     cm.sync()
     barrier()
     n_traj = 3
     lf_ms = 0.0
     for _ in range(n_traj):
+        lf_reset()
+        barrier()
         cm.flush_l2(FLUSH_BYTES)
         cm.timer_start()
-        cm.vv_integrate_async(nl, par, 1.0, 2.0e-8, L)
+        cm.vv_integrate_async(nl, par, 1.0, lf_dt, L)
         lf_ms += cm.timer_stop()
-    cm.sync()
+    lf_reset()
     barrier()
-    # list rebuild on current positions (collective: pulls the far field first)
+    cm.vv_integrate_async(nl, par, 1.0, lf_dt, L, True)
+    st = cm.vv_stats(par)[0]
+    kin = torch.tensor([st[1], st[3]], dtype=torch.float64, device="cuda")     # kinetic energy: owned shares
+    if world > 1:
+        dist.all_reduce(kin, op=dist.ReduceOp.SUM)
+    h0, h1 = st[0] + float(kin[0]), st[2] + float(kin[1])
+    assert np.isfinite([h0, h1]).all(), "partitioned leapfrog trajectory diverged"
+    # list rebuild on current positions (collective: pulls the far field first); second build timed (warm pool)
+    make_nl(cm).close(); cm.sync()
+    barrier()
     t1 = time.time()
     nl2 = make_nl(cm); cm.sync()
     rebuild_ms = 1e3 * (time.time() - t1)
@@ -222,6 +240,7 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
             "mvertex_evals_per_s": steps / (eg_ms / 1e3) * V / 1e6,
             "leapfrog_ms_per_step": lf_ms / n_traj / L, "mvertex_steps_per_s": n_traj * L / (lf_ms / 1e3) * V / 1e6,
             "verlet_rebuild_ms": rebuild_ms,
+            "hamiltonian": {"H0": h0, "H1": h1, "time_step": lf_dt},
             "max_owned": int(halo[2]), "max_ghost_ring1": int(halo[0]), "max_pulled_per_update": int(halo[1]),
             "energy_rel_diff_vs_whole_mesh_on_one_device": abs(e_part - e_single) / abs(e_single),
             "exchange": "halo positions pulled over NVLink from the owners' arrays (cudaIpc), six sums added in rank order; "
@@ -367,25 +386,31 @@ def main():
     # ---- device-resident velocity-Verlet trajectory (tm_vv_integrate_async; hmc.py:14-26): L steps per
     # timed trajectory = L+1 gradient evaluations + L fused update kernels, state never leaves HBM
     L = max(1, args.leapfrog_steps)
-    lf_dt = 1.0e-7                      # stable for the stiff stress potential at this resolution
-    cm.set_positions(x0)
-    cm.set_momenta(np.random.default_rng(100 + rank).normal(size=x0.shape))
+    lf_dt = 2.0e-8                      # stable for the stiff stress potential at this resolution
+    p_host = np.random.default_rng(100 + rank).normal(size=x0.shape)
+
+    def lf_reset():                     # every trajectory starts from (x0, p0): no drift across trajectories
+        cm.set_positions(x0)
+        cm.set_momenta(p_host)
+        cm.sync()
+    lf_reset()
     cm.vv_integrate_async(nl, p, 1.0, lf_dt, 2)
-    cm.sync()
     n_traj = max(3, min(10, args.steps // 5))
     barrier()
     lf_ms = 0.0
     for _ in range(n_traj):
+        lf_reset()
         cm.flush_l2(FLUSH_BYTES)
         cm.timer_start()
         cm.vv_integrate_async(nl, p, 1.0, lf_dt, L)
         lf_ms += cm.timer_stop()
     barrier()
     clocks = sampler.stop()       # covers the device-resident loops, the per-kernel timings and the e2e loop
-    lf_stats = None
+    lf_reset()
     cm.vv_integrate_async(nl, p, 1.0, lf_dt, L, True)
     st = cm.vv_stats(p)[0]
-    lf_stats = {"H0": st[0] + st[1], "H1": st[2] + st[3]}
+    lf_stats = {"H0": st[0] + st[1], "H1": st[2] + st[3], "time_step": lf_dt}
+    assert np.isfinite(st).all(), "leapfrog trajectory diverged"
     cm.set_positions(x0)
 
     part = None

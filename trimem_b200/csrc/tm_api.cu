@@ -170,6 +170,7 @@ int tm_mesh_create(int device, tm_mesh** out) {
     TM_CUDA(cudaSetDevice(device));
     tm_mesh* m = new tm_mesh();
     m->device = device;
+    TM_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
     TM_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     TM_CUDA(cudaEventCreate(&m->ev0));
     TM_CUDA(cudaEventCreate(&m->ev1));
@@ -292,6 +293,7 @@ int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
     TM_CUDA(cudaMemcpyAsync(m->xio3, xyz, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
     m->stage_pending = true;
     m->have_positions = true;
+    tm_part_positions_uploaded(m);
     return 0;
 }
 

@@ -47,9 +47,11 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 #define TM_GRAD_NT 128
 #endif
 // resident blocks per SM the register allocation aims at (measured on B200 at 655k vertices,
-// profiles/r01: ring gradient 130 us at 176 regs, 99 us at 128 regs, 119 us at 96 regs)
+// profiles/r01, r01g). With the ring records staged in shared memory the property sweep needs
+// 64-70 registers (6 blocks of 128: 55 us) and the ring gradient 128 without spilling (4 blocks:
+// 82 us; 96 registers / 5 blocks spills and takes 91 us, 80 / 6 blocks 122 us).
 #ifndef TM_PROPS_MINB
-#define TM_PROPS_MINB 5
+#define TM_PROPS_MINB 6
 #endif
 #ifndef TM_GRAD_MINB
 #define TM_GRAD_MINB 4
@@ -116,6 +118,7 @@ struct NlView {
 // ----------------------------------------------------------------- handles --
 struct tm_mesh {
     int device = 0;
+    int sm_count = 148;          // multiprocessors of the device (persistent grids)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int V = 0, HE = 0;
@@ -209,6 +212,8 @@ __host__ __device__
 #endif
 inline size_t tm_row_base(int i, int row_cap) { return ((size_t)(i >> 5) * row_cap) * 32 + (i & 31); }
 
+inline int tm_sm_count(const tm_mesh* m) { return m->sm_count; }
+
 inline NlView tm_no_nlist() {
     NlView v;
     memset(&v, 0, sizeof(v));
@@ -262,7 +267,8 @@ int tm_preload_layout();      // tm_layout.cu
 int tm_part_refresh(tm_mesh* m, const NlView& nl);   // halo lists for the current connectivity / list (local)
 int tm_part_make_current(tm_mesh* m);            // full position exchange if the far field is stale
 int tm_part_quiesce(tm_mesh* m);                 // partitioned: drain the stream before enqueuing a copy
-int tm_part_poll_error(tm_mesh* m);              // syncs; reports an exchange time-out
+int tm_part_poll_error(tm_mesh* m);
+void tm_part_positions_uploaded(tm_mesh* m);              // syncs; reports an exchange time-out
 
 // ------------------------------------------------------------ device maths --
 #ifdef __CUDACC__

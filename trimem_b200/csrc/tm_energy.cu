@@ -90,6 +90,29 @@ __device__ __forceinline__ void verlet_pairs(const P4* pos, const NlView& nl, in
     }
 }
 
+// ---- ring records staged in shared memory -----------------------------------------------------
+// The sweeps' ring data (8 records per thread) go global -> shared with cp.async, without
+// passing through registers, into [slot][thread] arrays of 16- and 8-byte parts (conflict-free
+// wide accesses); the slot loops fetch spoke s+1 when they reach it. Keeping the whole ring in
+// registers instead costs 48-64 registers next to the walk's own state: the gradient sweep
+// spilled ~200 bytes per thread at 128 registers (99 -> 82 us at 655,362 vertices, same bits).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#ifndef TM_PROPS_SMEM
+#define TM_PROPS_SMEM 1
+#endif
+#ifndef TM_PROPS_UNROLL
+#define TM_PROPS_UNROLL 1
+#endif
+constexpr int PROPS_UNROLL = TM_PROPS_UNROLL;
+
 // ---- K1: per-vertex properties ------------------------------------------------------
 // one ring slot of vertex_properties (mesh_properties.cpp:19-38): spoke e_cur, face
 // (i, j_s, j_{s-1}) with normal n_cur, next spoke / normal for the dihedral of the spoke
@@ -136,6 +159,39 @@ __device__ __forceinline__ void ring_props_fast(const P4* pos, const DevParams& 
 }
 
 template <bool FULL>
+__device__ __forceinline__ void ring_props_smem(const P4* pos, const DevParams& P, const R8& row, int d, d3 xi,
+                                                double& area, double& vol, double& curv, double& teth) {
+    __shared__ double2 s_xy[8][TM_PROPS_THREADS];
+    __shared__ double s_z[8][TM_PROPS_THREADS];
+    __shared__ int s_w[8][TM_PROPS_THREADS];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < d) {
+            // (x, y) and z only: rho (.w) of other vertices is being written by this very sweep
+            const P4* src = pos + (row.v[s] & TM_RING_MASK);
+            cp_async16(&s_xy[s][tid], src);
+            cp_async8(&s_z[s][tid], &src->z);
+            s_w[s][tid] = row.v[s];
+        }
+    }
+    cp_async_wait_all();
+    auto spoke = [&](int s) {
+        const double2 a = s_xy[s][tid];
+        return mk3(a.x, a.y, s_z[s][tid]) - xi;
+    };
+    d3 e_cur = spoke(0);
+    d3 n_cur = cross3(e_cur, spoke(d - 1));
+#pragma unroll PROPS_UNROLL
+    for (int s = 0; s < d; s++) {
+        const d3 e_next = spoke(s + 1 == d ? 0 : s + 1);
+        const d3 n_next = cross3(e_next, e_cur);
+        props_slot<FULL>(P, xi, s_w[s][tid], e_cur, n_cur, e_next, n_next, area, vol, curv, teth);
+        e_cur = e_next; n_cur = n_next;
+    }
+}
+
+template <bool FULL>
 __device__ __forceinline__ void ring_props_generic(const MeshView& mv, const DevParams& P, int i, d3 xi,
                                                    double& area, double& vol, double& curv, double& teth) {
     const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
@@ -169,7 +225,11 @@ k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
         if (row.v[0] == TM_RING_GENERIC) ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
         else {
             const int d = row_valence(row);
+#if TM_PROPS_SMEM
+            if (d > 0) ring_props_smem<FULL>(mv.pos, P, row, d, xi, area, vol, curv, teth);
+#else
             if (d > 0) ring_props_fast<FULL>(mv.pos, P, row, d, xi, area, vol, curv, teth);
+#endif
         }
         area = area / 3.0;
         vol = vol / 18.0;                          // /6 per face, /3 multiplicity
@@ -271,30 +331,38 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
         if (nl.kind == TM_NLIST_VERLET) {
             const int e = nl.row_cnt[i];
             const int* col = nl.row_j + tm_row_base(i, nl.row_cap);
-            for (int k = 0; k < e; k += PB) {
-                int j[PB];
-                j[0] = __ldg(col + k * 32);
+            // Software pipeline over the row, PB entries per stage: while stage k is evaluated the
+            // records of stage k+1 are in flight and the indices of stage k+2 have been requested, so
+            // the two dependent memory levels (index -> record, ~1000 cycles each from a cold L2)
+            // overlap the ~80 instructions per entry instead of preceding them (100 -> 66 us at
+            // 655,362 vertices, fp64 pipe 48 -> 70 % busy; profiles/r01g). Slots past the row's end
+            // read the vertex's own record (always valid) and are masked in the evaluation.
+            int jn[PB];
+            P4 xn[PB];
 #pragma unroll
-                for (int u = 1; u < PB; u++) j[u] = (k + u < e) ? __ldg(col + (k + u) * 32) : j[0];
+            for (int u = 0; u < PB; u++) jn[u] = (u < e) ? __ldg(col + u * 32) : i;
+#pragma unroll
+            for (int u = 0; u < PB; u++) xn[u] = ldrec(mv.pos, jn[u]);
+#pragma unroll
+            for (int u = 0; u < PB; u++) jn[u] = (PB + u < e) ? __ldg(col + (PB + u) * 32) : i;
+            for (int k = 0; k < e; k += PB) {
                 P4 x[PB];
 #pragma unroll
-                for (int u = 0; u < PB; u++) x[u] = ldrec(mv.pos, j[u]);
+                for (int u = 0; u < PB; u++) x[u] = xn[u];
+                if (k + PB < e) {
+#pragma unroll
+                    for (int u = 0; u < PB; u++) xn[u] = ldrec(mv.pos, jn[u]);
+#pragma unroll
+                    for (int u = 0; u < PB; u++) jn[u] = (k + 2 * PB + u < e) ? __ldg(col + (k + 2 * PB + u) * 32) : i;
+                }
 #pragma unroll
                 for (int u = 0; u < PB; u++) {
                     const d3 dv = xi - mk3(x[u].x, x[u].y, x[u].z);
                     const double l2 = dot3(dv, dv);
                     double phi, sl;
-#ifdef TM_PAIR_BRANCHY
-                    if ((k + u < e) && (l2 < C.lc1sq)) {
-                        pair_eval<R2>(C, rr, l2, true, phi, sl);
-                        if (WITH_E) rep += phi;
-                        if (WITH_F) axpy3(gr, sl, dv);
-                    }
-#else
                     pair_eval<R2>(C, rr, l2, (k + u < e) && (l2 < C.lc1sq), phi, sl);
                     if (WITH_E) rep += phi;
                     if (WITH_F) axpy3(gr, sl, dv);
-#endif
                 }
             }
         } else {
@@ -487,6 +555,54 @@ __device__ __forceinline__ void ring_grad_fast(const P4* pos, const DevParams& P
     }
 }
 
+#ifndef TM_GRAD_SMEM
+#define TM_GRAD_SMEM 1
+#endif
+#ifndef TM_GRAD_UNROLL
+#define TM_GRAD_UNROLL 1
+#endif
+constexpr int GRAD_UNROLL = TM_GRAD_UNROLL;
+
+// The same walk with the ring records staged in shared memory instead of registers: the eight
+// (x, y, z, rho) records of a thread go global -> shared with cp.async (no register staging), in
+// a [slot][thread] layout of 16-byte halves (conflict-free 128-bit accesses), and the slot loop
+// fetches spoke s+1 when it needs it. The register version keeps 8 x 4 doubles of ring data live
+// next to three GSlots and nine accumulators and spills ~200 bytes per thread at 128 registers.
+__device__ __forceinline__ void ring_grad_smem(const P4* pos, const DevParams& P, const GradK& K, const R8& row,
+                                               int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
+    __shared__ double2 s_xy[8][TM_GRAD_THREADS];
+    __shared__ double2 s_zr[8][TM_GRAD_THREADS];
+    __shared__ int s_w[8][TM_GRAD_THREADS];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < d) {
+            const P4* src = pos + (row.v[s] & TM_RING_MASK);
+            cp_async16(&s_xy[s][tid], src);
+            cp_async16(&s_zr[s][tid], reinterpret_cast<const char*>(src) + 16);
+            s_w[s][tid] = row.v[s];
+        }
+    }
+    cp_async_wait_all();
+    auto spoke = [&](GSlot& t, int s) {
+        const double2 a = s_xy[s][tid], b = s_zr[s][tid];
+        gslot_point(t, mk3(a.x, a.y, b.x) - xi, b.y);
+    };
+    GSlot prv, cur;
+    spoke(prv, d - 1);
+    spoke(cur, 0);
+    gslot_pair(cur, prv);
+#pragma unroll GRAD_UNROLL
+    for (int s = 0; s < d; s++) {
+        GSlot nxt;
+        spoke(nxt, s + 1 == d ? 0 : s + 1);
+        gslot_pair(nxt, cur);
+        grad_slot(P, K, rho_i, s_w[s][tid], prv, cur, nxt, g, nsum, esum);
+        prv = cur;
+        cur = nxt;
+    }
+}
+
 __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevParams& P, const GradK& K, int i,
                                                   d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
     const int beg = mv.ring_off[i], d = mv.ring_off[i + 1] - beg;
@@ -535,7 +651,11 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     if (row.v[0] == TM_RING_GENERIC) ring_grad_generic(mv, P, K, i, xi, ri.w, g, nsum, esum);
     else {
         const int d = row_valence(row);
+#if TM_GRAD_SMEM
+        if (d > 0) ring_grad_smem(mv.pos, P, K, row, d, xi, ri.w, g, nsum, esum);
+#else
         if (d > 0) ring_grad_fast(mv.pos, P, K, row, d, xi, ri.w, g, nsum, esum);
+#endif
     }
     // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
     axpy3(g, K.fV / 6.0, nsum + cross3(xi, esum));

@@ -295,6 +295,8 @@ int tm_part_make_current(tm_mesh* m) {
 }
 
 int tm_part_poll_error(tm_mesh* m) { return m->part ? check_error(m) : 0; }
+// the caller uploaded a whole position array (the same one on every rank): nothing is stale
+void tm_part_positions_uploaded(tm_mesh* m) { if (m->part) m->part->stale_far = false; }
 int tm_part_quiesce(tm_mesh* m) {
     if (m->part) TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
