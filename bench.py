@@ -148,6 +148,64 @@ def time_reference(subdiv, steps, warmup, threads=None):
             "setup_s": setup, "energy": float(e), "grad_norm": float(np.linalg.norm(g))}
 
 
+def replica_run(args, core, cabi, workload, rank, world, local, barrier):
+    """BASELINE config 5: independent HMC replicas, `--replicas` per GPU, each a 40,962-vertex membrane of
+    the reduced-volume / kappa_b sweep with its own mesh handle and CUDA stream; no communication. Timed:
+    every replica integrates one device-resident trajectory of L steps, all enqueued before the first
+    is waited for; aggregate vertex-steps/s over the whole job."""
+    R = args.replicas
+    L = max(1, args.leapfrog_steps)
+    reps = []
+    for k in range(R):
+        gid = rank * R + k                                        # position in the 8 x 8 sweep of config 5
+        mesh, estore, x0 = workload.make_case(core, 6, repulsion="physical", n_search="verlet-list", seed=gid,
+                                              kappa=(10.0 * (1 + gid % 8), 1.0e6, 1.0e6, 0.0, 1.0e5, 1.0e3),
+                                              fracs=(1.0, 0.5 + 0.5 * ((gid // 8) % 8) / 7.0, 1.0))
+        arrs = mesh.halfedge_arrays()[:4]
+        cm = cabi.Mesh(*arrs, xyz=x0, device=local)
+        rp = estore.eparams.repulse_params
+        nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+        par = workload.abi_params(estore)
+        p0 = np.random.default_rng(1000 + gid).normal(size=x0.shape)
+        reps.append((cm, nl, par, x0, p0))
+    V = reps[0][0].V
+    dt = 1.0e-6
+
+    def reset():
+        for cm, nl, par, x0, p0 in reps:
+            cm.set_positions(x0); cm.set_momenta(p0)
+        for r in reps:
+            r[0].sync()
+    for _ in range(3):                  # direct launch, graph capture, first replay
+        reset()
+        for cm, nl, par, _, _ in reps:
+            cm.vv_integrate_async(nl, par, 1.0, dt, L)
+        for r in reps:
+            r[0].sync()
+    n_rounds = 5
+    barrier()
+    wall = 0.0
+    for _ in range(n_rounds):
+        reset()
+        t0 = time.perf_counter()
+        for cm, nl, par, _, _ in reps:
+            cm.vv_integrate_async(nl, par, 1.0, dt, L)
+        for r in reps:
+            r[0].sync()
+        wall += time.perf_counter() - t0
+    # one replica alone, for the concurrency gain
+    cm, nl, par, x0, p0 = reps[0]
+    reset()
+    cm.timer_start(); cm.vv_integrate_async(nl, par, 1.0, dt, L); solo_ms = cm.timer_stop()
+    cm.vv_integrate_async(nl, par, 1.0, dt, L, True)
+    st = cm.vv_stats(par)[0]
+    assert np.isfinite(st).all()
+    for cm, nl, _, _, _ in reps:
+        nl.close(); cm.close()
+    return {"wall_s": wall, "rounds": n_rounds, "L": L, "R": R, "V": V, "solo_ms_per_step": solo_ms / L,
+            "hamiltonian": {"H0": st[0] + st[1], "H1": st[2] + st[3], "time_step": dt}}
+
+
 def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist, torch):
     """BASELINE config 4: ONE mesh (subdiv --part-subdiv) whose vertices are partitioned across the ranks
     (csrc/tm_part.cu): E+G evals/s and leapfrog steps/s of the whole mesh, strong scaling. At one rank the
@@ -198,9 +256,11 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
         cm.set_positions(v)
         cm.set_momenta(p_host)
         cm.sync()
-    lf_reset()
-    cm.vv_integrate_async(nl, par, 1.0, lf_dt, 2)
-    cm.sync()
+    for _ in range(3):
+        lf_reset()
+        barrier()
+        cm.vv_integrate_async(nl, par, 1.0, lf_dt, L)
+        cm.sync()
     barrier()
     n_traj = 3
     lf_ms = 0.0
@@ -261,6 +321,8 @@ def main():
                     help="icosphere subdivisions of the ONE mesh partitioned across the ranks (BASELINE config 4: 10 = "
                          "10,485,762 vertices); also evaluated unpartitioned at --gpus 1 as the strong-scaling base")
     ap.add_argument("--no-partition", action="store_true", help="skip the partitioned-mesh measurement")
+    ap.add_argument("--replicas", type=int, default=8,
+                    help="independent 40,962-vertex membranes per GPU in the replica measurement (BASELINE config 5; 0 = skip)")
     ap.add_argument("--leapfrog-steps", type=int, default=10, help="velocity-Verlet steps per timed trajectory")
     args = ap.parse_args()
 
@@ -371,8 +433,8 @@ def main():
         t_d = time.perf_counter()
         phase[0] += t_b - t_a; phase[1] += t_c - t_b; phase[2] += t_d - t_c
         return e, g
-    for k in range(3):
-        eg_api(k)
+    for k in range(4):
+        e_last, g_last = eg_api(k)          # same ownership pattern as the timed loop (two result arrays circulate)
     e2e_steps = max(5, min(args.steps, 30))
     barrier()
     phase[:] = [0.0, 0.0, 0.0]
@@ -393,8 +455,10 @@ def main():
         cm.set_positions(x0)
         cm.set_momenta(p_host)
         cm.sync()
-    lf_reset()
-    cm.vv_integrate_async(nl, p, 1.0, lf_dt, 2)
+    for _ in range(3):                  # direct launch, graph capture, first replay (tm_integrate.cu)
+        lf_reset()
+        cm.vv_integrate_async(nl, p, 1.0, lf_dt, L)
+    cm.sync()
     n_traj = max(3, min(10, args.steps // 5))
     barrier()
     lf_ms = 0.0
@@ -413,6 +477,7 @@ def main():
     assert np.isfinite(st).all(), "leapfrog trajectory diverged"
     cm.set_positions(x0)
 
+    repl = replica_run(args, core, cabi, workload, rank, world, local, barrier) if args.replicas > 0 else None
     part = None
     if not args.no_partition:
         part = partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist if world > 1 else None, torch)
@@ -421,10 +486,10 @@ def main():
     e_dev, _ = cm.energy(nl, p)
 
     # max over ranks
-    t = torch.tensor([total_ms, e2e_s, lf_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s, lf_ms, repl["wall_s"] if repl else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, lf_ms = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_s, lf_ms, repl_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -467,6 +532,14 @@ def main():
                          "ms_per_step": lf_ms / n_traj / L, "steps_per_s": world * n_traj * L / (lf_ms / 1e3),
                          "mvertex_steps_per_s": world * n_traj * L / (lf_ms / 1e3) * V / 1e6,
                          "trajectories": n_traj, "hamiltonian": lf_stats},
+            "replicas": None if not repl else {
+                "what": f"{repl['R']} independent {repl['V']}-vertex membranes per GPU (BASELINE config 5 sweep: kappa_b x volume_frac, "
+                        f"physical repulsion, verlet-list), each on its own stream; one {repl['L']}-step device-resident trajectory per "
+                        "replica per round, host wall clock around enqueue + wait, max over ranks",
+                "replicas_total": world * repl["R"], "steps_per_s": world * repl["R"] * repl["rounds"] * repl["L"] / repl_s,
+                "mvertex_steps_per_s": world * repl["R"] * repl["rounds"] * repl["L"] / repl_s * repl["V"] / 1e6,
+                "ms_per_step_per_replica_concurrent": 1e3 * repl_s / (repl["rounds"] * repl["L"]) / repl["R"],
+                "ms_per_step_one_replica_alone": repl["solo_ms_per_step"], "hamiltonian": repl["hamiltonian"]},
             "partitioned": part,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",

@@ -32,3 +32,24 @@ print("cabi get_positions pageable %.3f ms" % T(lambda: cm.positions()))
 print("np.empty+fill 15MB          %.3f ms" % T(lambda: np.empty_like(x0).fill(0.0)))
 a = np.empty_like(x0)
 print("memcpy 15MB warm            %.3f ms" % T(lambda: np.copyto(a, x0)))
+
+# raw PCIe copies of the same size through torch (pinned host memory), both directions
+try:
+    import torch
+    h = torch.empty(x0.size, dtype=torch.float64).pin_memory()
+    d = torch.empty(x0.size, dtype=torch.float64, device="cuda")
+    def h2d():
+        d.copy_(h, non_blocking=True); torch.cuda.synchronize()
+    def d2h():
+        h.copy_(d, non_blocking=True); torch.cuda.synchronize()
+    print("torch pinned H2D 15.7MB     %.3f ms" % T(h2d))
+    print("torch pinned D2H 15.7MB     %.3f ms" % T(d2h))
+except Exception as exc:
+    print("torch copy probe failed:", exc)
+for rep in range(3):
+    g = None
+    ts = []
+    for _ in range(10):
+        copy(); estore.energy(mesh)
+        t0 = time.perf_counter(); g = estore.gradient(mesh); ts.append(1e3 * (time.perf_counter() - t0))
+    print("gradient() in a step loop   " + " ".join("%.2f" % t for t in ts))

@@ -109,3 +109,46 @@ def test_argument_errors(gpu_core):
         gpu_core.vv_integrate(mesh, es, p0, 0.0, 1e-4, 2)
     with pytest.raises(RuntimeError):
         gpu_core.vv_integrate(mesh, es, p0, 1.0, 1e-4, -1)
+
+
+@pytest.mark.parametrize("name", ["vv_ico4_stress_verlet2", "vv_ico4_stress_cell2"])
+def test_repeated_trajectory_replays_identically(gpu_core, name):
+    """The second request of a trajectory is captured into a CUDA graph and later ones replay it
+    (tm_integrate.cu): direct launch, capture and replay must give the same bits, for both parities
+    of the gradient ping-pong, and a parameter change must not reuse a stale graph."""
+    gold = cases.load_golden(name)
+    case, p0, mass, dt, n = cases.vv_inputs(name)
+    mesh, es = cases.build(gpu_core, case)
+    x0 = mesh.points().copy()
+    runs = [gpu_core.vv_integrate(mesh, es, p0, mass, dt, n) for _ in range(5)]
+    for x, p, st in runs[1:]:
+        assert np.array_equal(x, runs[0][0]) and np.array_equal(p, runs[0][1]) and np.array_equal(st, runs[0][2])
+    assert nrm(runs[0][0] - x0, gold["x"] - x0) < TOL_TRAJ
+    # odd step count: the two gradient buffers change roles from call to call
+    odd = [gpu_core.vv_integrate(mesh, es, p0, mass, dt, 3) for _ in range(5)]
+    for x, p, st in odd[1:]:
+        assert np.array_equal(x, odd[0][0]) and np.array_equal(p, odd[0][1]) and np.array_equal(st, odd[0][2])
+    # a changed parameter is a different trajectory
+    es.eparams.kappa_b = 2.0 * es.eparams.kappa_b
+    xb, pb, stb = gpu_core.vv_integrate(mesh, es, p0, mass, dt, n)
+    assert not np.array_equal(xb, runs[0][0])
+    es.eparams.kappa_b = 0.5 * es.eparams.kappa_b
+    xa, pa, sta = gpu_core.vv_integrate(mesh, es, p0, mass, dt, n)
+    assert np.array_equal(xa, runs[0][0]) and np.array_equal(sta, runs[0][2])
+    # continuing a trajectory on the device (C ABI, no re-upload) through replays
+    he_to, he_next, he_face, v_he, _ = mesh.halfedge_arrays()
+    rp = es.eparams.repulse_params
+    kind = cabi.NLIST_CELL if rp.n_search == "cell-list" else cabi.NLIST_VERLET
+    par = workload.abi_params(es)
+    ends = []
+    for graph_legs in (False, True):
+        cm = cabi.Mesh(he_to, he_next, he_face, v_he, xyz=x0)
+        nl = cabi.NList(cm, kind, rp.rlist, rp.exclusion_level)
+        cm.set_momenta(p0)
+        if graph_legs:
+            for _ in range(n // 2):
+                cm.vv_integrate_async(nl, par, mass, dt, 2)          # same request over and over: replays
+        else:
+            cm.vv_integrate_async(nl, par, mass, dt, 2 * (n // 2))   # one direct launch sequence
+        ends.append((cm.positions(), cm.momenta()))
+    assert np.array_equal(ends[0][0], ends[1][0]) and np.array_equal(ends[0][1], ends[1][1])

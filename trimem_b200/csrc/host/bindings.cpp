@@ -7,6 +7,7 @@
 #include <pybind11/stl.h>
 
 #include <map>
+#include <set>
 #include <mutex>
 #include <sstream>
 #include <vector>
@@ -83,6 +84,16 @@ public:
                 return p;
             }
         }
+        // first block of this size: the usual caller keeps the previous result alive while it asks
+        // for the next one (g = estore.gradient(mesh) in a loop), so two blocks circulate; pinning a
+        // 16 MB block costs ~15 ms, which belongs here and not into the caller's second step
+        if (!seen_.count(bytes)) {
+            seen_.insert(bytes);
+            if (void* spare = tm_host_alloc(bytes)) {
+                std::lock_guard<std::mutex> lk(mu_);
+                free_[bytes].push_back(spare);
+            }
+        }
         return tm_host_alloc(bytes);
     }
     void give(void* p, size_t bytes) {
@@ -96,6 +107,7 @@ public:
 private:
     std::mutex mu_;
     std::map<size_t, std::vector<void*>> free_;
+    std::set<size_t> seen_;
 };
 
 struct PinnedBlock { void* p; size_t bytes; };

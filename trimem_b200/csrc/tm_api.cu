@@ -102,6 +102,7 @@ int check_mesh(tm_mesh* m, bool need_layout = true) {
     TM_CHECK(m != nullptr, "null mesh handle");
     TM_CHECK(m->V > 0 && m->he_to_h != nullptr, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CUDA(cudaSetDevice(m->device));
+    if (tm_join_pairs(m)) return 1;
     if (need_layout && tm_ensure_layout(m)) return 1;
     return 0;
 }
@@ -174,6 +175,9 @@ int tm_mesh_create(int device, tm_mesh** out) {
     TM_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     TM_CUDA(cudaEventCreate(&m->ev0));
     TM_CUDA(cudaEventCreate(&m->ev1));
+    TM_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    TM_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    TM_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     TM_CUDA(cudaMalloc(&m->sums, sizeof(double) * 8));
     TM_CUDA(cudaMalloc(&m->ticket, sizeof(unsigned) * 4));
     TM_CUDA(cudaMemset(m->ticket, 0, sizeof(unsigned) * 4));
@@ -187,6 +191,7 @@ int tm_mesh_create(int device, tm_mesh** out) {
 int tm_mesh_destroy(tm_mesh* m) {
     if (!m) return 0;
     cudaSetDevice(m->device);
+    cudaStreamSynchronize(m->stream2);
     cudaStreamSynchronize(m->stream);
     tm_flips_release(m);
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
@@ -196,10 +201,13 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     tm_part_release(m);
+    tm_vv_release(m);
     cudaFree(m->mom); cudaFree(m->grad_prev); cudaFree(m->dot_part); cudaFree(m->d_stats);
     if (m->h_stats) cudaFreeHost(m->h_stats);
     cudaFreeHost(m->h_sums);
     cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
+    cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
+    cudaStreamDestroy(m->stream2);
     cudaStreamDestroy(m->stream);
     delete m;
     return 0;

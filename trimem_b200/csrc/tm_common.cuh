@@ -121,6 +121,11 @@ struct tm_mesh {
     int sm_count = 148;          // multiprocessors of the device (persistent grids)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // the pair sweep depends on positions only, like the ring property sweep: it runs beside it on
+    // a second stream (fork after the positions are final, join before its first consumer)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool pairs_inflight = false;
     int V = 0, HE = 0;
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
@@ -151,6 +156,7 @@ struct tm_mesh {
     double* d_stats = nullptr;   // 16: what h_stats receives, collected on the device during a trajectory
     // vertex-partitioned evaluation across devices (tm_part.cu); nullptr = whole mesh on this device
     struct tm_part* part = nullptr;
+    struct tm_vvcache* vvcache = nullptr;   // captured trajectories (tm_integrate.cu)
     double* frep = nullptr;      // V*3 pair force of the last pair sweep (allocated on demand)
     unsigned long long frep_epoch = 0;     // pos_epoch, potential and list it was evaluated for
     double frep_lc1 = 0; int frep_r = 0; unsigned long long frep_list = 0;
@@ -241,10 +247,12 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p);  // tm_energy.cu
 int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); // tm_energy.cu (force only)
+int tm_join_pairs(tm_mesh* m);   // tm_energy.cu: the mesh's stream waits for a pair sweep still running beside it
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
 double tm_energy_from_props(const tm_energy_params& p, const double s[6]);    // tm_api.cu (kernel.h:110-122)
 int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
               bool with_energies);                               // tm_integrate.cu
+void tm_vv_release(tm_mesh* m);                                  // tm_integrate.cu
 int tm_import_momenta(tm_mesh* m, const double* p_host);         // tm_integrate.cu
 int tm_export_vec3_owned(tm_mesh* m, const double* dev, double* host);   // tm_integrate.cu (async copy)
 // vertices this device sweeps (whole mesh, or the owned slice of a partitioned mesh)   tm_part.cu

@@ -678,14 +678,27 @@ static bool pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy
            m->frep_list == nl.serial;
 }
 
+bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
+    return nl.kind >= 0 && pair_force_valid(m, nl, p);
+}
+
 // pair sweep: energy partials (quantity 5) and/or per-vertex force
+// beside = on the mesh's second stream, concurrently with whatever the caller launches next on the
+// main stream (the ring property sweep); tm_join_pairs before the first consumer
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
-                        int nwarps) {
+                        int nwarps, bool beside = false) {
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
     const SweepRange R = tm_owned_range(m);
     const int nb = (R.count + PAIR_THREADS - 1) / PAIR_THREADS;
     MeshView mv = m->view();
-#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, 0, m->stream>>>( \
+    cudaStream_t st = m->stream;
+    if (beside) {
+        if (tm_join_pairs(m)) return 1;
+        TM_CUDA(cudaEventRecord(m->ev_fork, m->stream));
+        TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+        st = m->stream2;
+    }
+#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, 0, st>>>( \
         mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
@@ -694,8 +707,19 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
 #undef TM_PAIRS
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
+    if (beside) {
+        TM_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        m->pairs_inflight = true;
+    }
     m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
     m->frep_list = nl.serial;
+    return 0;
+}
+
+int tm_join_pairs(tm_mesh* m) {
+    if (!m->pairs_inflight) return 0;
+    TM_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    m->pairs_inflight = false;
     return 0;
 }
 
@@ -719,9 +743,16 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     // quantities the ring sweep reduces: geometry + bending (4) for the gradient's sweep, all but
     // the repulsion when a pair sweep follows, else all six (repulsion = 0)
     const int nq = !full ? 4 : (pairs ? 5 : 6);
+    // The pair sweep runs beside the ring sweep: with the energy (full), or force-only for the gradient
+    // sweep that follows a geometry-only property sweep (joined in tm_launch_grad).
+    const bool pairs_for_grad = !full && nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0 && !pair_force_valid(m, nl, p);
     if (write_vprops) {
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
         TM_CUDA(cudaMemsetAsync(m->vprops, 0, sizeof(double) * 6 * (size_t)m->V, m->stream));
+    }
+    if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps, true)) return 1;
+    if (pairs_for_grad && launch_pairs(m, nl, p, false, false, 0, true)) return 1;
+    if (write_vprops) {
         k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq, R);
     } else if (full) {
         k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
@@ -737,7 +768,7 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
             mv, P, m->pos, nullptr, m->partials, 0, 0, G);
         TM_LAUNCHED();
     }
-    if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps)) return 1;
+    if (pairs && tm_join_pairs(m)) return 1;            // the reduction adds the pair sweep's partials
     int rb = (nwarps + 4 * RT - 1) / (4 * RT);
     rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
     const int per = (nwarps + rb - 1) / rb;
@@ -760,6 +791,7 @@ int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
     if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
+    if (tm_join_pairs(m)) return 1;
     const SweepRange R = tm_owned_range(m);
     int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     DevParams P = tm_to_dev(p);

@@ -150,8 +150,8 @@ int kinetic(tm_mesh* m, double mass, double* out_dev) {
 
 }  // namespace
 
-int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
-              bool with_energies) {
+static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
+                         bool with_energies) {
     if (ensure_state(m) || tm_part_refresh(m, nl)) return 1;
     const double dt2 = dt * dt;
     if (with_energies) {
@@ -193,6 +193,119 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
         if (kinetic(m, mass, m->d_stats + 13)) return 1;
         TM_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+// ---- trajectory as a CUDA graph ------------------------------------------------------------
+// A trajectory is ~6 launches per step; on a 40,962-vertex membrane each kernel runs for 4-8 us, so
+// a chain of them (and even more so eight replicas' chains issued by one host thread) is bound by
+// launch cost, not by the device. The second time the same trajectory is requested (same step
+// count, step size, mass, parameters, neighbour list, connectivity, cache state and gradient-buffer
+// parity) the launch sequence is captured into a graph -- including the pair sweep's side stream --
+// and from then on replayed with one cudaGraphLaunch; the host-side bookkeeping the launch functions
+// do (epochs, buffer ping-pong) is replayed beside it. Partitioned meshes launch directly: their
+// exchange kernels carry sequence numbers as arguments. TM_VV_GRAPH=0 disables.
+struct VVKey {
+    int n_steps, with_e, geo_valid, frep_valid, V;
+    double mass, dt;
+    tm_energy_params p;
+    unsigned long long nl_serial, topo_epoch, layout_epoch;
+    const double* grad;
+};
+struct VVGraph {
+    VVKey key;
+    cudaGraphExec_t exec = nullptr;
+    int uses = 0;
+    unsigned long long launches = 0, stamp = 0;
+    bool frep_touched = false;
+};
+struct tm_vvcache {
+    VVGraph g[4];
+    unsigned long long clock = 0;
+    bool disabled = false;
+};
+
+bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p);   // tm_energy.cu
+
+static bool same_key(const VVKey& a, const VVKey& b) { return memcmp(&a, &b, sizeof(VVKey)) == 0; }
+
+void tm_vv_release(tm_mesh* m) {
+    if (!m->vvcache) return;
+    for (auto& g : m->vvcache->g) if (g.exec) cudaGraphExecDestroy(g.exec);
+    delete m->vvcache;
+    m->vvcache = nullptr;
+}
+
+int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
+              bool with_energies) {
+    static const bool enabled = [] { const char* e = getenv("TM_VV_GRAPH"); return !(e && e[0] == '0'); }();
+    if (!enabled || m->part || n_steps < 1) return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+    if (!m->vvcache) m->vvcache = new tm_vvcache();
+    tm_vvcache* C = m->vvcache;
+    if (C->disabled) return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+
+    VVKey key;
+    memset(&key, 0, sizeof(key));
+    key.n_steps = n_steps; key.with_e = with_energies; key.V = m->V;
+    key.geo_valid = m->geo_epoch == m->pos_epoch;
+    key.frep_valid = tm_pair_force_valid(m, nl, p);
+    key.mass = mass; key.dt = dt;
+    memcpy(&key.p, &p, sizeof(p));
+    key.p._pad = 0;
+    key.nl_serial = nl.kind >= 0 ? nl.serial : 0;
+    key.topo_epoch = m->topo_epoch; key.layout_epoch = m->layout_epoch;
+    key.grad = m->grad;
+
+    VVGraph* slot = nullptr;
+    for (auto& g : C->g) if (g.uses > 0 && same_key(g.key, key)) slot = &g;
+    if (!slot) {                                   // first request: run directly (allocates what is needed), remember
+        slot = &C->g[0];
+        for (auto& g : C->g) if (g.stamp < slot->stamp) slot = &g;
+        if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+        slot->key = key; slot->uses = 1; slot->stamp = ++C->clock;
+        return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+    }
+    slot->stamp = ++C->clock;
+    slot->uses++;
+    if (!slot->exec) {
+        // second request: capture. The launch functions update host-side state while they enqueue;
+        // snapshot it so that a failed capture can be undone and rerun directly.
+        const tm_mesh snap = *m;
+        const unsigned long long l0 = g_tm_launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            const int rc = vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+            const cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
+            ok = rc == 0 && e == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();
+            tm_vvcache* keep = m->vvcache;
+            *m = snap;
+            m->vvcache = keep;
+            g_tm_launches = l0;
+            C->disabled = true;
+            slot->exec = nullptr;
+            return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+        }
+        slot->launches = g_tm_launches - l0;
+        slot->frep_touched = m->frep_epoch == m->pos_epoch;
+        TM_CUDA(cudaGraphLaunch(slot->exec, m->stream));
+        return 0;
+    }
+    // replay: one launch, plus the bookkeeping of vv_run_direct
+    TM_CUDA(cudaGraphLaunch(slot->exec, m->stream));
+    g_tm_launches += slot->launches;
+    m->pos_epoch += (unsigned long long)n_steps;
+    m->geo_epoch = m->pos_epoch;
+    m->grad_epoch = m->pos_epoch;
+    if (slot->frep_touched) {
+        m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r; m->frep_list = nl.serial;
+    }
+    if (n_steps & 1) std::swap(m->grad, m->grad_prev);
     return 0;
 }
 
