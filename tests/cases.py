@@ -109,3 +109,13 @@ def vv_inputs(name):
     v, _ = mesh_of(case)
     p0 = scale * np.random.default_rng(seed).normal(size=v.shape)
     return case, p0, mass, dt, n
+
+
+# HMC chains (reference: HMC.step, src/trimem/mc/hmc.py:133-190): name -> (case, numpy seed, options, steps)
+HMC_CASES = {
+    "hmc_ico3_edge": ("ico3_edge", 21, {"time_step": 2.0e-3, "num_integration_steps": 5, "info_step": 0}, 6),
+    "hmc_ico4_stress_verlet2": ("ico4_stress_verlet2", 22, {"time_step": 1.0e-5, "num_integration_steps": 8,
+                                                             "initial_temperature": 50.0, "info_step": 0}, 5),
+    "hmc_ico3_cooling": ("ico3_area", 23, {"time_step": 2.0e-3, "num_integration_steps": 4, "info_step": 0,
+                                           "cooling_factor": 0.5, "cooling_start_step": 1, "mass": 2.0}, 5),
+}

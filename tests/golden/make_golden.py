@@ -216,6 +216,33 @@ def trajectory_cases():
         save(name, x=xn, p=pn, stats=np.array([u0, k0, u1, k1]), moved=np.array([np.abs(xn - x0).max()]))
 
 
+def hmc_chain_cases():
+    """Chains of the reference's own HMC class (src/trimem/mc/hmc.py:48-190) on the reference build."""
+    hmc = reference_hmc_module()
+    import contextlib, io
+    for name, (case, seed, opts, nsteps) in cases.HMC_CASES.items():
+        mesh, es = cases.build(ref, case)
+        x0 = mesh.points().copy()
+
+        def nlog_prob(x):
+            np.copyto(mesh.points(), x)
+            return es.energy(mesh)
+
+        def grad(x):
+            np.copyto(mesh.points(), x)
+            return es.gradient(mesh)
+
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            chain = hmc.HMC(x0, nlog_prob, grad, counter=hmc.get_step_counters(), options=dict(opts))
+            xs, accs = [], []
+            for _ in range(nsteps):
+                chain.step()
+                xs.append(chain.x.copy())
+                accs.append(chain.acc)
+        save(name, xs=np.array(xs), acc=np.array(accs), temperature=np.array([chain.T]))
+
+
 def thread_spread():
     """The reference's own 1-vs-N-thread spread on the headline case (its noise floor)."""
     import subprocess
@@ -232,7 +259,7 @@ def thread_spread():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory"]
+    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc"]
     if "topology" in which: topology_cases()
     if "analytic" in which: analytic_cases()
     if "primitives" in which: primitive_cases()
@@ -241,3 +268,4 @@ if __name__ == "__main__":
     if "energy" in which: energy_cases()
     if "spread" in which: thread_spread()
     if "trajectory" in which: trajectory_cases()
+    if "hmc" in which: hmc_chain_cases()

@@ -152,3 +152,32 @@ def test_repeated_trajectory_replays_identically(gpu_core, name):
             cm.vv_integrate_async(nl, par, mass, dt, 2 * (n // 2))   # one direct launch sequence
         ends.append((cm.positions(), cm.momenta()))
     assert np.array_equal(ends[0][0], ends[1][0]) and np.array_equal(ends[0][1], ends[1][1])
+
+
+@pytest.mark.parametrize("name", list(cases.HMC_CASES))
+def test_hmc_chain_vs_reference_hmc(gpu_core, name):
+    """trimem_b200.hmc.MeshHMC (device-resident trajectory) against chains of the reference's own HMC
+    class run on the reference build with the same numpy seed (tests/golden/make_golden.py
+    hmc_chain_cases): the same states, the same accept/reject decisions, the same temperature schedule."""
+    from trimem_b200 import hmc
+    gold = cases.load_golden(name)
+    case, seed, opts, nsteps = cases.HMC_CASES[name]
+    mesh, es = cases.build(gpu_core, case)
+    x0 = mesh.points().copy()
+    np.random.seed(seed)
+    chain = hmc.MeshHMC(mesh, es, options=dict(opts), verbose=False)
+    prev = x0
+    for k in range(nsteps):
+        mine_before = chain.x.copy()
+        chain.step()
+        assert chain.acc == int(gold["acc"][k])
+        want = gold["xs"][k]
+        moved = np.linalg.norm(want - prev)
+        if moved == 0.0:
+            assert np.array_equal(chain.x, mine_before)           # rejected: the state stays
+        else:
+            assert np.linalg.norm((chain.x - prev) - (want - prev)) < 1e-8 * moved
+        assert np.array_equal(mesh.points(), chain.x)             # MeshHMC.step updates the mesh
+        prev = want
+    assert abs(chain.T - float(gold["temperature"][0])) <= 1e-15 * chain.T
+    assert chain.counter["move"] == nsteps
