@@ -91,10 +91,12 @@ def main_gpu(out):
     x = cm.positions()
     kin = np.sum(allgather(np.array([st[1], st[3]])), axis=0)
     nl2 = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
-    n_entries = nl2.info()[0]
-    es_all = allgather((e, tuple(props), st[0], st[2], x.tobytes(), n_entries))
+    n_entries = sum(allgather(nl2.info()[0]))          # every rank holds the rows of its own vertices
+    es_all = allgather((e, tuple(props), st[0], st[2], x.tobytes()))
     assert all(t == es_all[0] for t in es_all), "ranks disagree on global results"
     if rank == 0:
+        one = cabi.Mesh(*arrs, xyz=x, device=dev)      # the same list on one device
+        assert cabi.NList(one, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level).info()[0] == n_entries
         np.savez(out, energy=e, props=props, grad=g, x=x, p=p, stats=np.array([st[0], kin[0], st[2], kin[1]]),
                  n_entries=n_entries, info=np.array(list(cm.part_info().values())))
 

@@ -140,9 +140,14 @@ def test_rebuild_after_trajectory_and_allsum(gpu_core):
     one = cabi.Mesh(*arrs, xyz=x_end)
     nl1 = cabi.NList(one, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
     d1 = nl1.distance_matrix(rp.rlist)
-    for r in range(2):
-        d = new[r].distance_matrix(rp.rlist)
-        assert np.array_equal(d[1], d1[1]) and np.array_equal(d[2], d1[2])
+    # every rank builds the rows of the vertices it owns; together they are the single-device list
+    parts = [new[r].distance_matrix(rp.rlist) for r in range(2)]
+    key1 = d1[1].astype(np.int64) * one.V + d1[2]
+    keyp = np.concatenate([p[1].astype(np.int64) * one.V + p[2] for p in parts])
+    assert len(keyp) == len(key1) and np.array_equal(np.sort(keyp), np.sort(key1))
+    order = np.argsort(keyp)
+    assert np.array_equal(np.concatenate([p[0] for p in parts])[order], d1[0][np.argsort(key1)])
+    assert sum(new[r].info()[0] for r in range(2)) == nl1.info()[0]
     assert nrm(x_end - R.v, gold["x"] - R.v) < 1e-9
 
 

@@ -195,6 +195,7 @@ struct tm_nlist {
     int *cell_start = nullptr, *cell_items = nullptr;
     int *row_cnt = nullptr, *row_j = nullptr;
     int row_cap = 0;
+    int rows_first = 0, rows_count = 0;   // vertices whose verlet rows were built (all, or a partition's slice)
     unsigned long long serial = 0;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
     long long n_entries = 0;

@@ -382,6 +382,9 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     // cell lists evaluate exclusions on the live connectivity: keep the ring table usable for
     // everything outside the sweep, and walk half-edges inside it
     if (tm_check_nlist(m, nl) || ensure_ws(m, n)) return 1;
+    TM_CHECK(!nl || nl->kind != TM_NLIST_VERLET || nl->rows_count == m->V,
+             "flip sweeps read the rows of arbitrary vertices: this verlet list holds a partition's slice only "
+             "(use a cell list, or a list built before tm_part_create)");
     FlipWS* ws = (FlipWS*)m->flipws;
     cudaStream_t st = m->stream;
     const DevParams P = tm_to_dev(*p);
@@ -441,6 +444,8 @@ int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* 
     if (check(m, p)) return 1;
     TM_CHECK(edge >= 0 && edge < m->HE / 2, "edge %d out of range", edge);
     if (tm_check_nlist(m, nl) || ensure_ws(m, 1)) return 1;
+    TM_CHECK(!nl || nl->kind != TM_NLIST_VERLET || nl->rows_count == m->V,
+             "this verlet list holds a partition's slice only");
     FlipWS* ws = (FlipWS*)m->flipws;
     TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, m->stream));
     k_evp<<<1, 32, 0, m->stream>>>(m->view(), topo_of(m), nl ? nl->view() : tm_no_nlist(), tm_to_dev(*p), edge,

@@ -311,6 +311,12 @@ int tm_check_nlist(const tm_mesh* m, const tm_nlist* nl) {
     TM_CHECK(nl->V == m->V, "neighbour list was built for %d vertices, mesh has %d", nl->V, m->V);
     TM_CHECK(nl->layout_epoch == m->layout_epoch,
              "neighbour list is stale: the mesh's vertex order changed after it was built (rebuild it)");
+    if (nl->kind == TM_NLIST_VERLET) {
+        const SweepRange R = tm_owned_range(m);
+        TM_CHECK(nl->rows_first <= R.first && nl->rows_first + nl->rows_count >= R.first + R.count,
+                 "verlet list holds the rows of vertices [%d, %d) but the mesh now evaluates [%d, %d): rebuild it",
+                 nl->rows_first, nl->rows_first + nl->rows_count, R.first, R.first + R.count);
+    }
     return 0;
 }
 

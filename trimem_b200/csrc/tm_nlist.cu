@@ -131,10 +131,11 @@ __device__ __forceinline__ bool in_sorted(const int* __restrict__ v, int b, int 
 __global__ void __launch_bounds__(128)
 k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
                 const int* __restrict__ ex2_off, const int* __restrict__ ex2_v, int excl, double rlist,
-                int cap, int* __restrict__ row_j, int* __restrict__ row_cnt, int* __restrict__ maxcnt) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
+                int cap, int* __restrict__ row_j, int* __restrict__ row_cnt, int* __restrict__ maxcnt, SweepRange R) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const int i = R.first + t;
     int n = 0;
-    if (i < mv.V) {
+    if (t < R.count) {
         const d3 xi = ldpos(mv.pos, i);
         int c[3];
         vcell(g, xi, c);
@@ -372,14 +373,19 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
 
     nl->row_cnt = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)V);
     TM_CHECK(nl->row_cnt, "out of device memory for verlet rows");
+    // a partitioned mesh builds the rows of the vertices it owns (the only rows its sweeps read); the
+    // cell grid above covers every vertex, so owned rows list non-owned neighbours as they should
+    const SweepRange R = tm_owned_range(m);
+    nl->rows_first = R.first; nl->rows_count = R.count;
+    if (R.count < V) TM_CUDA(cudaMemsetAsync(nl->row_cnt, 0, sizeof(int) * (size_t)V, m->stream));
     int cap = m->verlet_cap_hint > 0 ? m->verlet_cap_hint : 32;
     for (int attempt = 0; attempt < 3; attempt++) {
         nl->row_cap = cap;
         nl->row_j = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)cap * 32 * ((V + 31) / 32));
         TM_CHECK(nl->row_j, "out of device memory for verlet rows of width %d", cap);
-        k_verlet_search<<<(V + 127) / 128, 128, 0, m->stream>>>(m->view(), g, start.p, items.p, m->ex2_off, m->ex2_v,
-                                                                nl->excl, nl->rlist, cap, nl->row_j,
-                                                                nl->row_cnt, maxcnt.p);
+        k_verlet_search<<<(R.count + 127) / 128, 128, 0, m->stream>>>(m->view(), g, start.p, items.p, m->ex2_off, m->ex2_v,
+                                                                      nl->excl, nl->rlist, cap, nl->row_j,
+                                                                      nl->row_cnt, maxcnt.p, R);
         TM_LAUNCHED();
         TM_CUDA(cudaGetLastError());
         int widest = 0;
