@@ -206,6 +206,57 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
             "hamiltonian": {"H0": st[0] + st[1], "H1": st[2] + st[3], "time_step": dt}}
 
 
+def hmc_step_run(args, core, workload, rank):
+    """BASELINE config 2: the pieces of one full HMC step at 40,962 vertices through the public API
+    (trimem_b200.core / trimem_b200.hmc): a 10-step trajectory move with cell-list stress repulsion,
+    update_repulsion, and the batch-parallel flip sweep pflip(ratio 0.1) that runs every 10 moves
+    (flip statistics on the physical variant with all kappa = 1, as tests/test_flips.py of the reference)."""
+    from trimem_b200 import hmc
+    out = {}
+    mesh, estore, x0 = workload.make_case(core, 6, repulsion="stress", n_search="cell-list")
+    V = mesh.n_vertices()
+    np.random.seed(5)
+    chain = hmc.MeshHMC(mesh, estore, options={"time_step": 1.0e-6, "num_integration_steps": 10, "info_step": 0,
+                                               "initial_temperature": 1.0e3}, verbose=False)
+    for _ in range(3):
+        chain.step()
+    n = 10
+    t0 = time.perf_counter()
+    for _ in range(n):
+        chain.step()
+    out["hmc_move_ms"] = 1e3 * (time.perf_counter() - t0) / n
+    out["hmc_acceptance"] = chain.acc / max(chain.i, 1)
+    estore.update_repulsion(mesh)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        estore.update_repulsion(mesh)
+    out["update_repulsion_cell_list_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    e = estore.energy(mesh); g = estore.gradient(mesh)
+    out["eg_cell_list_ms_host_buffers"] = 1e3 * (time.perf_counter() - t0)
+    # flips
+    fmesh, festore, _ = workload.make_case(core, 6, repulsion="physical", n_search="cell-list",
+                                           kappa=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0), fracs=(1.0, 1.0, 1.0))
+    core.pflip(fmesh, festore, 0.1, seed=1)
+    acc, ts = [], []
+    for k in range(5):
+        t0 = time.perf_counter()
+        acc.append(core.pflip(fmesh, festore, 0.1, seed=10 + k))
+        ts.append(1e3 * (time.perf_counter() - t0))
+    out["pflip_ms"] = float(np.median(ts))
+    out["pflip_proposals"] = int(fmesh.n_edges() * 0.1)
+    out["pflip_acceptance"] = float(np.mean(acc)) / out["pflip_proposals"]
+    t0 = time.perf_counter()
+    a = core.flip(fmesh, festore, 0.1, seed=3)
+    out["flip_serial_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["flip_serial_acceptance"] = a / out["pflip_proposals"]
+    out["what"] = (f"icosphere subdiv=6 ({V} vertices), public API with host buffers: MeshHMC.step() = 10 velocity-Verlet steps "
+                   "on the device + Metropolis (stress repulsion, cell-list, excl 2); update_repulsion; "
+                   "pflip / flip over 10 % of the edges on the physical variant with kappa = 1")
+    out["mvertex_steps_per_s_hmc_move"] = V * 10 / (out["hmc_move_ms"] * 1e-3) / 1e6
+    return out
+
+
 def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist, torch):
     """BASELINE config 4: ONE mesh (subdiv --part-subdiv) whose vertices are partitioned across the ranks
     (csrc/tm_part.cu): E+G evals/s and leapfrog steps/s of the whole mesh, strong scaling. At one rank the
@@ -323,6 +374,7 @@ def main():
     ap.add_argument("--no-partition", action="store_true", help="skip the partitioned-mesh measurement")
     ap.add_argument("--replicas", type=int, default=8,
                     help="independent 40,962-vertex membranes per GPU in the replica measurement (BASELINE config 5; 0 = skip)")
+    ap.add_argument("--no-hmc-step", action="store_true", help="skip the config-2 HMC-step measurement")
     ap.add_argument("--leapfrog-steps", type=int, default=10, help="velocity-Verlet steps per timed trajectory")
     args = ap.parse_args()
 
@@ -357,6 +409,9 @@ def main():
     import torch
     import torch.distributed as dist
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...") off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
@@ -478,6 +533,7 @@ def main():
     cm.set_positions(x0)
 
     repl = replica_run(args, core, cabi, workload, rank, world, local, barrier) if args.replicas > 0 else None
+    hmc2 = hmc_step_run(args, core, workload, rank) if (rank == 0 and not args.no_hmc_step) else None
     part = None
     if not args.no_partition:
         part = partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist if world > 1 else None, torch)
@@ -540,6 +596,7 @@ def main():
                 "mvertex_steps_per_s": world * repl["R"] * repl["rounds"] * repl["L"] / repl_s * repl["V"] / 1e6,
                 "ms_per_step_per_replica_concurrent": 1e3 * repl_s / (repl["rounds"] * repl["L"]) / repl["R"],
                 "ms_per_step_one_replica_alone": repl["solo_ms_per_step"], "hamiltonian": repl["hamiltonian"]},
+            "hmc_step_config2": hmc2,
             "partitioned": part,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",

@@ -85,6 +85,8 @@ struct MeshView {
     const int* ring_v;     // HE entries, flags in the two top bits
     const R8* ring8;       // V fixed-width rows (see TM_RING_PAD / TM_RING_GENERIC)
     const P4* pos;         // V packed (x, y, z, rho) records, device vertex numbering
+    const int* ex2_off;    // sorted two-ring rows (exclusion level 2), valid after tm_ensure_ring2
+    const int* ex2_v;
 };
 
 // Vertices one sweep launch covers: device slots [first, first + count), or the explicit list
@@ -180,6 +182,7 @@ struct tm_mesh {
         v.V = V; v.HE = HE;
         v.he_to = he_to; v.he_next = he_next; v.he_face = he_face; v.v_he = v_he;
         v.ring_off = ring_off; v.ring_v = ring_v; v.ring8 = ring8; v.pos = pos;
+        v.ex2_off = ex2_off; v.ex2_v = ex2_v;
         return v;
     }
 };

@@ -366,7 +366,7 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
                 }
             }
         } else {
-            for_each_pair_fast<false, true>(mv, nl, i, xi, C.lc1sq, [&](int, d3 dv, double l2) {
+            cell_pairs_batched(mv, nl, i, xi, C.lc1sq, [&](int, d3 dv, double l2) {
                 double phi, sl;
                 pair_eval<R2>(C, rr, l2, true, phi, sl);
                 if (WITH_E) rep += phi;
@@ -688,6 +688,8 @@ bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_par
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
                         int nwarps, bool beside = false) {
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
+    // cell lists test exclusion level 2 against the sorted two-ring rows (rebuilt when the connectivity changed)
+    if (nl.kind == TM_NLIST_CELL && nl.excl == 2 && tm_ensure_ring2(m)) return 1;
     const SweepRange R = tm_owned_range(m);
     const int nb = (R.count + PAIR_THREADS - 1) / PAIR_THREADS;
     MeshView mv = m->view();

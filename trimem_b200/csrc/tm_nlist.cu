@@ -117,17 +117,6 @@ __global__ void k_vcell_count(VGrid g, const P4* __restrict__ pos, int V, int* _
     atomicAdd(count + id, 1);
 }
 
-// is j in the sorted row [b, e)?
-__device__ __forceinline__ bool in_sorted(const int* __restrict__ v, int b, int e, int j) {
-    while (b < e) {
-        const int mid = (b + e) >> 1;
-        const int x = __ldg(v + mid);
-        if (x == j) return true;
-        if (x < j) b = mid + 1; else e = mid;
-    }
-    return false;
-}
-
 __global__ void __launch_bounds__(128)
 k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
                 const int* __restrict__ ex2_off, const int* __restrict__ ex2_v, int excl, double rlist,
