@@ -243,47 +243,80 @@ __global__ void k_batch_apply(Topo t, int nrem, const int* __restrict__ rem, con
     if (sel[p] == want) d_flip(t, edges[p]);
 }
 
-// ordered Metropolis scan over the round (single thread: inherently sequential, ~50 flops per
-// proposal); also compacts the not-yet-processed proposals for the next round and appends
+// ordered Metropolis scan over the round (the decisions are sequential, ~50 flops per
+// proposal; the warp fetches 32 proposals' data at a time); also compacts the not-yet-processed proposals for the next round and appends
 // the applied / reverted flips to the replay list.
 __global__ void k_batch_metropolis(DevParams P, int nrem, const int* __restrict__ rem, int* __restrict__ rem_next,
                                    const double* __restrict__ u, const int* __restrict__ edges,
                                    int* __restrict__ sel, const double* __restrict__ before,
                                    const double* __restrict__ after, double* __restrict__ state,
                                    int* __restrict__ flips, int* __restrict__ counters) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    // One warp. The decisions are inherently sequential (every acceptance changes the global sums the
+    // next energy difference is taken against), but the DATA of 32 proposals are fetched by the 32
+    // lanes at once and handed round by shuffles, so the scan costs ~100 cycles per proposal instead
+    // of a chain of dependent global loads. Every lane carries the same running state.
+    if (blockIdx.x != 0) return;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     double props[6];
     for (int q = 0; q < 6; q++) props[q] = state[q];
     double e0 = state[6];
     int nflips = counters[1], nacc = counters[2], nnext = 0;
-    // replay list of this round: first every applied flip ...
-    for (int r = 0; r < nrem; r++) {
-        const int p = rem[r];
-        if (sel[p] == 1) flips[nflips++] = edges[p];
+    // replay list of this round: first every applied flip, in proposal order ...
+    for (int r0 = 0; r0 < nrem; r0 += 32) {
+        const int r = r0 + lane;
+        const int p = r < nrem ? rem[r] : -1;
+        const int s = p >= 0 ? sel[p] : -1;
+        const unsigned applied = __ballot_sync(FULL, s == 1);
+        if (s == 1) flips[nflips + __popc(applied & ((1u << lane) - 1))] = edges[p];
+        nflips += __popc(applied);
     }
-    for (int r = 0; r < nrem; r++) {
-        const int p = rem[r];
-        const int s = sel[p];
-        if (s == 0) { rem_next[nnext++] = p; continue; }
-        if (s != 1) continue;
-        // flips.cpp:133-160: dprops = before - after; props -= dprops
-        double d[6];
-        for (int q = 0; q < 6; q++) { d[q] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q]; props[q] -= d[q]; }
-        const double en = energy_of(P, props);
-        const double de = en - e0;
-        const double alpha = de < 0.0 ? 1.0 : exp(-de);
-        if (u[p] <= alpha) {
-            e0 = en;
-            ++nacc;
-        } else {
-            for (int q = 0; q < 6; q++) props[q] += d[q];
-            sel[p] = 3;                      // rejected: flip back
-            flips[nflips++] = edges[p];      // ... then every reverted flip
+    for (int r0 = 0; r0 < nrem; r0 += 32) {
+        const int r = r0 + lane;
+        const int p = r < nrem ? rem[r] : -1;
+        const int s = p >= 0 ? sel[p] : -1;
+        // not selected this round: carried over, order kept
+        const unsigned carry = __ballot_sync(FULL, s == 0);
+        if (s == 0) rem_next[nnext + __popc(carry & ((1u << lane) - 1))] = p;
+        nnext += __popc(carry);
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        double up = 0.0;
+        int ed = 0;
+        if (s == 1) {
+            for (int q = 0; q < 6; q++) d[q] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q];
+            up = u[p];
+            ed = edges[p];
         }
+        unsigned todo = __ballot_sync(FULL, s == 1);
+        bool rejected = false;
+        while (todo) {
+            const int k = __ffs(todo) - 1;
+            todo &= todo - 1;
+            // flips.cpp:133-160: dprops = before - after; props -= dprops
+            double dk[6];
+            for (int q = 0; q < 6; q++) { dk[q] = __shfl_sync(FULL, d[q], k); props[q] -= dk[q]; }
+            const double uk = __shfl_sync(FULL, up, k);
+            const int ek = __shfl_sync(FULL, ed, k);
+            const double en = energy_of(P, props);
+            const double de = en - e0;
+            const double alpha = de < 0.0 ? 1.0 : exp(-de);
+            if (uk <= alpha) {
+                e0 = en;
+                ++nacc;
+            } else {
+                for (int q = 0; q < 6; q++) props[q] += dk[q];
+                if (lane == k) rejected = true;
+                if (lane == 0) flips[nflips] = ek;       // ... then every reverted flip
+                ++nflips;
+            }
+        }
+        if (rejected) sel[p] = 3;                        // rejected: flip back
     }
-    for (int q = 0; q < 6; q++) state[q] = props[q];
-    state[6] = e0;
-    counters[0] = nnext; counters[1] = nflips; counters[2] = nacc;
+    if (lane == 0) {
+        for (int q = 0; q < 6; q++) state[q] = props[q];
+        state[6] = e0;
+        counters[0] = nnext; counters[1] = nflips; counters[2] = nacc;
+    }
 }
 
 __global__ void k_iota(int n, int* a) {
