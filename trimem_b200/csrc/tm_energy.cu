@@ -312,6 +312,7 @@ __device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2,
 #define TM_PAIR_BATCH 4
 #endif
 constexpr int PAIR_THREADS = TM_PAIR_NT;
+constexpr int PAIR_QCAP = 48;                   // queued hits per thread before an early flush (cell lists)
 constexpr int PB = TM_PAIR_BATCH;
 template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2>
 __global__ void __launch_bounds__(PAIR_THREADS, TM_PAIR_MINB)
@@ -328,23 +329,22 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
         const P4 ri = ldrec(mv.pos, i);
         const d3 xi = mk3(ri.x, ri.y, ri.z);
         d3 gr = mk3(0, 0, 0);
-        if (nl.kind == TM_NLIST_VERLET) {
-            const int e = nl.row_cnt[i];
-            const int* col = nl.row_j + tm_row_base(i, nl.row_cap);
-            // Software pipeline over the row, PB entries per stage: while stage k is evaluated the
-            // records of stage k+1 are in flight and the indices of stage k+2 have been requested, so
-            // the two dependent memory levels (index -> record, ~1000 cycles each from a cold L2)
-            // overlap the ~80 instructions per entry instead of preceding them (100 -> 66 us at
-            // 655,362 vertices, fp64 pipe 48 -> 70 % busy; profiles/r01g). Slots past the row's end
-            // read the vertex's own record (always valid) and are masked in the evaluation.
+        // Evaluation of a row of neighbour ids, entry k at col[k * stride]: a software pipeline, PB entries
+        // per stage: while stage k is evaluated the records of stage k+1 are in flight and the indices of
+        // stage k+2 have been requested, so the two dependent memory levels (index -> record, ~1000 cycles
+        // each from a cold L2) overlap the ~80 instructions per entry instead of preceding them (100 -> 66 us
+        // at 655,362 vertices, fp64 pipe 48 -> 70 % busy; profiles/r01g). Slots past the row's end read the
+        // vertex's own record (always valid) and are masked in the evaluation.
+        auto run_row = [&](const int* col, const int e, const int stride, const bool in_smem) {
+            auto idx = [&](int k) { return in_smem ? col[k * stride] : __ldg(col + k * stride); };
             int jn[PB];
             P4 xn[PB];
 #pragma unroll
-            for (int u = 0; u < PB; u++) jn[u] = (u < e) ? __ldg(col + u * 32) : i;
+            for (int u = 0; u < PB; u++) jn[u] = (u < e) ? idx(u) : i;
 #pragma unroll
             for (int u = 0; u < PB; u++) xn[u] = ldrec(mv.pos, jn[u]);
 #pragma unroll
-            for (int u = 0; u < PB; u++) jn[u] = (PB + u < e) ? __ldg(col + (PB + u) * 32) : i;
+            for (int u = 0; u < PB; u++) jn[u] = (PB + u < e) ? idx(PB + u) : i;
             for (int k = 0; k < e; k += PB) {
                 P4 x[PB];
 #pragma unroll
@@ -353,7 +353,7 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
 #pragma unroll
                     for (int u = 0; u < PB; u++) xn[u] = ldrec(mv.pos, jn[u]);
 #pragma unroll
-                    for (int u = 0; u < PB; u++) jn[u] = (k + 2 * PB + u < e) ? __ldg(col + (k + 2 * PB + u) * 32) : i;
+                    for (int u = 0; u < PB; u++) jn[u] = (k + 2 * PB + u < e) ? idx(k + 2 * PB + u) : i;
                 }
 #pragma unroll
                 for (int u = 0; u < PB; u++) {
@@ -365,13 +365,24 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
                     if (WITH_F) axpy3(gr, sl, dv);
                 }
             }
+        };
+        if (nl.kind == TM_NLIST_VERLET) {
+            run_row(nl.row_j + tm_row_base(i, nl.row_cap), nl.row_cnt[i], 32, false);
         } else {
-            cell_pairs_batched(mv, nl, i, xi, C.lc1sq, [&](int, d3 dv, double l2) {
-                double phi, sl;
-                pair_eval<R2>(C, rr, l2, true, phi, sl);
-                if (WITH_E) rep += phi;
-                if (WITH_F) axpy3(gr, sl, dv);
+            // Cell list: ~150 candidates per vertex of which ~20 pass the cut-off and the exclusion test.
+            // Evaluating the potential inside the candidate loop makes the warp run the ~80-instruction
+            // evaluation whenever ANY lane has a hit, i.e. nearly every candidate. So the scan only
+            // queues the hits (per-thread column of a shared-memory queue, in scan order) and the
+            // queue is then evaluated like a verlet row, all lanes busy (same summation order).
+            extern __shared__ int pair_queue[];
+            int* q = pair_queue + threadIdx.x;
+            int cnt = 0;
+            cell_pairs_batched(mv, nl, i, xi, C.lc1sq, [&](int j, d3, double) {
+                if (cnt == PAIR_QCAP) { run_row(q, cnt, PAIR_THREADS, true); cnt = 0; }
+                q[cnt * PAIR_THREADS] = j;
+                ++cnt;
             });
+            run_row(q, cnt, PAIR_THREADS, true);
         }
         if (WITH_F) {
             double* o = force + 3 * (size_t)i;
@@ -700,7 +711,8 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
         TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
         st = m->stream2;
     }
-#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, 0, st>>>( \
+    const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * PAIR_QCAP * PAIR_THREADS : 0;
+#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, qbytes, st>>>( \
         mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
