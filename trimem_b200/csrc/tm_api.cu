@@ -178,6 +178,7 @@ int tm_mesh_create(int device, tm_mesh** out) {
     TM_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     TM_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     TM_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+    TM_CUDA(cudaEventCreateWithFlags(&m->ev_pre_upload, cudaEventDisableTiming));
     TM_CUDA(cudaMalloc(&m->sums, sizeof(double) * 8));
     TM_CUDA(cudaMalloc(&m->ticket, sizeof(unsigned) * 4));
     TM_CUDA(cudaMemset(m->ticket, 0, sizeof(unsigned) * 4));
@@ -206,7 +207,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     if (m->h_stats) cudaFreeHost(m->h_stats);
     cudaFreeHost(m->h_sums);
     cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
-    cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join);
+    cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); cudaEventDestroy(m->ev_pre_upload);
     cudaStreamDestroy(m->stream2);
     cudaStreamDestroy(m->stream);
     delete m;
@@ -298,6 +299,7 @@ int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
     TM_CHECK(xyz != nullptr, "null positions");
     // staged in host numbering; scattered into the packed device records by the next compute
     // entry on the same stream (tm_ensure_layout)
+    TM_CUDA(cudaEventRecord(m->ev_pre_upload, m->stream));
     TM_CUDA(cudaMemcpyAsync(m->xio3, xyz, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyHostToDevice, m->stream));
     m->stage_pending = true;
     m->have_positions = true;
@@ -383,6 +385,33 @@ int tm_energy(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* energ
 }
 
 int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* grad, double props[6]) {
+    if (check_mesh(m, false) || check_params(p)) return 1;
+    TM_CHECK(grad != nullptr, "null gradient buffer");
+    // Speculation across the re-upload. The caller's positions cross the boundary on every call
+    // (TriMesh.points() is writable host memory), but energy() followed by gradient() at ONE position
+    // is the usual pair: when the property sums, rho and the pair force of the current device positions
+    // are cached, the gradient sweep, its export and its download run on the second stream from the
+    // positions already on the device WHILE the upload and its bitwise comparison run on the first
+    // (PCIe is full duplex). Unchanged -> the result is the answer; changed -> it is discarded and the
+    // normal path runs. Saves the upload's 0.3 ms of the 0.7 ms call at 655,362 vertices.
+    const NlView nv = view_of(nl);
+    const bool spec = m->stage_pending && !m->part && m->perm_valid && m->topo_dev_valid && m->rings_valid &&
+                      m->geo_epoch == m->pos_epoch && tm_check_nlist(m, nl) == 0 &&
+                      (!(p->rep_lc1 > 0.0 && p->kappa_r != 0.0) || tm_pair_force_valid(m, nv, *p));
+    const unsigned long long epoch0 = m->pos_epoch;
+    if (spec) {
+        TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_pre_upload, 0));
+        if (tm_launch_grad_speculative(m, nv, *p, m->stream2, grad)) return 1;
+    }
+    if (tm_ensure_layout(m)) return 1;             // imports the upload; bumps pos_epoch if a coordinate changed
+    if (spec) {
+        TM_CUDA(cudaStreamSynchronize(m->stream2));
+        if (m->pos_epoch == epoch0) {
+            m->grad_epoch = m->pos_epoch;
+            if (props) return fetch_sums(m, props);
+            return 0;
+        }
+    }
     if (tm_gradient_async(m, nl, p)) return 1;
     if (props) {
         if (tm_part_quiesce(m)) return 1;

@@ -128,6 +128,7 @@ struct tm_mesh {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool pairs_inflight = false;
+    cudaEvent_t ev_pre_upload = nullptr;   // recorded on `stream` just before a position upload is enqueued
     int V = 0, HE = 0;
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
@@ -251,6 +252,10 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p);  // tm_energy.cu
 int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); // tm_energy.cu (force only)
+// gradient sweep from the CURRENT device positions and caches on `st`, exported (host numbering) into
+// m->xout3 and copied to `grad_host`; no layout / staging work (speculative path of tm_gradient)
+int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_params& p, cudaStream_t st, double* grad_host);
+bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p);
 int tm_join_pairs(tm_mesh* m);   // tm_energy.cu: the mesh's stream waits for a pair sweep still running beside it
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
 double tm_energy_from_props(const tm_energy_params& p, const double s[6]);    // tm_api.cu (kernel.h:110-122)

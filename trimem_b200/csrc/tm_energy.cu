@@ -816,6 +816,27 @@ int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     return 0;
 }
 
+__global__ void k_export_grad(int V, const double* __restrict__ in, const int* __restrict__ d2h, double* __restrict__ out) {
+    const int d = blockIdx.x * 256 + threadIdx.x;
+    if (d >= V) return;
+    const double* s = in + 3 * (size_t)d;
+    double* o = out + 3 * (size_t)d2h[d];
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}
+
+int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_params& p, cudaStream_t st, double* grad_host) {
+    const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
+    SweepRange R;
+    R.first = 0; R.count = m->V; R.vlist = nullptr;
+    const int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
+    k_grad<<<nb, TM_GRAD_THREADS, 0, st>>>(m->view(), tm_to_dev(p), m->sums, pairs ? m->frep : nullptr, m->grad, R);
+    TM_LAUNCHED();
+    k_export_grad<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, m->grad, m->d2h, m->xout3); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    TM_CUDA(cudaMemcpyAsync(grad_host, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 int tm_preload_energy() {
     TM_PRELOAD((k_props<true, true>)); TM_PRELOAD((k_props<true, false>)); TM_PRELOAD((k_props<false, false>));
     TM_PRELOAD((k_pairs<true, true, true, true>)); TM_PRELOAD((k_pairs<true, true, true, false>));
