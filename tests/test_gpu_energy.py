@@ -246,3 +246,40 @@ def test_full_size_properties(gpu_core):
     np.copyto(mesh.points(), x0 - h * d); em = es.energy(mesh)
     np.copyto(mesh.points(), x0)
     assert rel((ep - em) / (2 * h), float((g * d).sum())) < 1e-5
+
+
+def test_minimiser_path_lbfgs(gpu_core):
+    """The minimisation driver of the reference (mc/util.py:240-306) runs scipy's L-BFGS-B over
+    EnergyEvaluators.fun / .grad with the neighbour list refreshed every iteration: the same calls here
+    (positions written through points(), energy(), gradient(), update_repulsion from the callback)."""
+    from scipy.optimize import minimize
+    mesh, es = cases.build(gpu_core, "ico4_stress_verlet2")
+    x0 = mesh.points().copy()
+
+    def fun(x):
+        np.copyto(mesh.points(), x.reshape(x0.shape))
+        return es.energy(mesh)
+
+    def grad(x):
+        np.copyto(mesh.points(), x.reshape(x0.shape))
+        return es.gradient(mesh).ravel()
+
+    calls = []
+
+    def callback(x):
+        np.copyto(mesh.points(), x.reshape(x0.shape))
+        es.update_repulsion(mesh)
+        es.update_reference_properties()
+        calls.append(es.energy(mesh))
+
+    e0 = fun(x0.ravel())
+    res = minimize(fun, x0.ravel(), jac=grad, callback=callback, method="L-BFGS-B", options={"maxiter": 15})
+    assert len(calls) >= 5 and res.fun < 0.5 * e0
+    # the gradient the minimiser used is the gradient of the energy it used (directional finite difference)
+    x = res.x.copy()
+    g = grad(x)
+    d = np.random.default_rng(0).normal(size=x.shape)
+    d /= np.linalg.norm(d)
+    h = 1e-6
+    fd = (fun(x + h * d) - fun(x - h * d)) / (2 * h)
+    assert abs(fd - g.dot(d)) <= 1e-5 * max(abs(fd), np.linalg.norm(g) * 1e-3)

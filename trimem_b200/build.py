@@ -18,7 +18,7 @@ CORE = os.path.join(HERE, "core" + sysconfig.get_config_var("EXT_SUFFIX"))
 CU_SOURCES = ["tm_api.cu", "tm_layout.cu", "tm_rings.cu", "tm_energy.cu", "tm_nlist.cu", "tm_flips.cu", "tm_geometry.cu",
               "tm_integrate.cu", "tm_part.cu"]
 CU_HEADERS = ["tm_common.cuh", "tm_neigh.cuh", "tm_vertex.cuh", "tm_math.cuh"]
-HOST_SOURCES = ["host/halfedge_mesh.cpp", "host/energy_manager.cpp", "host/bindings.cpp"]
+HOST_SOURCES = ["host/halfedge_mesh.cpp", "host/energy_manager.cpp", "host/mesh_io.cpp", "host/bindings.cpp"]
 HOST_HEADERS = ["host/halfedge_mesh.h", "host/energy_manager.h"]
 # the image exports CXX=/opt/gcc/bin/g++ whose OpenMP link is broken; use the system compiler
 GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

@@ -200,10 +200,14 @@ PYBIND11_MODULE(core, m) {
 
     m.def("read_mesh",
           [](const std::string& fname) -> std::unique_ptr<HalfedgeMesh> {
-              throw std::runtime_error("read_mesh('" + fname + "'): mesh file IO is outside the accelerated "
-                                       "path; construct TriMesh(points, faces) from arrays");
+              // src/mesh.cpp:7-16. The reference prints "read error on file <name>" and calls exit(1);
+              // killing the interpreter from a library call is the one behaviour not reproduced: the
+              // same message is raised as a RuntimeError.
+              auto mesh = std::make_unique<HalfedgeMesh>();
+              if (!read_mesh_file(fname, *mesh)) throw std::runtime_error("read error on file " + fname);
+              return mesh;
           },
-          py::arg("fname"), "Read mesh from file (not provided by the B200 build).");
+          py::arg("fname"), "Read mesh from file (STL binary/ASCII, OFF, OBJ).");
 
     // ---- properties (src/bindings.cpp:192-247) ------------------------------------------
     py::class_<VertexProperties>(m, "VertexProperties", "Container for vertex-averaged properties.")

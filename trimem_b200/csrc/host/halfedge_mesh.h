@@ -90,4 +90,7 @@ private:
     uint64_t dev_topo_version_ = 0;
 };
 
+// OpenMesh::IO::read_mesh for the formats trimem's drivers use (STL, OFF, OBJ); mesh_io.cpp
+bool read_mesh_file(const std::string& fname, HalfedgeMesh& mesh);
+
 }  // namespace trimem_b200
