@@ -601,7 +601,11 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_grad launch at 655,362 vertices from the
+                         # committed `ncu --set full` capture (profiles/r01l_ncu_full_sweeps.txt: 57.71 + 1.99 MB); below the
+                         # algorithmic bytes because part of the ring records is served by L2
+                         "traffic": 59.70e6 if args.subdiv == 8 else None,
+                         "traffic_source": "profiles/r01l_ncu_full_sweeps.txt (bytes per launch)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_grad, "ms_per_launch": k_ms[2],
                          "eg_algorithmic_bytes": alg_eg, "eg_frac_of_peak": alg_eg / (ms_step * 1e-3) / 1e9 / peak,
                          "kernel_ms": {"energy_sweeps": k_ms[0], "props_for_gradient": k_ms[1], "ring_grad": k_ms[2],
