@@ -176,7 +176,7 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
             cm.set_positions(x0); cm.set_momenta(p0)
         for r in reps:
             r[0].sync()
-    for _ in range(3):                  # direct launch, graph capture, first replay
+    for _ in range(6):                  # both record-array parities: direct launch, graph capture, first replay
         reset()
         for cm, nl, par, _, _ in reps:
             cm.vv_integrate_async(nl, par, 1.0, dt, L)
@@ -307,7 +307,7 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
         cm.set_positions(v)
         cm.set_momenta(p_host)
         cm.sync()
-    for _ in range(3):
+    for _ in range(2):
         lf_reset()
         barrier()
         cm.vv_integrate_async(nl, par, 1.0, lf_dt, L)
@@ -510,7 +510,7 @@ def main():
         cm.set_positions(x0)
         cm.set_momenta(p_host)
         cm.sync()
-    for _ in range(3):                  # direct launch, graph capture, first replay (tm_integrate.cu)
+    for _ in range(6):                  # both record-array parities: direct launch, graph capture, first replay
         lf_reset()
         cm.vv_integrate_async(nl, p, 1.0, lf_dt, L)
     cm.sync()

@@ -198,7 +198,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
     cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt); cudaFree(m->ring8);
     cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
-    cudaFree(m->pos); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); cudaFree(m->ex2_v);
+    cudaFree(m->pos); cudaFree(m->pos_alt); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); cudaFree(m->ex2_v);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     tm_part_release(m);
@@ -224,7 +224,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
     if (V != m->V) {
         if (dev_alloc(&m->v_he, V) || dev_alloc(&m->v_he_h, V) || dev_alloc(&m->d2h, V) || dev_alloc(&m->h2d, V) ||
             dev_alloc(&m->ring_off, (size_t)V + 1) || dev_alloc(&m->ring_cnt, (size_t)V + 1) || dev_alloc(&m->ring8, V) ||
-            dev_alloc(&m->pos, V) || dev_alloc(&m->xio3, 3 * (size_t)V) || dev_alloc(&m->xout3, 3 * (size_t)V) ||
+            dev_alloc(&m->pos, V) || dev_alloc(&m->pos_alt, V) || dev_alloc(&m->xio3, 3 * (size_t)V) || dev_alloc(&m->xout3, 3 * (size_t)V) ||
             dev_alloc(&m->grad, 3 * (size_t)V))
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
@@ -235,6 +235,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
         if (m->ex2_off) { cudaFree(m->ex2_off); m->ex2_off = nullptr; }
         m->frep_epoch = 0;
         TM_CUDA(cudaMemsetAsync(m->pos, 0, sizeof(P4) * (size_t)V, m->stream));
+        TM_CUDA(cudaMemsetAsync(m->pos_alt, 0, sizeof(P4) * (size_t)V, m->stream));
         m->perm_valid = false;          // a new vertex set: the order is rebuilt from its first positions
         m->have_positions = false;
         m->stage_pending = false;

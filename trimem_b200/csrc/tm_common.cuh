@@ -146,6 +146,8 @@ struct tm_mesh {
     unsigned long long pos_epoch = 1;      // bumped whenever positions or connectivity change
     unsigned long long geo_epoch = 0;      // pos_epoch at which sums[0..2] and rho were evaluated
     P4* pos = nullptr;           // V   (x, y, z, rho), device numbering
+    P4* pos_alt = nullptr;       // V   second record array: a trajectory step writes x_{n+1} here while the gradient
+                                 //     sweep still gathers x_n from `pos`, then the two swap (tm_integrate.cu)
     double* xio3 = nullptr;      // V*3 staging in HOST numbering: uploaded positions
     double* xout3 = nullptr;     // V*3 staging in HOST numbering: results on their way out
     double* vprops = nullptr;    // V*6 (allocated on demand)
@@ -250,7 +252,17 @@ void tm_pool_free(int device, void* p);
 int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* total);  // tm_rings.cu
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu
-int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p);  // tm_energy.cu
+// Velocity-Verlet update fused into the gradient sweep's epilogue (tm_integrate.cu): mode 1 = momentum
+// update of the step that ends at the swept positions, mode 2 = that plus the position update of the next
+// step, written to pos_next (the sweep itself still reads the old records).
+struct VVFuse {
+    int mode;                    // 0 none
+    double* mom;
+    const double* g_prev;
+    P4* pos_next;
+    double dt, dt2, mass;
+};
+int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p, const VVFuse* fuse = nullptr);  // tm_energy.cu
 int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); // tm_energy.cu (force only)
 // gradient sweep from the CURRENT device positions and caches on `st`, exported (host numbering) into
 // m->xout3 and copied to `grad_host`; no layout / staging work (speculative path of tm_gradient)

@@ -640,9 +640,10 @@ __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevP
 
 // Reads only: every ring / list neighbour costs one 256-bit read-only load of its
 // (x, y, z, rho) record.
+template <int UPD>
 __global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
 k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
-       double* __restrict__ grad, SweepRange R) {
+       double* __restrict__ grad, SweepRange R, VVFuse U) {
     const int t = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
     if (t >= R.count) return;
     const int i = R.first + t;
@@ -655,6 +656,11 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
 
     const R8 row = ldrow(mv.ring8, i);
     const P4 ri = ldrec(mv.pos, i);
+    if (UPD > 0) {
+        // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
+    }
     const d3 xi = mk3(ri.x, ri.y, ri.z);
     d3 g = mk3(0, 0, 0);
     d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
@@ -679,6 +685,29 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
 
     double* o = grad + 3 * (size_t)i;
     o[0] = g.x; o[1] = g.y; o[2] = g.z;
+
+    if (UPD > 0) {
+        // velocity Verlet in the epilogue (same explicitly rounded operations as k_vv_update, i.e. numpy's
+        // order): p += 0.5 (a + an) dt ; x_next = x + (p dt + 0.5 an dt^2) / m, with a = -g_prev, an = -g
+        const double an[3] = {-g.x, -g.y, -g.z};
+        const double xs[3] = {ri.x, ri.y, ri.z};
+        double xn[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double a = -U.g_prev[3 * (size_t)i + k];
+            const double pk = __dadd_rn(U.mom[3 * (size_t)i + k], __dmul_rn(__dmul_rn(0.5, __dadd_rn(a, an[k])), U.dt));
+            U.mom[3 * (size_t)i + k] = pk;
+            if (UPD > 1) {
+                const double num = __dadd_rn(__dmul_rn(pk, U.dt), __dmul_rn(__dmul_rn(0.5, an[k]), U.dt2));
+                xn[k] = __dadd_rn(xs[k], __ddiv_rn(num, U.mass));
+            }
+        }
+        if (UPD > 1) {
+            P4* q = U.pos_next + i;
+            *reinterpret_cast<double2*>(q) = make_double2(xn[0], xn[1]);
+            *(reinterpret_cast<double2*>(q) + 1) = make_double2(xn[2], ri.w);
+        }
+    }
 }
 
 }  // namespace
@@ -801,7 +830,7 @@ int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     return launch_pairs(m, nl, p, false, false, 0);
 }
 
-int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
+int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p, const VVFuse* fuse) {
     if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
     if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
@@ -809,7 +838,13 @@ int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     const SweepRange R = tm_owned_range(m);
     int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     DevParams P = tm_to_dev(p);
-    k_grad<<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, pairs ? m->frep : nullptr, m->grad, R);
+    VVFuse U;
+    memset(&U, 0, sizeof(U));
+    if (fuse) U = *fuse;
+    const double* frc = pairs ? m->frep : nullptr;
+    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
+    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
+    else k_grad<0><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->grad_epoch = m->pos_epoch;
@@ -829,7 +864,9 @@ int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_par
     SweepRange R;
     R.first = 0; R.count = m->V; R.vlist = nullptr;
     const int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
-    k_grad<<<nb, TM_GRAD_THREADS, 0, st>>>(m->view(), tm_to_dev(p), m->sums, pairs ? m->frep : nullptr, m->grad, R);
+    VVFuse U;
+    memset(&U, 0, sizeof(U));
+    k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(m->view(), tm_to_dev(p), m->sums, pairs ? m->frep : nullptr, m->grad, R, U);
     TM_LAUNCHED();
     k_export_grad<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, m->grad, m->d2h, m->xout3); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
@@ -842,6 +879,6 @@ int tm_preload_energy() {
     TM_PRELOAD((k_pairs<true, true, true, true>)); TM_PRELOAD((k_pairs<true, true, true, false>));
     TM_PRELOAD((k_pairs<true, true, false, true>)); TM_PRELOAD((k_pairs<true, true, false, false>));
     TM_PRELOAD((k_pairs<false, true, false, true>)); TM_PRELOAD((k_pairs<false, true, false, false>));
-    TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad);
+    TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad<0>); TM_PRELOAD(k_grad<1>); TM_PRELOAD(k_grad<2>);
     return 0;
 }

@@ -171,12 +171,25 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
         k_vv_update<false, true><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad, m->grad, dt, dt2, mass);
         TM_LAUNCHED();
     }
+    // Steps. On an unpartitioned mesh the update rides in the gradient sweep's epilogue: the sweep of step n
+    // gathers x_n from `pos` and writes x_{n+1} into `pos_alt`, then the two arrays swap roles (a partitioned
+    // mesh keeps ONE array, which its peers have mapped, and runs the separate update kernel).
+    const bool fused = m->part == nullptr;
     for (int n = 1; n <= n_steps; n++) {
         m->pos_epoch++;
         if (tm_part_positions_updated(m)) return 1;
         std::swap(m->grad, m->grad_prev);          // a = -grad_prev, an = -grad (about to be evaluated)
         const bool last = n == n_steps;
         if (tm_launch_props(m, nl, p, last && with_energies, false)) return 1;
+        if (fused) {
+            VVFuse U;
+            U.mode = last ? 1 : 2;
+            U.mom = m->mom; U.g_prev = m->grad_prev; U.pos_next = m->pos_alt;
+            U.dt = dt; U.dt2 = dt2; U.mass = mass;
+            if (tm_launch_grad(m, nl, p, &U)) return 1;
+            if (!last) std::swap(m->pos, m->pos_alt);
+            continue;
+        }
         if (tm_launch_grad(m, nl, p)) return 1;
         if (last) {
             k_vv_update<true, false><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad_prev, m->grad, dt, dt2, mass);
@@ -211,6 +224,7 @@ struct VVKey {
     tm_energy_params p;
     unsigned long long nl_serial, topo_epoch, layout_epoch;
     const double* grad;
+    const P4* pos;
 };
 struct VVGraph {
     VVKey key;
@@ -255,6 +269,7 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
     key.nl_serial = nl.kind >= 0 ? nl.serial : 0;
     key.topo_epoch = m->topo_epoch; key.layout_epoch = m->layout_epoch;
     key.grad = m->grad;
+    key.pos = m->pos;
 
     VVGraph* slot = nullptr;
     for (auto& g : C->g) if (g.uses > 0 && same_key(g.key, key)) slot = &g;
@@ -306,6 +321,7 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
         m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r; m->frep_list = nl.serial;
     }
     if (n_steps & 1) std::swap(m->grad, m->grad_prev);
+    if ((n_steps - 1) & 1) std::swap(m->pos, m->pos_alt);      // fused steps ping-pong the record arrays
     return 0;
 }
 
