@@ -106,6 +106,12 @@ int tm_nlist_distance_matrix(tm_nlist* nl, tm_mesh* m, double rdist,
  * d_ij = x_pid - x_j (n x 3) and j for all listed j with |d_ij| < rdist.        */
 int tm_nlist_point_distances(tm_nlist* nl, tm_mesh* m, int pid, double rdist,
                              int* n, double** dxyz, int** jdx);
+/* Skin criterion of a verlet list (extension; the reference rebuilds on a fixed
+ * cadence, mc/evaluators.py:181-182): the frozen rows stay complete for the cut-off
+ * dmax (the repulsion's lc1) while no vertex has moved further than
+ * (rlist - dmax) / 2 since the build. displacement = the largest such move on the
+ * mesh's current device positions; needs_rebuild = 2 * displacement > rlist - dmax. */
+int tm_nlist_displacement(tm_nlist* nl, tm_mesh* m, double dmax, double* displacement, int* needs_rebuild);
 /* diagnostics: number of directed verlet entries (0 for a cell list), cells     */
 int tm_nlist_info(tm_nlist* nl, long long* n_entries, int shape[3], double box[6], double cell[3]);
 

@@ -105,3 +105,32 @@ def test_errors(gpu_core):
         get_nlist(gpu_core, mesh, "verlet-list", 0.2, 3)
     with pytest.raises(RuntimeError, match="Unknown neighbour search algorithm."):
         get_nlist(gpu_core, mesh, "ball-tree", 0.2, 0)
+
+
+def test_skin_criterion(gpu_core):
+    """tm_nlist_displacement / EnergyManager.repulsion_outdated: the frozen verlet rows are complete for the
+    cut-off lc1 exactly as long as no vertex moved more than (rlist - lc1) / 2 since the build."""
+    mesh, es = cases.build(gpu_core, "ico4_stress_verlet2")
+    rp = es.eparams.repulse_params
+    skin = rp.rlist - rp.lc1
+    x0 = mesh.points().copy()
+    assert not es.repulsion_outdated(mesh)
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=x0.shape)
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    np.copyto(mesh.points(), x0 + 0.49 * skin * d)
+    assert not es.repulsion_outdated(mesh)
+    # while the criterion holds, the frozen rows give the repulsion sum of a freshly built list
+    # (same pairs inside the cut-off; the row order, hence the rounding, may differ)
+    r_frozen = es.properties(mesh).repulsion
+    es2 = gpu_core.EnergyManager(mesh, es.eparams)
+    assert abs(es2.properties(mesh).repulsion - r_frozen) <= 1e-12 * abs(r_frozen)
+    x1 = x0 + 0.49 * skin * d
+    x1[17] = x0[17] + 0.51 * skin * d[17]
+    np.copyto(mesh.points(), x1)
+    assert es.repulsion_outdated(mesh)
+    es.update_repulsion(mesh)
+    assert not es.repulsion_outdated(mesh)
+    # cell lists are always reported as due
+    mesh_c, es_c = cases.build(gpu_core, "ico4_stress_cell2")
+    assert es_c.repulsion_outdated(mesh_c)

@@ -61,7 +61,8 @@ class Ranks:
 
 
 @pytest.mark.parametrize("case,nranks", [("ico4_stress_verlet2", 2), ("ico4_stress_verlet2", 3), ("ico4_stress_cell2", 2),
-                                         ("ico4_config1", 4), ("ico4_area_stress", 2), ("ico6_stress_verlet2", 8)])
+                                         ("ico4_config1", 4), ("ico4_area_stress", 2), ("ico6_stress_verlet2", 8),
+                                         ("ico8_stress_verlet2", 4)])
 def test_energy_gradient_partitioned(gpu_core, case, nranks):
     gold = cases.load_golden(case)
     R = Ranks(gpu_core, case, nranks)

@@ -74,6 +74,7 @@ def lib():
                                            C.POINTER(_dp), C.POINTER(_ip), C.POINTER(_ip)]
     L.tm_nlist_point_distances.argtypes = [vp, vp, C.c_int, C.c_double, _ip, C.POINTER(_dp), C.POINTER(_ip)]
     L.tm_nlist_info.argtypes = [vp, C.POINTER(C.c_longlong), _ip, _dp, _dp]
+    L.tm_nlist_displacement.argtypes = [vp, vp, C.c_double, _dp, _ip]
     pp = C.POINTER(EnergyParamsABI)
     L.tm_properties.argtypes = [vp, vp, pp, _dp]
     L.tm_vertex_properties.argtypes = [vp, vp, pp, _dp]
@@ -374,6 +375,12 @@ class NList:
         cell = np.zeros(3)
         _chk(lib().tm_nlist_info(self.h, C.byref(n), _i(shape), _d(box), _d(cell)))
         return n.value, shape, box, cell
+
+    def displacement(self, dmax):
+        """(largest displacement since the build, rows may have become incomplete for cut-off dmax)"""
+        d, need = C.c_double(), C.c_int()
+        _chk(lib().tm_nlist_displacement(self.h, self.mesh.h, dmax, C.byref(d), C.byref(need)))
+        return d.value, bool(need.value)
 
     def distance_matrix(self, rdist):
         n = C.c_longlong()

@@ -301,6 +301,9 @@ PYBIND11_MODULE(core, m) {
              "Update reference configurations (parameter continuation).")
         .def("update_repulsion", &EnergyManager::update_repulsion, py::arg("mesh"),
              "Rebuild the neighbour list / repulsion penalty from the current mesh state.")
+        .def("repulsion_outdated", &EnergyManager::repulsion_outdated, py::arg("mesh"),
+             "Extension: True when a vertex has moved more than (rlist - lc1)/2 since the last update_repulsion,\n"
+             "i.e. when the frozen verlet rows may miss a pair inside the repulsion cut-off.")
         .def("print_info",
              [](EnergyManager& self, HalfedgeMesh& mesh) { py::print(self.info(mesh), py::arg("end") = ""); },
              py::arg("mesh"), "Print energy information evaluated on the state defined by mesh.")

@@ -102,6 +102,13 @@ void EnergyManager::update_repulsion(HalfedgeMesh& mesh) {
     nlist = make_nlist(mesh, params);
 }
 
+bool EnergyManager::repulsion_outdated(HalfedgeMesh& mesh) {
+    if (params.repulse_params.n_search != "verlet-list") return true;
+    int need = 1;
+    if (tm_nlist_displacement(nlist_handle(), mesh.device(), params.repulse_params.lc1, nullptr, &need)) fail();
+    return need != 0;
+}
+
 tm_energy_params EnergyManager::abi_params() const {
     if (params.bond_params.type != BondType::Edge && params.bond_params.type != BondType::Area)
         throw std::runtime_error("Unknown bond potential");

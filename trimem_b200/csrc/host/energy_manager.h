@@ -82,6 +82,9 @@ public:
     void update_reference_properties();
     VertexProperties interpolate_reference_properties() const;
     void update_repulsion(HalfedgeMesh& mesh);
+    // extension: has any vertex moved far enough since the last update_repulsion that the verlet rows may
+    // miss a pair inside the repulsion cut-off? (always true for cell lists, which are cheap to keep current)
+    bool repulsion_outdated(HalfedgeMesh& mesh);
 
     VertexProperties properties(HalfedgeMesh& mesh);
     double energy(HalfedgeMesh& mesh);

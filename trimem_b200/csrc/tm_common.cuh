@@ -204,6 +204,7 @@ struct tm_nlist {
     int rows_first = 0, rows_count = 0;   // vertices whose verlet rows were built (all, or a partition's slice)
     unsigned long long serial = 0;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
+    double* x_build = nullptr;   // V*3 positions the verlet rows were built from (device numbering): skin criterion
     long long n_entries = 0;
     unsigned long long layout_epoch = 0;   // vertex numbering the list was built in
     NlView view() const {

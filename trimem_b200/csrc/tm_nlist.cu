@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cmath>
+
 #include "tm_common.cuh"
 #include "tm_neigh.cuh"
 
@@ -179,6 +181,26 @@ __global__ void k_sort_rows(int V, int cap, const int* __restrict__ row_cnt, int
         while (q >= 0 && col[q * 32] > v) { col[(q + 1) * 32] = col[q * 32]; --q; }
         col[(q + 1) * 32] = v;
     }
+}
+
+// positions at build time, and the largest displacement since (max is order-free: deterministic)
+__global__ void k_save_positions(int V, const P4* __restrict__ pos, double* __restrict__ x3) {
+    const int i = blockIdx.x * NT + threadIdx.x;
+    if (i >= V) return;
+    const d3 p = ldpos(pos, i);
+    x3[3 * (size_t)i] = p.x; x3[3 * (size_t)i + 1] = p.y; x3[3 * (size_t)i + 2] = p.z;
+}
+__global__ void k_max_displacement2(int V, const P4* __restrict__ pos, const double* __restrict__ x3,
+                                    unsigned long long* __restrict__ out) {
+    double mx = 0.0;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < V; i += gridDim.x * NT) {
+        const d3 p = ldpos(pos, i);
+        const d3 d = mk3(p.x - x3[3 * (size_t)i], p.y - x3[3 * (size_t)i + 1], p.z - x3[3 * (size_t)i + 2]);
+        mx = fmax(mx, dot3(d, d));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
 }
 
 // number of directed entries: sum of row_cnt (fixed-order, integers)
@@ -391,6 +413,9 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
         cap = ((widest + 7) / 8) * 8;
     }
     k_sort_rows<<<vb, NT, 0, m->stream>>>(V, nl->row_cap, nl->row_cnt, nl->row_j); TM_LAUNCHED();
+    nl->x_build = (double*)tm_pool_alloc(dev, sizeof(double) * 3 * (size_t)V);
+    TM_CHECK(nl->x_build, "out of device memory for the list's build positions");
+    k_save_positions<<<vb, NT, 0, m->stream>>>(V, m->pos, nl->x_build); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     nl->n_entries = -1;                 // counted on demand (tm_nlist_info)
     return 0;
@@ -437,7 +462,34 @@ int tm_nlist_destroy(tm_nlist* nl) {
     tm_pool_free(nl->device, nl->cell_start); tm_pool_free(nl->device, nl->cell_items);
     tm_pool_free(nl->device, nl->row_cnt); tm_pool_free(nl->device, nl->row_j);
     tm_pool_free(nl->device, nl->cell_of);
+    tm_pool_free(nl->device, nl->x_build);
     delete nl;
+    return 0;
+}
+
+// Skin criterion of a verlet list (extension; the reference rebuilds on a fixed cadence,
+// mc/evaluators.py:181-182): the frozen rows stay complete for a cut-off dmax as long as no vertex has moved
+// further than (rlist - dmax) / 2 since the build. Returns the largest displacement on the mesh's
+// current device positions; needs_rebuild = 2 * displacement > rlist - dmax.
+int tm_nlist_displacement(tm_nlist* nl, tm_mesh* m, double dmax, double* displacement, int* needs_rebuild) {
+    TM_CHECK(nl != nullptr && m != nullptr, "null argument");
+    TM_CHECK(nl->kind == TM_NLIST_VERLET && nl->x_build, "the skin criterion applies to verlet lists");
+    TM_CUDA(cudaSetDevice(m->device));
+    if (tm_ensure_layout(m) || tm_check_nlist(m, nl) || tm_part_make_current(m)) return 1;
+    unsigned long long* d = (unsigned long long*)tm_pool_alloc(nl->device, 8);
+    TM_CHECK(d, "out of device memory");
+    unsigned long long h = 0;
+    cudaMemsetAsync(d, 0, 8, m->stream);
+    k_max_displacement2<<<296, NT, 0, m->stream>>>(m->V, m->pos, nl->x_build, d); TM_LAUNCHED();
+    cudaError_t e = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, m->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+    tm_pool_free(nl->device, d);
+    TM_CHECK(e == cudaSuccess, "tm_nlist_displacement failed: %s", cudaGetErrorString(e));
+    double d2;
+    memcpy(&d2, &h, 8);
+    const double disp = sqrt(d2);
+    if (displacement) *displacement = disp;
+    if (needs_rebuild) *needs_rebuild = (2.0 * disp > nl->rlist - dmax) ? 1 : 0;
     return 0;
 }
 
