@@ -406,6 +406,25 @@ def main():
         return 0
 
     # ------------------------------------------------------------------------ our arm
+    bound_cpus = None
+    if world > 1:
+        # one process per GPU: run on (and first-touch the pinned buffers from) the cores next to this rank's
+        # GPU; with 8 ranks the end-to-end path is host-memory- and PCIe-bound, so locality matters
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(ClockSampler._nvml_index(local))
+            words = nv.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+            allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+            if allowed:
+                # spread the ranks that share a socket over its cores
+                per = max(2, len(allowed) // max(1, min(world, 8)))
+                mine = allowed[(local * per) % len(allowed):][:per] or allowed
+                os.sched_setaffinity(0, mine)
+                bound_cpus = len(mine)
+        except Exception:
+            bound_cpus = None
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -576,6 +595,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl, "n_vertices": V, "verlet_entries": int(n_entries), "entries_per_vertex": P,
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "host_cores_bound_per_rank": bound_cpus,
                        "l2": f"flushed before every timed step ({FLUSH_BYTES >> 20} MiB memset, outside the timed span)"},
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": "evals/s",
