@@ -49,17 +49,22 @@ __device__ __forceinline__ double exp_nonpos(double t) {
 
 // atan2(y, x), all quadrants, y == x == 0 -> 0.
 //   q = min(|x|,|y|)/max(|x|,|y|) in [0,1];  c = q rounded to a multiple of 1/4;
-//   atan q = atan c + atan((q - c)/(1 + q c)),  |(q - c)/(1 + q c)| <= 1/8  -> odd series to r^17.
+//   atan q = atan c + atan r,  r = (q - c)/(1 + q c) = (mn - c mx)/(mx + c mn),  |r| <= 1/8 (+1e-6)
+//   -> odd series to r^17.
+// c only selects the interval, so it is taken from a 20-bit estimate of q (the MUFU seed alone, no Newton
+// steps), and r needs ONE full-precision reciprocal instead of two: 11 dependent fp64 operations before the
+// polynomial instead of 16 (the sweeps are bound by exactly this kind of dependent latency).
 __device__ __forceinline__ double atan2_fast(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
     const double mx = swap ? ay : ax, mn = swap ? ax : ay;
-    const double q = mn * rcp_pos(mx);
+    double seed;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(mx));
     const double M = 1688849860263936.0;                     // 1.5 * 2^50: ulp = 1/4
-    const double t = q + M;
+    const double t = fma(mn, seed, M);
     const int k = __double2loint(t) & 7;                     // 0 .. 4
     const double c = t - M;
-    const double r = (q - c) * rcp_pos(fma(q, c, 1.0));
+    const double r = fma(-c, mx, mn) * rcp_pos(fma(c, mn, mx));
     const double s = r * r;
     double p = ATAN_C[0];
 #pragma unroll
