@@ -5,7 +5,8 @@
 
 #include "tm_common.cuh"
 
-unsigned long long g_tm_launches = 0;
+std::atomic<unsigned long long> g_tm_launches{0};
+thread_local unsigned long long tl_tm_launches = 0;
 static thread_local char g_err[1024] = "";
 
 void tm_set_error(const char* fmt, ...) {
@@ -160,7 +161,7 @@ void tm_host_free(void* p) {
 }
 
 void tm_free(void* p) { free(p); }
-unsigned long long tm_launch_count(void) { return g_tm_launches; }
+unsigned long long tm_launch_count(void) { return g_tm_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------- mesh --
 int tm_mesh_create(int device, tm_mesh** out) {

@@ -1,6 +1,7 @@
 // Shared declarations of libtrimem_b200: handle structs, device views, helpers.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,7 +12,8 @@
 
 // ------------------------------------------------------------------ errors --
 void tm_set_error(const char* fmt, ...);
-extern unsigned long long g_tm_launches;
+extern std::atomic<unsigned long long> g_tm_launches;      // all threads (tm_launch_count)
+extern thread_local unsigned long long tl_tm_launches;     // this thread (per-call deltas)
 
 #define TM_CUDA(call)                                                           \
     do {                                                                        \
@@ -28,7 +30,7 @@ extern unsigned long long g_tm_launches;
         if (!(cond)) { tm_set_error(__VA_ARGS__); return 1; }                   \
     } while (0)
 
-#define TM_LAUNCHED() (++g_tm_launches)
+#define TM_LAUNCHED() (++tl_tm_launches, g_tm_launches.fetch_add(1, std::memory_order_relaxed))
 
 // --------------------------------------------------------------- constants --
 constexpr int TM_RING_FACE  = 1 << 30;          // slot's outgoing half-edge has a face

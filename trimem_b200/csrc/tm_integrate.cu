@@ -286,7 +286,7 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
         // second request: capture. The launch functions update host-side state while they enqueue;
         // snapshot it so that a failed capture can be undone and rerun directly.
         const tm_mesh snap = *m;
-        const unsigned long long l0 = g_tm_launches;
+        const unsigned long long l0 = tl_tm_launches;
         cudaGraph_t graph = nullptr;
         bool ok = cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
@@ -301,19 +301,21 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
             tm_vvcache* keep = m->vvcache;
             *m = snap;
             m->vvcache = keep;
-            g_tm_launches = l0;
+            g_tm_launches.fetch_sub(tl_tm_launches - l0, std::memory_order_relaxed);   // nothing was launched
+            tl_tm_launches = l0;
             C->disabled = true;
             slot->exec = nullptr;
             return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
         }
-        slot->launches = g_tm_launches - l0;
+        slot->launches = tl_tm_launches - l0;
         slot->frep_touched = m->frep_epoch == m->pos_epoch;
         TM_CUDA(cudaGraphLaunch(slot->exec, m->stream));
         return 0;
     }
     // replay: one launch, plus the bookkeeping of vv_run_direct
     TM_CUDA(cudaGraphLaunch(slot->exec, m->stream));
-    g_tm_launches += slot->launches;
+    g_tm_launches.fetch_add(slot->launches, std::memory_order_relaxed);
+    tl_tm_launches += slot->launches;
     m->pos_epoch += (unsigned long long)n_steps;
     m->geo_epoch = m->pos_epoch;
     m->grad_epoch = m->pos_epoch;
