@@ -68,7 +68,7 @@ struct tm_part {
     int* g1 = nullptr; int n_g1 = 0;              // non-owned ring neighbours of owned vertices
     int* pull = nullptr; int n_pull = 0;          // non-owned vertices whose positions the owned sweeps read
     bool pull_all = false;                        // cell lists: everything non-owned
-    int* mark = nullptr;                          // 2V workspace
+    int* mark = nullptr;                          // 3V + 4 workspace (two mark arrays, scan output)
     unsigned long long lists_topo = 0, lists_nl = 0; bool lists_valid = false;
     unsigned long long pos_seq = 0, sums_seq = 0; // host mirrors of the published counters
     bool stale_far = false;                       // non-halo positions are older than the owners'
@@ -312,7 +312,8 @@ int tm_part_refresh(tm_mesh* m, const NlView& nl) {
     const int V = m->V, vb = (V + NT - 1) / NT;
     const SweepRange R = tm_owned_range(m);
     const int lo = R.first, hi = R.first + R.count;
-    if (!P->mark) TM_CUDA(cudaMalloc(&P->mark, sizeof(int) * 3 * (size_t)V));
+    // two mark arrays and the scan's output, which has V + 1 entries (offsets and the total)
+    if (!P->mark) TM_CUDA(cudaMalloc(&P->mark, sizeof(int) * (3 * (size_t)V + 4)));
     int *m1 = P->mark, *m2 = P->mark + V, *scratch = P->mark + 2 * (size_t)V;
     TM_CUDA(cudaMemsetAsync(m1, 0, sizeof(int) * 2 * (size_t)V, m->stream));
     k_mark_rings<<<vb, NT, 0, m->stream>>>(lo, hi, nullptr, V, m->ring_off, m->ring_v, m1); TM_LAUNCHED();
