@@ -109,6 +109,8 @@ struct NlView {
     int strides[3];
     const int* cell_start; // ncell+1
     const int* cell_items; // V, ascending vertex id inside a cell
+    const P4* cell_rec;    // V, (x, y, z, id bits) of cell_items[k] at the positions of the current sweep: the
+                           //    candidates of a cell-list scan as contiguous records (refreshed per sweep)
     // verlet rows, fixed width, sliced by warp: entry k of vertex i is
     // row_j[((i >> 5) * row_cap + k) * 32 + (i & 31)], k < row_cnt[i]. The 32 threads of a warp
     // read 32 consecutive ints per step and a warp's whole slice is one contiguous block
@@ -165,6 +167,7 @@ struct tm_mesh {
     struct tm_part* part = nullptr;
     struct tm_vvcache* vvcache = nullptr;   // captured trajectories (tm_integrate.cu)
     double* frep = nullptr;      // V*3 pair force of the last pair sweep (allocated on demand)
+    unsigned long long cellrec_epoch = 0, cellrec_list = 0;   // positions / cell list the list's cell_rec holds
     unsigned long long frep_epoch = 0;     // pos_epoch, potential and list it was evaluated for
     double frep_lc1 = 0; int frep_r = 0; unsigned long long frep_list = 0;
     // sorted, de-duplicated two-ring rows (verlet exclusion level 2), rebuilt when the topology changed
@@ -201,6 +204,7 @@ struct tm_nlist {
     int shape[3] = {1, 1, 1}, strides[3] = {1, 1, 1};
     long long ncell = 0;
     int *cell_start = nullptr, *cell_items = nullptr;
+    P4* cell_rec = nullptr;
     int *row_cnt = nullptr, *row_j = nullptr;
     int row_cap = 0;
     int rows_first = 0, rows_count = 0;   // vertices whose verlet rows were built (all, or a partition's slice)
@@ -216,7 +220,7 @@ struct tm_nlist {
             v.box_min[k] = box_min[k]; v.cell[k] = cell[k];
             v.shape[k] = shape[k]; v.strides[k] = strides[k];
         }
-        v.cell_start = cell_start; v.cell_items = cell_items;
+        v.cell_start = cell_start; v.cell_items = cell_items; v.cell_rec = cell_rec;
         v.row_cnt = row_cnt; v.row_j = row_j; v.row_cap = row_cap; v.serial = serial;
         return v;
     }

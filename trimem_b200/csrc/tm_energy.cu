@@ -302,6 +302,18 @@ __device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2,
     sl = -fma(C.lc1 * w, w, C.rd * il) * (phi * il);
 }
 
+// cell-ordered copy of the position records for the cell-list scan: rec[k] = (x, y, z of cell_items[k], id)
+__global__ void k_cell_gather(int V, const int* __restrict__ items, const P4* __restrict__ pos, P4* __restrict__ rec) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= V) return;
+    const int j = items[k];
+    const d3 p = ldpos(pos, j);
+    P4 r;
+    r.x = p.x; r.y = p.y; r.z = p.z;
+    r.w = __hiloint2double(0, j);
+    rec[k] = r;
+}
+
 #ifndef TM_PAIR_NT
 #define TM_PAIR_NT 128
 #endif
@@ -312,10 +324,16 @@ __device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2,
 #define TM_PAIR_BATCH 4
 #endif
 constexpr int PAIR_THREADS = TM_PAIR_NT;
-constexpr int PAIR_QCAP = 48;                   // queued hits per thread before an early flush (cell lists)
+constexpr int PAIR_QCAP = 56;                   // queued candidates per thread before an early flush (cell lists)
+constexpr int PAIR_XCAP = 32;                   // exclusion-row entries per thread kept in shared memory
 constexpr int PB = TM_PAIR_BATCH;
-template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2>
-__global__ void __launch_bounds__(PAIR_THREADS, TM_PAIR_MINB)
+#ifndef TM_PAIR_CELL_MINB
+#define TM_PAIR_CELL_MINB 3
+#endif
+// CELL: the list is a cell list (a separate instantiation, so that the verlet sweep keeps its own register
+// allocation: 126 registers, no spills)
+template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2, bool CELL>
+__global__ void __launch_bounds__(PAIR_THREADS, CELL ? TM_PAIR_CELL_MINB : TM_PAIR_MINB)
 k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
         double* __restrict__ partials, int nwarps, SweepRange R) {
     const int t = blockIdx.x * PAIR_THREADS + threadIdx.x;
@@ -366,23 +384,105 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
                 }
             }
         };
-        if (nl.kind == TM_NLIST_VERLET) {
+        if (!CELL) {
             run_row(nl.row_j + tm_row_base(i, nl.row_cap), nl.row_cnt[i], 32, false);
         } else {
-            // Cell list: ~150 candidates per vertex of which ~20 pass the cut-off and the exclusion test.
-            // Evaluating the potential inside the candidate loop makes the warp run the ~80-instruction
-            // evaluation whenever ANY lane has a hit, i.e. nearly every candidate. So the scan only
-            // queues the hits (per-thread column of a shared-memory queue, in scan order) and the
-            // queue is then evaluated like a verlet row, all lanes busy (same summation order).
-            extern __shared__ int pair_queue[];
-            int* q = pair_queue + threadIdx.x;
+            // Cell list (CellList::point_distances, cell_list.h:131-219: build-time occupancy, the query
+            // vertex's live cell, exclusions on the current connectivity): ~150 candidates per vertex, ~37
+            // inside the cut-off, ~19 left after the exclusion test. Three phases per thread, each shaped
+            // for what bounds it:
+            //  A  scan: the candidates of a cell are CONTIGUOUS records (cell_rec, gathered once per sweep at
+            //     the current positions, the vertex id in the fourth word) and x is the fastest cell index,
+            //     so the 27 cells are 9 runs read four records per trip, the next trip's in flight: one
+            //     memory level, no index -> record dependency. Candidates inside the cut-off are queued.
+            //  B  exclusion: the vertex's sorted two-ring row (level 2) or ring row (level 1) sits in shared
+            //     memory and is compared against four queued candidates per pass: no global latency.
+            //  C  evaluation: the surviving queue is a verlet row (all lanes busy, scan order kept).
+            extern __shared__ int pair_smem[];
+            int* q = pair_smem + threadIdx.x;                                   // [PAIR_QCAP][PAIR_THREADS]
+            int* xrow = pair_smem + PAIR_QCAP * PAIR_THREADS + threadIdx.x;     // [PAIR_XCAP][PAIR_THREADS]
+            int xb = 0, xe = 0;
+            const int* xsrc = nullptr;
+            if (nl.excl == 2) { xb = mv.ex2_off[i]; xe = mv.ex2_off[i + 1]; xsrc = mv.ex2_v; }
+            else if (nl.excl == 1) { xb = mv.ring_off[i]; xe = mv.ring_off[i + 1]; xsrc = mv.ring_v; }
+            const int xlen = xe - xb;
+            const bool xfast = xlen <= PAIR_XCAP;
+            if (xfast)
+                for (int s = 0; s < xlen; s++) xrow[s * PAIR_THREADS] = __ldg(xsrc + xb + s) & TM_RING_MASK;
             int cnt = 0;
-            cell_pairs_batched(mv, nl, i, xi, C.lc1sq, [&](int j, d3, double) {
-                if (cnt == PAIR_QCAP) { run_row(q, cnt, PAIR_THREADS, true); cnt = 0; }
-                q[cnt * PAIR_THREADS] = j;
-                ++cnt;
-            });
-            run_row(q, cnt, PAIR_THREADS, true);
+            auto flush = [&]() {
+                // B: drop the excluded candidates, order kept
+                int keep = 0;
+                for (int k = 0; k < cnt; k += 4) {
+                    int j[4];
+                    bool ex[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { j[u] = (k + u < cnt) ? q[(k + u) * PAIR_THREADS] : -1; ex[u] = false; }
+                    if (xfast) {
+                        for (int s = 0; s < xlen; s++) {
+                            const int v = xrow[s * PAIR_THREADS];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) ex[u] |= (v == j[u]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (j[u] < 0) continue;
+                            if (nl.excl == 2) ex[u] = in_sorted(xsrc, xb, xe, j[u]);
+                            else for (int s = xb; s < xe; s++) ex[u] |= ((__ldg(xsrc + s) & TM_RING_MASK) == j[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j[u] >= 0 && !ex[u]) { q[keep * PAIR_THREADS] = j[u]; ++keep; }
+                }
+                // C
+                run_row(q, keep, PAIR_THREADS, true);
+                cnt = 0;
+            };
+            // A
+            int c[3];
+            c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
+            c[1] = (int)((xi.y - nl.box_min[1]) / nl.cell[1]);
+            c[2] = (int)((xi.z - nl.box_min[2]) / nl.cell[2]);
+            const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, nl.shape[0] - 1);
+            if (x0 <= x1) {
+                for (int b = -1; b < 2; b++) {
+                    const int jj = c[1] + b;
+                    if (jj < 0 || jj >= nl.shape[1]) continue;
+                    for (int g = -1; g < 2; g++) {
+                        const int kk = c[2] + g;
+                        if (kk < 0 || kk >= nl.shape[2]) continue;
+                        const int base = jj * nl.strides[1] + kk * nl.strides[2];      // strides[0] == 1
+                        const int kb = __ldg(nl.cell_start + base + x0), ke = __ldg(nl.cell_start + base + x1 + 1);
+                        if (kb >= ke) continue;
+                        P4 xn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) xn[u] = ldrec(nl.cell_rec, min(kb + u, ke - 1));
+                        for (int k = kb; k < ke; k += 4) {
+                            P4 x[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) x[u] = xn[u];
+                            if (k + 4 < ke) {
+#pragma unroll
+                                for (int u = 0; u < 4; u++) xn[u] = ldrec(nl.cell_rec, min(k + 4 + u, ke - 1));
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const d3 d = xi - mk3(x[u].x, x[u].y, x[u].z);
+                                const double l2 = dot3(d, d);
+                                const int j = __double2loint(x[u].w);
+                                if (k + u < ke && j != i && l2 < C.lc1sq) {
+                                    if (cnt == PAIR_QCAP) flush();
+                                    q[cnt * PAIR_THREADS] = j;
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            flush();
         }
         if (WITH_F) {
             double* o = force + 3 * (size_t)i;
@@ -740,14 +840,22 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
         TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
         st = m->stream2;
     }
-    const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * PAIR_QCAP * PAIR_THREADS : 0;
-#define TM_PAIRS(E, F, W, R2) k_pairs<E, F, W, R2><<<nb, PAIR_THREADS, qbytes, st>>>( \
+    const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * (PAIR_QCAP + PAIR_XCAP) * PAIR_THREADS : 0;
+    if (nl.kind == TM_NLIST_CELL && !(m->cellrec_epoch == m->pos_epoch && m->cellrec_list == nl.serial)) {
+        // the candidates' records at the current positions, in cell order
+        k_cell_gather<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, nl.cell_items, m->pos, const_cast<P4*>(nl.cell_rec));
+        TM_LAUNCHED();
+        m->cellrec_epoch = m->pos_epoch; m->cellrec_list = nl.serial;
+    }
+#define TM_PAIRS2(E, F, W, R2, CL) k_pairs<E, F, W, R2, CL><<<nb, PAIR_THREADS, qbytes, st>>>( \
         mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
+#define TM_PAIRS(E, F, W, R2) do { if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
     else if (with_e)  { if (r2) TM_PAIRS(true, true, false, true); else TM_PAIRS(true, true, false, false); }
     else              { if (r2) TM_PAIRS(false, true, false, true); else TM_PAIRS(false, true, false, false); }
 #undef TM_PAIRS
+#undef TM_PAIRS2
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     if (beside) {
@@ -876,9 +984,12 @@ int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_par
 
 int tm_preload_energy() {
     TM_PRELOAD((k_props<true, true>)); TM_PRELOAD((k_props<true, false>)); TM_PRELOAD((k_props<false, false>));
-    TM_PRELOAD((k_pairs<true, true, true, true>)); TM_PRELOAD((k_pairs<true, true, true, false>));
-    TM_PRELOAD((k_pairs<true, true, false, true>)); TM_PRELOAD((k_pairs<true, true, false, false>));
-    TM_PRELOAD((k_pairs<false, true, false, true>)); TM_PRELOAD((k_pairs<false, true, false, false>));
+#define TM_PL(CL) \
+    TM_PRELOAD((k_pairs<true, true, true, true, CL>)); TM_PRELOAD((k_pairs<true, true, true, false, CL>)); \
+    TM_PRELOAD((k_pairs<true, true, false, true, CL>)); TM_PRELOAD((k_pairs<true, true, false, false, CL>)); \
+    TM_PRELOAD((k_pairs<false, true, false, true, CL>)); TM_PRELOAD((k_pairs<false, true, false, false, CL>))
+    TM_PL(false); TM_PL(true);
+#undef TM_PL
     TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad<0>); TM_PRELOAD(k_grad<1>); TM_PRELOAD(k_grad<2>);
     return 0;
 }

@@ -315,6 +315,8 @@ int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
 
     nl->cell_start = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)(ncell + 1));
     nl->cell_items = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)V);
+    nl->cell_rec = (P4*)tm_pool_alloc(m->device, sizeof(P4) * (size_t)V);
+    TM_CHECK(nl->cell_rec, "out of device memory for the cell list");
     PoolBuf<int> count(m->device);
     int* cell_of = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)V);
     *cell_of_out = cell_of;
@@ -460,6 +462,7 @@ int tm_nlist_destroy(tm_nlist* nl) {
     if (!nl) return 0;
     cudaSetDevice(nl->device);
     tm_pool_free(nl->device, nl->cell_start); tm_pool_free(nl->device, nl->cell_items);
+    tm_pool_free(nl->device, nl->cell_rec);
     tm_pool_free(nl->device, nl->row_cnt); tm_pool_free(nl->device, nl->row_j);
     tm_pool_free(nl->device, nl->cell_of);
     tm_pool_free(nl->device, nl->x_build);
