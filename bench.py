@@ -244,6 +244,7 @@ def hmc_step_run(args, core, workload, rank):
         acc.append(core.pflip(fmesh, festore, 0.1, seed=10 + k))
         ts.append(1e3 * (time.perf_counter() - t0))
     out["pflip_ms"] = float(np.median(ts))
+    out["pflip_ms_min"] = float(np.min(ts))
     out["pflip_proposals"] = int(fmesh.n_edges() * 0.1)
     out["pflip_acceptance"] = float(np.mean(acc)) / out["pflip_proposals"]
     t0 = time.perf_counter()
@@ -307,7 +308,7 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
         cm.set_positions(v)
         cm.set_momenta(p_host)
         cm.sync()
-    for _ in range(2):
+    for _ in range(2 if world > 1 else 5):      # unpartitioned: both record-array parities direct, captured, replayed
         lf_reset()
         barrier()
         cm.vv_integrate_async(nl, par, 1.0, lf_dt, L)
