@@ -43,20 +43,22 @@ constexpr int TM_RING_PAD     = TM_RING_MASK;
 constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 // launch shapes of the two sweeps (overridable with -D for timing experiments, scripts/build_variant.py)
 #ifndef TM_PROPS_NT
-#define TM_PROPS_NT 128
+#define TM_PROPS_NT 64
 #endif
 #ifndef TM_GRAD_NT
-#define TM_GRAD_NT 128
+#define TM_GRAD_NT 64
 #endif
 // resident blocks per SM the register allocation aims at (measured on B200 at 655k vertices,
 // profiles/r01, r01g). With the ring records staged in shared memory the property sweep needs
 // 64-70 registers (6 blocks of 128: 55 us) and the ring gradient 128 without spilling (4 blocks:
 // 82 us; 96 registers / 5 blocks spills and takes 91 us, 80 / 6 blocks 122 us).
+// 64-thread blocks at the same number of resident warps drain a little more evenly than 128-thread ones
+// (property sweep 54.6 -> 52.6 us, ring gradient 81.3 -> 78.9 us).
 #ifndef TM_PROPS_MINB
-#define TM_PROPS_MINB 6
+#define TM_PROPS_MINB 12
 #endif
 #ifndef TM_GRAD_MINB
-#define TM_GRAD_MINB 4
+#define TM_GRAD_MINB 8
 #endif
 constexpr int TM_PROPS_THREADS = TM_PROPS_NT;
 constexpr int TM_GRAD_THREADS  = TM_GRAD_NT;
