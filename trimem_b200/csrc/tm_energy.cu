@@ -990,6 +990,7 @@ int tm_preload_energy() {
     TM_PRELOAD((k_pairs<false, true, false, true, CL>)); TM_PRELOAD((k_pairs<false, true, false, false, CL>))
     TM_PL(false); TM_PL(true);
 #undef TM_PL
+    TM_PRELOAD(k_cell_gather); TM_PRELOAD(k_export_grad);
     TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad<0>); TM_PRELOAD(k_grad<1>); TM_PRELOAD(k_grad<2>);
     return 0;
 }
