@@ -173,57 +173,3 @@ __device__ __forceinline__ void for_each_pair_fast(const MeshView& mv, const NlV
         }
     }
 }
-
-
-// Cell-list candidates of the energy / gradient sweeps: the same candidate and exclusion set as
-// for_each_pair_fast<false> (CellList::point_distances, cell_list.h:131-219: build-time occupancy,
-// the query vertex's live position, exclusions on the current connectivity), organised for the
-// memory system. x is the fastest cell index, so the three x-neighbours of a (y, z) pair are ONE
-// contiguous run of cell_items: 9 runs instead of 27 cells; a run is consumed four candidates at
-// a time (indices, then the four records, then the tests); the level-2 exclusion is a binary
-// search in the vertex's sorted two-ring row (tm_rings.cu) instead of the nested ring walk
-// (~5 loads instead of up to 42 per candidate inside the cut-off). Requires tm_ensure_ring2 for
-// exclusion level 2. f(j, d = x_i - x_j, l2).
-template <class F>
-__device__ __forceinline__ void cell_pairs_batched(const MeshView& mv, const NlView& nl, int i, d3 xi, double dmax2, F f) {
-    int c[3];
-    c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
-    c[1] = (int)((xi.y - nl.box_min[1]) / nl.cell[1]);
-    c[2] = (int)((xi.z - nl.box_min[2]) / nl.cell[2]);
-    const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, nl.shape[0] - 1);
-    if (x0 > x1) return;
-    int xb = 0, xe = 0;
-    if (nl.excl == 2) { xb = mv.ex2_off[i]; xe = mv.ex2_off[i + 1]; }
-    else if (nl.excl == 1) { xb = mv.ring_off[i]; xe = mv.ring_off[i + 1]; }
-    for (int b = -1; b < 2; b++) {
-        const int jj = c[1] + b;
-        if (jj < 0 || jj >= nl.shape[1]) continue;
-        for (int g = -1; g < 2; g++) {
-            const int kk = c[2] + g;
-            if (kk < 0 || kk >= nl.shape[2]) continue;
-            const int base = jj * nl.strides[1] + kk * nl.strides[2];      // strides[0] == 1
-            const int kb = __ldg(nl.cell_start + base + x0), ke = __ldg(nl.cell_start + base + x1 + 1);
-            for (int k = kb; k < ke; k += 4) {
-                int j[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) j[u] = (k + u < ke) ? __ldg(nl.cell_items + k + u) : i;
-                P4 x[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) x[u] = ldrec(mv.pos, j[u]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const d3 d = xi - mk3(x[u].x, x[u].y, x[u].z);
-                    const double l2 = dot3(d, d);
-                    if (j[u] != i && l2 < dmax2) {
-                        bool ex = false;
-                        if (nl.excl == 2) ex = in_sorted(mv.ex2_v, xb, xe, j[u]);
-                        else if (nl.excl == 1) {
-                            for (int s = xb; s < xe; s++) ex |= ((mv.ring_v[s] & TM_RING_MASK) == j[u]);
-                        }
-                        if (!ex) f(j[u], d, l2);
-                    }
-                }
-            }
-        }
-    }
-}
