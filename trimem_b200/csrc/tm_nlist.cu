@@ -119,11 +119,38 @@ __global__ void k_vcell_count(VGrid g, const P4* __restrict__ pos, int V, int* _
     atomicAdd(count + id, 1);
 }
 
-__global__ void __launch_bounds__(128)
-k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const int* __restrict__ cell_items,
-                const int* __restrict__ ex2_off, const int* __restrict__ ex2_v, int excl, double rlist,
-                int cap, int* __restrict__ row_j, int* __restrict__ row_cnt, int* __restrict__ maxcnt, SweepRange R) {
-    const int t = blockIdx.x * 128 + threadIdx.x;
+// cell-ordered copy of the positions for the search: rec[k] = (x, y, z of items[k], id)
+__global__ void k_vgather(int V, const int* __restrict__ items, const P4* __restrict__ pos, P4* __restrict__ rec) {
+    const int k = blockIdx.x * NT + threadIdx.x;
+    if (k >= V) return;
+    const int j = items[k];
+    const d3 p = ldpos(pos, j);
+    P4 r;
+    r.x = p.x; r.y = p.y; r.z = p.z;
+    r.w = __hiloint2double(0, j);
+    rec[k] = r;
+}
+
+// The search, shaped for the memory system and the issue slots (first version: one thread per vertex over
+// 27 cells with an index -> record chain, a square root per candidate and a binary search per hit, 776 us
+// at 655,362 vertices, plus two sort kernels; now ~400 us in all):
+//  * the candidates of a cell are contiguous records (k_vgather), x is the fastest cell index, so the 27
+//    cells are 9 runs read four records per trip with the next trip's in flight (one memory level);
+//  * `dist <= rlist` is decided on the squared distance, accumulated exactly like the reference's norm
+//    (no FMA): s2max is the largest double whose correctly rounded square root is <= rlist (found on the
+//    host), so the decision is bit-identical and the 150 square roots per vertex disappear;
+//  * candidates inside the radius are queued per thread in shared memory, the exclusion test compares four
+//    of them per pass with the vertex's two-ring (or ring) row held in shared memory, and the survivors go
+//    to the vertex's row in scan order.
+constexpr int VS_THREADS = 128, VS_QCAP = 64, VS_XCAP = 32;
+__global__ void __launch_bounds__(VS_THREADS, 4)
+k_verlet_search2(MeshView mv, VGrid g, const int* __restrict__ cell_start, const P4* __restrict__ rec,
+                 int excl, double s2max, int cap, int* __restrict__ row_j, int* __restrict__ row_cnt,
+                 int* __restrict__ maxcnt, SweepRange R) {
+    __shared__ int q_s[VS_QCAP][VS_THREADS];
+    __shared__ int x_s[VS_XCAP][VS_THREADS];
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * VS_THREADS + tid;
     const int i = R.first + t;
     int n = 0;
     if (t < R.count) {
@@ -131,32 +158,109 @@ k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const 
         int c[3];
         vcell(g, xi, c);
         int xb = 0, xe = 0;
-        if (excl == 2) { xb = ex2_off[i]; xe = ex2_off[i + 1]; }
-        else if (excl == 1) { xb = mv.ring_off[i]; xe = mv.ring_off[i + 1]; }
+        const int* xsrc = nullptr;
+        if (excl == 2) { xb = mv.ex2_off[i]; xe = mv.ex2_off[i + 1]; xsrc = mv.ex2_v; }
+        else if (excl == 1) { xb = mv.ring_off[i]; xe = mv.ring_off[i + 1]; xsrc = mv.ring_v; }
+        const int xlen = xe - xb;
+        const bool xfast = xlen <= VS_XCAP;
+        if (xfast)
+            for (int s = 0; s < xlen; s++) x_s[s][tid] = __ldg(xsrc + xb + s) & TM_RING_MASK;
+        int* row = row_j + tm_row_base(i, cap);
+        // queue layout: [0, filt) candidates that passed the exclusion test, [filt, cnt) not yet tested
+        int cnt = 0, filt = 0;
+        bool spilled = false;
+        auto filter = [&]() {
+            int keep = filt;
+            for (int k = filt; k < cnt; k += 4) {
+                int j[4];
+                bool ex[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { j[u] = (k + u < cnt) ? q_s[k + u][tid] : -1; ex[u] = false; }
+                if (xfast) {
+                    for (int s = 0; s < xlen; s++) {
+                        const int v = x_s[s][tid];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) ex[u] |= (v == j[u]);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (j[u] < 0) continue;
+                        if (excl == 2) ex[u] = in_sorted(xsrc, xb, xe, j[u]);
+                        else for (int s = xb; s < xe; s++) ex[u] |= ((__ldg(xsrc + s) & TM_RING_MASK) == j[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (j[u] >= 0 && !ex[u]) { q_s[keep][tid] = j[u]; ++keep; }
+            }
+            filt = cnt = keep;
+        };
+        auto make_room = [&]() {
+            filter();
+            if (filt == VS_QCAP) {                 // a row longer than the queue: continue in global memory
+                for (int k = 0; k < filt; k++) { if (n < cap) row[n * 32] = q_s[k][tid]; ++n; }
+                filt = cnt = 0;
+                spilled = true;
+            }
+        };
+        auto flush = make_room;
+        const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, g.n[0] - 1);
         for (int dz = -1; dz < 2; dz++) {
             const int cz = c[2] + dz;
             if (cz < 0 || cz >= g.n[2]) continue;
             for (int dy = -1; dy < 2; dy++) {
                 const int cy = c[1] + dy;
                 if (cy < 0 || cy >= g.n[1]) continue;
-                // the three x-neighbours are consecutive cells: one contiguous range of items
-                const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, g.n[0] - 1);
                 const int base = (cz * g.n[1] + cy) * g.n[0];
                 const int kb = __ldg(cell_start + base + x0), ke = __ldg(cell_start + base + x1 + 1);
-                for (int k = kb; k < ke; k++) {
-                    const int j = __ldg(cell_items + k);
-                    if (j == i) continue;
-                    const double l = dist_nofma(sub_nofma(xi, ldpos(mv.pos, j)));
-                    if (!(l <= rlist)) continue;
-                    bool ex = false;
-                    if (excl == 2) ex = in_sorted(ex2_v, xb, xe, j);
-                    else if (excl == 1) {
-                        for (int s = xb; s < xe; s++) ex |= ((mv.ring_v[s] & TM_RING_MASK) == j);
+                if (kb >= ke) continue;
+                P4 xn[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) xn[u] = ldrec(rec, min(kb + u, ke - 1));
+                for (int k = kb; k < ke; k += 4) {
+                    P4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) x[u] = xn[u];
+                    if (k + 4 < ke) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) xn[u] = ldrec(rec, min(k + 4 + u, ke - 1));
                     }
-                    if (ex) continue;
-                    if (n < cap) row_j[tm_row_base(i, cap) + n * 32] = j;
-                    ++n;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const d3 d = sub_nofma(xi, mk3(x[u].x, x[u].y, x[u].z));
+                        double s2 = __dmul_rn(d.x, d.x);
+                        s2 = __dadd_rn(s2, __dmul_rn(d.y, d.y));
+                        s2 = __dadd_rn(s2, __dmul_rn(d.z, d.z));
+                        const int j = __double2loint(x[u].w);
+                        if (k + u < ke && j != i && s2 <= s2max) {
+                            if (cnt == VS_QCAP) flush();
+                            q_s[cnt][tid] = j;
+                            ++cnt;
+                        }
+                    }
                 }
+            }
+        }
+        filter();
+        if (!spilled) {
+            // the whole row sits in the queue: ascending ids (= ascending along the space-filling order,
+            // which keeps the pair sweep's gathers on few cache lines) by insertion in shared memory
+            for (int a = 1; a < filt; a++) {
+                const int v = q_s[a][tid];
+                int b = a - 1;
+                while (b >= 0 && q_s[b][tid] > v) { q_s[b + 1][tid] = q_s[b][tid]; --b; }
+                q_s[b + 1][tid] = v;
+            }
+            for (int k = 0; k < filt; k++) { if (n < cap) row[n * 32] = q_s[k][tid]; ++n; }
+        } else {
+            for (int k = 0; k < filt; k++) { if (n < cap) row[n * 32] = q_s[k][tid]; ++n; }
+            const int m = n < cap ? n : cap;
+            for (int a = 1; a < m; a++) {
+                const int v = row[a * 32];
+                int b = a - 1;
+                while (b >= 0 && row[b * 32] > v) { row[(b + 1) * 32] = row[b * 32]; --b; }
+                row[(b + 1) * 32] = v;
             }
         }
         row_cnt[i] = n < cap ? n : cap;
@@ -165,22 +269,6 @@ k_verlet_search(MeshView mv, VGrid g, const int* __restrict__ cell_start, const 
     int w = n;
     for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
     if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(maxcnt, w);
-}
-
-// ascending ids inside every row (column-major rows: the warp's accesses are coalesced).
-// Ascending device ids = ascending along the space-filling order, which keeps the position
-// gathers of the pair sweep on few cache lines.
-__global__ void k_sort_rows(int V, int cap, const int* __restrict__ row_cnt, int* __restrict__ row_j) {
-    const int i = blockIdx.x * NT + threadIdx.x;
-    if (i >= V) return;
-    const int n = row_cnt[i];
-    int* col = row_j + tm_row_base(i, cap);
-    for (int a = 1; a < n; a++) {
-        const int v = col[a * 32];
-        int q = a - 1;
-        while (q >= 0 && col[q * 32] > v) { col[(q + 1) * 32] = col[q * 32]; --q; }
-        col[(q + 1) * 32] = v;
-    }
 }
 
 // positions at build time, and the largest displacement since (max is order-free: deterministic)
@@ -382,7 +470,15 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
     if (tm_exclusive_scan(m, count.p, start.p, (int)ncell, nullptr)) return 1;
     TM_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int) * (size_t)(ncell + 1), m->stream));
     k_cell_fill<<<vb, NT, 0, m->stream>>>(V, cell_of.p, start.p, count.p, items.p); TM_LAUNCHED();
-    if (tm_sort_segments(m, ncell, start.p, items.p)) return 1;       // deterministic order inside a cell
+    // (the order inside a cell is whatever the atomics made it: every row is sorted before it is stored)
+
+    // largest squared distance whose correctly rounded square root is still <= rlist
+    double s2max = nl->rlist * nl->rlist;
+    while (std::sqrt(s2max) > nl->rlist) s2max = std::nextafter(s2max, 0.0);
+    while (std::sqrt(std::nextafter(s2max, HUGE_VAL)) <= nl->rlist) s2max = std::nextafter(s2max, HUGE_VAL);
+    PoolBuf<P4> rec(dev);
+    TM_CHECK(!rec.alloc(V), "out of device memory for the search records");
+    k_vgather<<<vb, NT, 0, m->stream>>>(V, items.p, m->pos, rec.p); TM_LAUNCHED();
 
     nl->row_cnt = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)V);
     TM_CHECK(nl->row_cnt, "out of device memory for verlet rows");
@@ -396,9 +492,8 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
         nl->row_cap = cap;
         nl->row_j = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)cap * 32 * ((V + 31) / 32));
         TM_CHECK(nl->row_j, "out of device memory for verlet rows of width %d", cap);
-        k_verlet_search<<<(R.count + 127) / 128, 128, 0, m->stream>>>(m->view(), g, start.p, items.p, m->ex2_off, m->ex2_v,
-                                                                      nl->excl, nl->rlist, cap, nl->row_j,
-                                                                      nl->row_cnt, maxcnt.p, R);
+        k_verlet_search2<<<(R.count + VS_THREADS - 1) / VS_THREADS, VS_THREADS, 0, m->stream>>>(
+            m->view(), g, start.p, rec.p, nl->excl, s2max, cap, nl->row_j, nl->row_cnt, maxcnt.p, R);
         TM_LAUNCHED();
         TM_CUDA(cudaGetLastError());
         int widest = 0;
@@ -414,7 +509,6 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
         tm_pool_free(dev, nl->row_j); nl->row_j = nullptr;
         cap = ((widest + 7) / 8) * 8;
     }
-    k_sort_rows<<<vb, NT, 0, m->stream>>>(V, nl->row_cap, nl->row_cnt, nl->row_j); TM_LAUNCHED();
     nl->x_build = (double*)tm_pool_alloc(dev, sizeof(double) * 3 * (size_t)V);
     TM_CHECK(nl->x_build, "out of device memory for the list's build positions");
     k_save_positions<<<vb, NT, 0, m->stream>>>(V, m->pos, nl->x_build); TM_LAUNCHED();
