@@ -214,32 +214,31 @@ k_verlet_search2(MeshView mv, VGrid g, const int* __restrict__ cell_start, const
                 if (cy < 0 || cy >= g.n[1]) continue;
                 const int base = (cz * g.n[1] + cy) * g.n[0];
                 const int kb = __ldg(cell_start + base + x0), ke = __ldg(cell_start + base + x1 + 1);
-                if (kb >= ke) continue;
-                P4 xn[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) xn[u] = ldrec(rec, min(kb + u, ke - 1));
-                for (int k = kb; k < ke; k += 4) {
-                    P4 x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) x[u] = xn[u];
-                    if (k + 4 < ke) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) xn[u] = ldrec(rec, min(k + 4 + u, ke - 1));
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const d3 d = sub_nofma(xi, mk3(x[u].x, x[u].y, x[u].z));
-                        double s2 = __dmul_rn(d.x, d.x);
-                        s2 = __dadd_rn(s2, __dmul_rn(d.y, d.y));
-                        s2 = __dadd_rn(s2, __dmul_rn(d.z, d.z));
-                        const int j = __double2loint(x[u].w);
-                        if (k + u < ke && j != i && s2 <= s2max) {
+                auto test = [&](const P4& x) {
+                    const d3 d = sub_nofma(xi, mk3(x.x, x.y, x.z));
+                    double s2 = __dmul_rn(d.x, d.x);
+                    s2 = __dadd_rn(s2, __dmul_rn(d.y, d.y));
+                    s2 = __dadd_rn(s2, __dmul_rn(d.z, d.z));
+                    if (s2 <= s2max) {
+                        const int j = __double2loint(x.w);
+                        if (j != i) {
                             if (cnt == VS_QCAP) flush();
                             q_s[cnt][tid] = j;
                             ++cnt;
                         }
                     }
+                };
+                int k = kb;
+                // whole groups of four without per-candidate bounds logic (two groups in flight), then the tail
+#pragma unroll 2
+                for (; k + 4 <= ke; k += 4) {
+                    P4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) x[u] = ldrec(rec, k + u);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) test(x[u]);
                 }
+                for (; k < ke; k++) test(ldrec(rec, k));
             }
         }
         filter();
