@@ -119,3 +119,48 @@ HMC_CASES = {
     "hmc_ico3_cooling": ("ico3_area", 23, {"time_step": 2.0e-3, "num_integration_steps": 4, "info_step": 0,
                                            "cooling_factor": 0.5, "cooling_start_step": 1, "mass": 2.0}, 5),
 }
+
+
+# open / irregular meshes (boundary rings, a valence-12 vertex) with a parametrisation that exercises every
+# term, for the gradient near boundaries
+def fan_mesh(n_spokes=12):
+    ang = np.linspace(0, 2 * np.pi, n_spokes, endpoint=False)
+    ring1 = np.column_stack([np.cos(ang), np.sin(ang), 0.15 * np.cos(3 * ang)])
+    ring2 = 2.0 * np.column_stack([np.cos(ang + np.pi / n_spokes), np.sin(ang + np.pi / n_spokes), 0.1 * np.sin(2 * ang)])
+    v = np.vstack([[0.0, 0.0, 0.3], ring1, ring2])
+    f = []
+    for k in range(n_spokes):
+        a, b = 1 + k, 1 + (k + 1) % n_spokes
+        f.append([0, a, b])
+        c = 1 + n_spokes + k
+        f.append([a, c, b])
+        f.append([b, c, 1 + n_spokes + (k + 1) % n_spokes])
+    return v, np.array(f, np.int32)
+
+
+OPEN_MESHES = ("tube", "rect", "fan")
+
+
+def open_mesh(name):
+    if name == "tube":
+        v, f = meshgen.tube(2.0, 0.7, 24)
+        # (off the exactly flat quad diagonals, where the reference's acos cannot resolve the angle)
+        return v + 0.01 * np.random.default_rng(6).normal(size=v.shape), f
+    if name == "rect":
+        v, f = meshgen.rect(12, 9)
+        return v + 0.02 * np.random.default_rng(4).normal(size=v.shape), f
+    return fan_mesh()
+
+
+def open_mesh_params(mod, mesh):
+    ep = mod.EnergyParams()
+    ep.kappa_b, ep.kappa_a, ep.kappa_v, ep.kappa_c, ep.kappa_t, ep.kappa_r = 3.0, 2.0, 1.5, 1.0, 0.5, 0.7
+    a, l = mod.avg_tri_props(mesh)
+    bp = ep.bond_params
+    bp.lc0, bp.lc1, bp.a0 = 1.05 * l, 0.95 * l, a
+    ep.bond_params = bp
+    rp = ep.repulse_params
+    rp.lc1, rp.rlist, rp.exclusion_level, rp.n_search = 2.2 * l, 2.5 * l, 1, "verlet-list"
+    ep.repulse_params = rp
+    ep.area_frac = ep.volume_frac = ep.curvature_frac = 0.9
+    return ep

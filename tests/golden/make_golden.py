@@ -243,6 +243,18 @@ def hmc_chain_cases():
         save(name, xs=np.array(xs), acc=np.array(accs), temperature=np.array([chain.T]))
 
 
+def open_mesh_cases():
+    out = {}
+    for name in cases.OPEN_MESHES:
+        v, f = cases.open_mesh(name)
+        mesh = ref.TriMesh(v, f)
+        es = ref.EnergyManager(mesh, cases.open_mesh_params(ref, mesh))
+        out[f"{name}_props"] = cases.props6(es.properties(mesh))
+        out[f"{name}_energy"] = es.energy(mesh)
+        out[f"{name}_grad"] = es.gradient(mesh)
+    save("open_meshes", **out)
+
+
 def thread_spread():
     """The reference's own 1-vs-N-thread spread on the headline case (its noise floor)."""
     import subprocess
@@ -259,7 +271,7 @@ def thread_spread():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc"]
+    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc", "open"]
     if "topology" in which: topology_cases()
     if "analytic" in which: analytic_cases()
     if "primitives" in which: primitive_cases()
@@ -269,3 +281,4 @@ if __name__ == "__main__":
     if "spread" in which: thread_spread()
     if "trajectory" in which: trajectory_cases()
     if "hmc" in which: hmc_chain_cases()
+    if "open" in which: open_mesh_cases()

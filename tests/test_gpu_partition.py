@@ -163,3 +163,53 @@ def test_partition_errors(gpu_core):
         cm.part_create(0, 2)
     with pytest.raises(cabi.TMError, match="not every peer is attached"):
         cm.energy_async(None, workload.abi_params(es))
+
+
+@pytest.mark.parametrize("gen,nranks", [("tube", 2), ("tube", 3), ("rect", 2), ("fan", 2)])
+def test_partitioned_open_and_irregular_meshes(gpu_core, port, gen, nranks):
+    """Boundary vertices (ring flags, open fans) and a valence-12 vertex (generic ring walk) across the cuts:
+    the partitioned sums and gradient rows equal the unpartitioned ones and the oracle port's."""
+    v, f = cases.open_mesh(gen)
+    mesh = gpu_core.TriMesh(v, f)
+    ep = cases.open_mesh_params(gpu_core, mesh)
+    a, l = gpu_core.avg_tri_props(mesh)
+    es = gpu_core.EnergyManager(mesh, ep)
+    e1, g1 = es.energy(mesh), es.gradient(mesh)
+    pm = port.TriMesh(v, f)
+    pe = port.EnergyManager(pm, port.params_from(ep))
+    assert abs(e1 - pe.energy(pm)) <= TOL * abs(e1)
+    # Gradient near a boundary: the reference's dihedral_angle is 0 on boundary edges while its
+    # dihedral_angle_grad is still evaluated there, on the fictitious sector of the boundary loop (SURVEY
+    # App. C #11): the reference gradient is not the gradient of its energy on open meshes. Parity means
+    # reproducing exactly that (k_grad: boundary_spoke_cot).
+    assert nrm(g1, pe.gradient(pm)) < 1e-9
+    gold = cases.load_golden("open_meshes")          # the reference build's own values
+    assert abs(e1 - float(gold[f"{gen}_energy"])) <= TOL * abs(e1)
+    assert nrm(g1, gold[f"{gen}_grad"]) < 1e-9
+    for q in range(6):
+        assert abs(cases.props6(es.properties(mesh))[q] - gold[f"{gen}_props"][q]) <= TOL * abs(gold[f"{gen}_props"][q]) + 1e-300
+    par = workload.abi_params(es)
+    arrs = mesh.halfedge_arrays()[:4]
+    cm = [cabi.Mesh(*arrs, xyz=v) for _ in range(nranks)]
+    for r, m in enumerate(cm):
+        m.part_create(r, nranks)
+    for r, m in enumerate(cm):
+        for q, o in enumerate(cm):
+            if q != r:
+                m.part_attach_local(q, o)
+    rp = ep.repulse_params
+    nls = [cabi.NList(m, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level) for m in cm]
+    for m, nl in zip(cm, nls):
+        m.part_prepare(nl)
+    import threading
+    out = [None] * nranks
+
+    def run(r):
+        out[r] = (cm[r].energy(nls[r], par)[0], cm[r].gradient(nls[r], par))
+    th = [threading.Thread(target=run, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert all(o[0] == out[0][0] for o in out)
+    assert abs(out[0][0] - e1) <= 1e-13 * abs(e1)
+    g = np.sum([o[1] for o in out], axis=0)
+    assert nrm(g, g1) < 1e-13

@@ -247,6 +247,8 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
             return 1;
     }
     m->V = V; m->HE = HE;
+    m->has_boundary = false;
+    for (int h = 0; h < HE; h++) if (he_face[h] < 0) { m->has_boundary = true; break; }
     // he_next / he_face do not hold vertex ids; he_to / v_he are kept as uploaded (host numbering)
     // and converted to the device numbering by tm_ensure_layout
     TM_CUDA(cudaMemcpyAsync(m->he_to_h, he_to, sizeof(int) * HE, cudaMemcpyHostToDevice, m->stream));

@@ -140,6 +140,7 @@ struct tm_mesh {
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
     R8* ring8 = nullptr;
     bool rings_valid = false;
+    bool has_boundary = false;   // the uploaded connectivity has boundary half-edges (open mesh)
     // host-numbered connectivity as uploaded (he_to_h, v_he_h) and the vertex permutation
     int *he_to_h = nullptr, *v_he_h = nullptr;
     int *d2h = nullptr, *h2d = nullptr;

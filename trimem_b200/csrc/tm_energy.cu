@@ -589,6 +589,63 @@ __device__ __forceinline__ void gslot_pair(GSlot& t, const GSlot& before) {
     t.in = rsqrt_pos(dot3(t.n, t.n));
 }
 
+// Boundary spoke (i -> j has a face, j -> i is a boundary half-edge). The reference's dihedral_angle is 0
+// there, but its vertex_properties_grad still adds l * dihedral_angle_grad<1> (mesh_properties.cpp:88-98,
+// mesh_util.h:135-185), evaluated on the boundary loop as OpenMesh defines sectors of
+// boundary half-edges: n1 = the normal of the sector (j -> i, i -> p) -- which is the wrapped-around
+// normal e_p x e_j of the ring walk -- and a04 = the signed angle at j between i and m, the boundary
+// neighbour of j on the other side, the sign taken against the face (j, m, q). Returns cot(a04).
+// Parity with the reference demands the same term; it only ever runs for boundary vertices of open meshes.
+__device__ __noinline__ double boundary_spoke_cot(const MeshView& mv, d3 xi, d3 xj, int j) {
+    const int b = mv.ring_off[j], d = mv.ring_off[j + 1] - b;
+    int sm = -1;
+    for (int t = 0; t < d; t++) {
+        const int w = mv.ring_v[b + t];
+        if ((w & TM_RING_FACE) && !(w & TM_RING_OFACE)) sm = t;       // j -> m has a face, m -> j is boundary
+    }
+    if (sm < 0 || d < 2) return 0.0;
+    const int m = mv.ring_v[b + sm] & TM_RING_MASK;
+    const int q = mv.ring_v[b + (sm == 0 ? d - 1 : sm - 1)] & TM_RING_MASK;   // face (j, m, q)
+    const d3 xm = ldpos(mv.pos, m), xq = ldpos(mv.pos, q);
+    const d3 v0 = xi - xj, v1 = xm - xj;
+    const d3 cr = cross3(v0, v1);
+    const d3 fn = cross3(xq - xm, xj - xm);
+    const double sn = sqrt_nn(dot3(cr, cr));
+    if (!(sn > 0.0)) return 0.0;
+    const double c = dot3(v0, v1) / sn;                                // |cot|, signed by the cosine
+    return dot3(cr, fn) >= 0.0 ? c : -c;
+}
+
+// The boundary-spoke terms of vertex i, evaluated apart from the ring walk (rare, and a call inside the
+// walk costs the closed-mesh path ~8 % in spills): for every slot with a face whose opposite half-edge is
+// on the boundary, W [cot(a03) n0^ + cot(a04) n1^] with W = fC/2 + kb (rho_i + rho_j).
+__device__ __noinline__ void boundary_spoke_terms(const MeshView& mv, double fC, double kb, int i, d3 xi, double rho_i,
+                                                  d3& g) {
+    const int b = mv.ring_off[i], d = mv.ring_off[i + 1] - b;
+    for (int s = 0; s < d; s++) {
+        const int w = mv.ring_v[b + s];
+        if (!(w & TM_RING_FACE) || (w & TM_RING_OFACE)) continue;
+        const int j = w & TM_RING_MASK;
+        const P4 rj = ldrec(mv.pos, j);
+        const d3 xj = mk3(rj.x, rj.y, rj.z);
+        const d3 e_s = xj - xi;
+        const d3 e_p = ldpos(mv.pos, mv.ring_v[b + (s == 0 ? d - 1 : s - 1)] & TM_RING_MASK) - xi;
+        const d3 e_n = ldpos(mv.pos, mv.ring_v[b + (s + 1 == d ? 0 : s + 1)] & TM_RING_MASK) - xi;
+        const d3 n_cur = cross3(e_s, e_p), n_nxt = cross3(e_n, e_s);
+        const double W = 0.5 * fC + kb * (rho_i + rj.w);
+        const double nn = dot3(n_cur, n_cur), mm = dot3(n_nxt, n_nxt);
+        if (nn > 0.0) axpy3(g, W * (dot3(e_s, e_s) - dot3(e_s, e_p)) / nn, n_cur);
+        if (mm > 0.0) axpy3(g, W * boundary_spoke_cot(mv, xi, xj, j) / sqrt_nn(mm), n_nxt);
+    }
+}
+__device__ __forceinline__ bool row_has_boundary_spoke(const R8& r) {
+    bool b = false;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        b |= r.v[k] != TM_RING_PAD && (r.v[k] & TM_RING_FACE) && !(r.v[k] & TM_RING_OFACE);
+    return b;
+}
+
 // contribution of ring slot s (mesh_properties.cpp:73-134) to g_i
 __device__ __forceinline__ void grad_slot(const DevParams& P, const GradK& K, double rho_i, int word,
                                           const GSlot& prv, const GSlot& cur, const GSlot& nxt,
@@ -631,14 +688,14 @@ __device__ __forceinline__ void grad_slot(const DevParams& P, const GradK& K, do
     esum = esum + (prv.e - cur.e);
 }
 
-__device__ __forceinline__ void ring_grad_fast(const P4* pos, const DevParams& P, const GradK& K, const R8& row,
+__device__ __forceinline__ void ring_grad_fast(const MeshView& mv, const DevParams& P, const GradK& K, const R8& row,
                                                int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
     d3 e[8];
     double rho[8];
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         if (s < d) {
-            const P4 q = ldrec(pos, row.v[s] & TM_RING_MASK);
+            const P4 q = ldrec(mv.pos, row.v[s] & TM_RING_MASK);
             e[s] = mk3(q.x, q.y, q.z) - xi;
             rho[s] = q.w;
         }
@@ -679,7 +736,7 @@ constexpr int GRAD_UNROLL = TM_GRAD_UNROLL;
 // a [slot][thread] layout of 16-byte halves (conflict-free 128-bit accesses), and the slot loop
 // fetches spoke s+1 when it needs it. The register version keeps 8 x 4 doubles of ring data live
 // next to three GSlots and nine accumulators and spills ~200 bytes per thread at 128 registers.
-__device__ __forceinline__ void ring_grad_smem(const P4* pos, const DevParams& P, const GradK& K, const R8& row,
+__device__ __forceinline__ void ring_grad_smem(const MeshView& mv, const DevParams& P, const GradK& K, const R8& row,
                                                int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
     __shared__ double2 s_xy[8][TM_GRAD_THREADS];
     __shared__ double2 s_zr[8][TM_GRAD_THREADS];
@@ -688,7 +745,7 @@ __device__ __forceinline__ void ring_grad_smem(const P4* pos, const DevParams& P
 #pragma unroll
     for (int s = 0; s < 8; s++) {
         if (s < d) {
-            const P4* src = pos + (row.v[s] & TM_RING_MASK);
+            const P4* src = mv.pos + (row.v[s] & TM_RING_MASK);
             cp_async16(&s_xy[s][tid], src);
             cp_async16(&s_zr[s][tid], reinterpret_cast<const char*>(src) + 16);
             s_w[s][tid] = row.v[s];
@@ -769,9 +826,9 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     else {
         const int d = row_valence(row);
 #if TM_GRAD_SMEM
-        if (d > 0) ring_grad_smem(mv.pos, P, K, row, d, xi, ri.w, g, nsum, esum);
+        if (d > 0) ring_grad_smem(mv, P, K, row, d, xi, ri.w, g, nsum, esum);
 #else
-        if (d > 0) ring_grad_fast(mv.pos, P, K, row, d, xi, ri.w, g, nsum, esum);
+        if (d > 0) ring_grad_fast(mv, P, K, row, d, xi, ri.w, g, nsum, esum);
 #endif
     }
     // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
@@ -808,6 +865,23 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
             *(reinterpret_cast<double2*>(q) + 1) = make_double2(xn[2], ri.w);
         }
     }
+}
+
+// Open meshes only (launched when the connectivity has boundary half-edges): adds the reference's
+// boundary-spoke terms to the finished gradient rows, so that the closed-mesh sweep carries none of it.
+__global__ void k_grad_boundary(MeshView mv, DevParams P, const double* __restrict__ sums, double* __restrict__ grad,
+                                SweepRange R) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= R.count) return;
+    const int i = R.first + t;
+    const R8 row = ldrow(mv.ring8, i);
+    if (!(row.v[0] == TM_RING_GENERIC || row_has_boundary_spoke(row))) return;
+    const double fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
+    const P4 ri = ldrec(mv.pos, i);
+    d3 g = mk3(0, 0, 0);
+    boundary_spoke_terms(mv, fC, P.kappa_b, i, mk3(ri.x, ri.y, ri.z), ri.w, g);
+    double* o = grad + 3 * (size_t)i;
+    o[0] += g.x; o[1] += g.y; o[2] += g.z;
 }
 
 }  // namespace
@@ -849,7 +923,7 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
     }
 #define TM_PAIRS2(E, F, W, R2, CL) k_pairs<E, F, W, R2, CL><<<nb, PAIR_THREADS, qbytes, st>>>( \
         mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
-#define TM_PAIRS(E, F, W, R2) do { if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)
+#define TM_PAIRS(E, F, W, R2) do { if (nb <= 0) break; if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
     else if (with_e)  { if (r2) TM_PAIRS(true, true, false, true); else TM_PAIRS(true, true, false, false); }
@@ -903,7 +977,9 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     }
     if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps, true)) return 1;
     if (pairs_for_grad && launch_pairs(m, nl, p, false, false, 0, true)) return 1;
-    if (write_vprops) {
+    if (nb <= 0) {
+        // a rank of a tiny partitioned mesh may own nothing: it still takes part in the reduction / exchange
+    } else if (write_vprops) {
         k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq, R);
     } else if (full) {
         k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
@@ -950,10 +1026,15 @@ int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p, cons
     memset(&U, 0, sizeof(U));
     if (fuse) U = *fuse;
     const double* frc = pairs ? m->frep : nullptr;
+    if (R.count <= 0) { m->grad_epoch = m->pos_epoch; return 0; }       // a rank of a tiny partitioned mesh may own nothing
     if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
     else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
     else k_grad<0><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
     TM_LAUNCHED();
+    if (m->has_boundary) {
+        // (callers do not fuse the update into the sweep on such meshes: U.mode == 0)
+        k_grad_boundary<<<(R.count + 127) / 128, 128, 0, m->stream>>>(m->view(), P, m->sums, m->grad, R); TM_LAUNCHED();
+    }
     TM_CUDA(cudaGetLastError());
     m->grad_epoch = m->pos_epoch;
     return 0;
@@ -976,6 +1057,9 @@ int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_par
     memset(&U, 0, sizeof(U));
     k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(m->view(), tm_to_dev(p), m->sums, pairs ? m->frep : nullptr, m->grad, R, U);
     TM_LAUNCHED();
+    if (m->has_boundary) {
+        k_grad_boundary<<<(m->V + 127) / 128, 128, 0, st>>>(m->view(), tm_to_dev(p), m->sums, m->grad, R); TM_LAUNCHED();
+    }
     k_export_grad<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, m->grad, m->d2h, m->xout3); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     TM_CUDA(cudaMemcpyAsync(grad_host, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, st));
@@ -990,7 +1074,7 @@ int tm_preload_energy() {
     TM_PRELOAD((k_pairs<false, true, false, true, CL>)); TM_PRELOAD((k_pairs<false, true, false, false, CL>))
     TM_PL(false); TM_PL(true);
 #undef TM_PL
-    TM_PRELOAD(k_cell_gather); TM_PRELOAD(k_export_grad);
+    TM_PRELOAD(k_cell_gather); TM_PRELOAD(k_export_grad); TM_PRELOAD(k_grad_boundary);
     TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad<0>); TM_PRELOAD(k_grad<1>); TM_PRELOAD(k_grad<2>);
     return 0;
 }

@@ -168,13 +168,13 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
     const int nb = (R.count + NT - 1) / NT;
     if (n_steps > 0) {
         if (tm_part_before_update(m)) return 1;
-        k_vv_update<false, true><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad, m->grad, dt, dt2, mass);
+        if (nb > 0) k_vv_update<false, true><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad, m->grad, dt, dt2, mass);
         TM_LAUNCHED();
     }
     // Steps. On an unpartitioned mesh the update rides in the gradient sweep's epilogue: the sweep of step n
     // gathers x_n from `pos` and writes x_{n+1} into `pos_alt`, then the two arrays swap roles (a partitioned
     // mesh keeps ONE array, which its peers have mapped, and runs the separate update kernel).
-    const bool fused = m->part == nullptr;
+    const bool fused = m->part == nullptr && !m->has_boundary;   // (open meshes: the boundary terms follow the sweep)
     for (int n = 1; n <= n_steps; n++) {
         m->pos_epoch++;
         if (tm_part_positions_updated(m)) return 1;
@@ -191,7 +191,9 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
             continue;
         }
         if (tm_launch_grad(m, nl, p)) return 1;
-        if (last) {
+        if (nb <= 0) {
+            if (!last && tm_part_before_update(m)) return 1;
+        } else if (last) {
             k_vv_update<true, false><<<nb, NT, 0, m->stream>>>(R, m->pos, m->mom, m->grad_prev, m->grad, dt, dt2, mass);
         } else {
             if (tm_part_before_update(m)) return 1;
@@ -323,7 +325,7 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
         m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r; m->frep_list = nl.serial;
     }
     if (n_steps & 1) std::swap(m->grad, m->grad_prev);
-    if ((n_steps - 1) & 1) std::swap(m->pos, m->pos_alt);      // fused steps ping-pong the record arrays
+    if (!m->has_boundary && ((n_steps - 1) & 1)) std::swap(m->pos, m->pos_alt);   // fused steps ping-pong the record arrays
     return 0;
 }
 
@@ -341,7 +343,7 @@ int tm_import_momenta(tm_mesh* m, const double* p_host) {
 int tm_export_vec3_owned(tm_mesh* m, const double* dev, double* host) {
     const SweepRange R = tm_owned_range(m);
     if (R.count < m->V) TM_CUDA(cudaMemsetAsync(m->xout3, 0, sizeof(double) * 3 * (size_t)m->V, m->stream));
-    k_export_vec3_range<<<(R.count + NT - 1) / NT, NT, 0, m->stream>>>(R, dev, m->d2h, m->xout3); TM_LAUNCHED();
+    if (R.count > 0) { k_export_vec3_range<<<(R.count + NT - 1) / NT, NT, 0, m->stream>>>(R, dev, m->d2h, m->xout3); TM_LAUNCHED(); }
     TM_CUDA(cudaGetLastError());
     if (tm_part_quiesce(m)) return 1;
     TM_CUDA(cudaMemcpyAsync(host, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, m->stream));

@@ -491,8 +491,9 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
         nl->row_cap = cap;
         nl->row_j = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)cap * 32 * ((V + 31) / 32));
         TM_CHECK(nl->row_j, "out of device memory for verlet rows of width %d", cap);
-        k_verlet_search2<<<(R.count + VS_THREADS - 1) / VS_THREADS, VS_THREADS, 0, m->stream>>>(
-            m->view(), g, start.p, rec.p, nl->excl, s2max, cap, nl->row_j, nl->row_cnt, maxcnt.p, R);
+        if (R.count > 0)
+            k_verlet_search2<<<(R.count + VS_THREADS - 1) / VS_THREADS, VS_THREADS, 0, m->stream>>>(
+                m->view(), g, start.p, rec.p, nl->excl, s2max, cap, nl->row_j, nl->row_cnt, maxcnt.p, R);
         TM_LAUNCHED();
         TM_CUDA(cudaGetLastError());
         int widest = 0;
