@@ -252,6 +252,25 @@ def open_mesh_cases():
         out[f"{name}_props"] = cases.props6(es.properties(mesh))
         out[f"{name}_energy"] = es.energy(mesh)
         out[f"{name}_grad"] = es.gradient(mesh)
+    # every half-edge primitive (scalars and gradients, bindings.cpp:249-407) of the small open meshes,
+    # boundary half-edges included: the reference evaluates them on the boundary loop's sectors
+    for name in ("rect", "fan"):
+        v, f = cases.open_mesh(name)
+        mesh = ref.TriMesh(v, f)
+        nh = 2 * mesh.n_edges()
+        geo = np.zeros((nh, 40))
+        bnd = np.zeros(nh, bool)
+        arrs = refprobe.halfedge_arrays(mesh)
+        for h in range(nh):
+            e = mesh.halfedge_handle(h)
+            bnd[h] = arrs[2][h] < 0 or arrs[2][h ^ 1] < 0
+            geo[h, 0:4] = [ref.edge_length(mesh, e), ref.face_area(mesh, e), ref.face_volume(mesh, e), ref.dihedral_angle(mesh, e)]
+            geo[h, 4:10] = ref.edge_length_grad(mesh, e).ravel()
+            geo[h, 10:19] = ref.face_area_grad(mesh, e).ravel()
+            geo[h, 19:28] = ref.face_volume_grad(mesh, e).ravel()
+            geo[h, 28:40] = ref.dihedral_angle_grad(mesh, e).ravel()
+        out[f"{name}_geometry"] = geo
+        out[f"{name}_on_boundary_edge"] = bnd
     save("open_meshes", **out)
 
 

@@ -38,3 +38,23 @@ def test_every_halfedge_of_a_rough_sphere(gpu_core):
     geo = np.array([cm.halfedge_geometry(h) for h in range(len(he_to))])
     scale = np.abs(gold).max(axis=0) + 1e-300
     assert np.max(np.abs(geo - gold) / scale) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["rect", "fan"])
+def test_every_halfedge_of_open_meshes(gpu_core, name):
+    """Every half-edge of open meshes, boundary half-edges included, against the reference build: the
+    reference evaluates those on the boundary loop's sectors as OpenMesh defines them (prev / next along
+    the loop, sector angles signed against the face across the edge)."""
+    from trimem_b200 import cabi
+    gold = cases.load_golden("open_meshes")
+    want, on_b = gold[f"{name}_geometry"], gold[f"{name}_on_boundary_edge"]
+    v, f = cases.open_mesh(name)
+    mesh = gpu_core.TriMesh(v, f)
+    he_to, he_next, he_face, v_he, _ = mesh.halfedge_arrays()
+    cm = cabi.Mesh(he_to, he_next, he_face, v_he, xyz=v)
+    geo = np.array([cm.halfedge_geometry(h) for h in range(len(he_to))])
+    scale = np.abs(want).max(axis=0) + 1e-300
+    err = np.abs(geo - want) / scale
+    assert np.max(err[~on_b]) < 1e-10
+    worst = err[on_b].max(axis=0)
+    assert np.max(err[on_b]) < 1e-10, np.nonzero(worst > 1e-10)[0].tolist()

@@ -220,3 +220,13 @@ def test_port_open_meshes_vs_reference(port, name):
     assert abs(pe.energy(pm) - float(gold[f"{name}_energy"])) <= 1e-12 * abs(float(gold[f"{name}_energy"]))
     g = pe.gradient(pm)
     assert np.linalg.norm(g - gold[f"{name}_grad"]) <= 1e-12 * np.linalg.norm(gold[f"{name}_grad"])
+
+
+@pytest.mark.parametrize("name", ["rect", "fan"])
+def test_port_primitives_on_open_meshes(port, name):
+    """Half-edge primitives of open meshes, boundary half-edges included (boundary-loop sectors)."""
+    gold = cases.load_golden("open_meshes")
+    v, f = cases.open_mesh(name)
+    pm = port.TriMesh(v, f)
+    geo = np.array([pm.halfedge_geometry(h) for h in range(2 * pm.n_edges())])
+    assert np.allclose(geo, gold[f"{name}_geometry"], rtol=1e-12, atol=1e-13)

@@ -79,7 +79,14 @@ __global__ void k_halfedge_geometry(MeshView mv, int h, double* __restrict__ out
     const d3 u0 = (1.0 / ln0) * n0;
     out[1] = 0.5 * ln0;
     st3(out + 10, 0.5 * cross3(u0, xk - xj));
-    st3(out + 13, 0.5 * cross3(u0, xi - xk));
+    // edge_vector(prev h): k -> i in a triangle; on a boundary half-edge the loop's previous half-edge u -> i
+    d3 e_prev = xi - xk;
+    if (mv.he_face[h] < 0) {
+        int q = h;
+        while (mv.he_next[q] != h) q = mv.he_next[q];
+        e_prev = xi - ldpos(mv.pos, mv.he_to[q ^ 1]);
+    }
+    st3(out + 13, 0.5 * cross3(u0, e_prev));
     st3(out + 16, 0.5 * cross3(u0, xj - xi));
 
     // volume (mesh_util.h:94-128)
@@ -97,10 +104,39 @@ __global__ void k_halfedge_geometry(MeshView mv, int h, double* __restrict__ out
     if (!boundary && ln0 * ln1 != 0.0)
         theta = atan2(dot3(cross3(n0, n1), e) / l, dot3(n0, n1));
     out[3] = theta;
-    const double cot01 = dot3(xj - xi, xk - xi) / ln0;   // angle at i in face (i,j,k)
-    const double cot03 = dot3(xk - xj, xi - xj) / ln0;   // angle at j in face (i,j,k)
-    const double cot02 = dot3(xm - xi, xj - xi) / ln1;   // angle at i in face (j,i,m)
-    const double cot04 = dot3(xi - xj, xm - xj) / ln1;   // angle at j in face (j,i,m)
+    double cot01 = dot3(xj - xi, xk - xi) / ln0;   // a01: angle at i in face (i,j,k)
+    double cot03 = dot3(xk - xj, xi - xj) / ln0;   // a03: angle at j in face (i,j,k)
+    double cot02 = dot3(xm - xi, xj - xi) / ln1;   // a02: angle at i in face (j,i,m)
+    double cot04 = dot3(xi - xj, xm - xj) / ln1;   // a04: angle at j in face (j,i,m)
+    // Boundary edges. The reference evaluates the four sector angles through OpenMesh, whose sectors of a
+    // boundary half-edge b run along the boundary loop: calc_sector_angle(b) is the angle between
+    // next(b) and opposite(b), signed against the normal of the face across the edge, and prev(b) is the
+    // loop's previous half-edge (mesh_util.h:135-185). With b the boundary side of the
+    // edge, c = its boundary predecessor u -> from(b), f the face normal across b, g the one across c:
+    auto signed_cot = [](d3 v0, d3 v1, d3 fn) {
+        const d3 cr = cross3(v0, v1);
+        const double sn = sqrt(dot3(cr, cr));
+        const double c = sn > 0.0 ? dot3(v0, v1) / sn : 0.0;
+        return dot3(cr, fn) >= 0.0 ? c : -c;
+    };
+    auto loop_prev = [&](int b) { int q = b; while (mv.he_next[q] != b) q = mv.he_next[q]; return q; };
+    if (mv.he_face[o] < 0 && mv.he_face[h] >= 0) {
+        // b = o (j -> i): sector of o = (i -> m, i -> j) -> a02; sector of c = (u -> j): (j -> i, j -> u) -> a04
+        cot02 = signed_cot(xm - xi, xj - xi, n0);
+        const int c = loop_prev(o), u = mv.he_to[c ^ 1];
+        const d3 xu = ldpos(mv.pos, u);
+        const int cf = c ^ 1;                                           // j -> u, has the face (j, u, q)
+        const d3 xq = ldpos(mv.pos, mv.he_to[mv.he_next[cf]]);
+        cot04 = signed_cot(xi - xj, xu - xj, cross3(xq - xu, xj - xu));
+    } else if (mv.he_face[h] < 0 && mv.he_face[o] >= 0) {
+        // b = h (i -> j): sector of h = (j -> k, j -> i) -> a03; sector of c = (u -> i): (i -> j, i -> u) -> a01
+        cot03 = signed_cot(xk - xj, xi - xj, n1);
+        const int c = loop_prev(h), u = mv.he_to[c ^ 1];
+        const d3 xu = ldpos(mv.pos, u);
+        const int cf = c ^ 1;                                           // i -> u, has the face (i, u, q)
+        const d3 xq = ldpos(mv.pos, mv.he_to[mv.he_next[cf]]);
+        cot01 = signed_cot(xj - xi, xu - xi, cross3(xq - xu, xi - xu));
+    }
     const double il = 1.0 / l;
     st3(out + 28, il * (cot03 * u0 + cot04 * u1));
     st3(out + 31, il * (cot01 * u0 + cot02 * u1));
