@@ -43,6 +43,8 @@ N_SAMPLED_ROWS = 512
 
 def mesh_of(case):
     gen, args, _ = CASES[case]
+    if gen.startswith("open:"):
+        return open_mesh(gen[5:])
     return getattr(meshgen, gen)(*args)
 
 
@@ -75,6 +77,8 @@ FLIP_CASES = {
     "flip_ico3_k1": ("ico3_flip", 960, 1),
     "flip_ico4_cell": ("ico4_flip_cell", 768, 2),
     "flip_ico4_verlet": ("ico4_flip_verlet", 768, 3),
+    # an open mesh: proposals on boundary edges, patches that contain boundary vertices
+    "flip_rect_open": ("rect_flip", 600, 4),
 }
 CASES.update({
     # reference tests/test_flips.py configuration
@@ -83,13 +87,16 @@ CASES.update({
                                                         n_search="cell-list", exclusion=2)),
     "ico4_flip_verlet": ("jittered_icosphere", (4,), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="stress",
                                                           n_search="verlet-list", exclusion=2)),
+    "rect_flip": ("open:rect", (), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="physical", n_search="cell-list",
+                                        exclusion=2)),
 })
 
 
 def flip_inputs(name):
     case, n, seed = FLIP_CASES[name]
     v, f = mesh_of(case)
-    n_edges = 3 * len(v) - 6
+    e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]), axis=1)
+    n_edges = len(np.unique(e[:, 0].astype(np.int64) * len(v) + e[:, 1]))      # = 3V - 6 on a closed sphere
     rng = np.random.default_rng(seed)
     return case, rng.integers(0, n_edges, n).astype(np.int32), rng.random(n)
 
@@ -101,6 +108,8 @@ VV_CASES = {
     "vv_ico4_stress_verlet2": ("ico4_stress_verlet2", 12, 1.0, 1.0, 2.5e-5, 10),
     "vv_ico4_stress_cell2": ("ico4_stress_cell2", 13, 2.0, 2.0, 2.0e-5, 6),
     "vv_ico3_area": ("ico3_area", 14, 1.0, 1.0, 1.0e-3, 8),
+    # an open mesh: the gradient's boundary terms, the update as a kernel of its own
+    "vv_rect_open": ("rect_flip", 15, 0.2, 1.0, 4.0e-4, 8),
 }
 
 
