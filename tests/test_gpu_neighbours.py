@@ -96,6 +96,17 @@ def test_stale_cells_live_exclusions_after_motion(gpu_core, port):
     pnl = port.NeighbourList(pm, "cell-list", ep.repulse_params.rlist, 1)
     _, jp = pnl.point_distances(pm, 17, ep.repulse_params.lc1)
     assert sorted(jd) == sorted(jp.tolist())
+    # the same with exclusion level 2 (sorted two-ring rows in the sweep), energy and gradient
+    ep2 = workload.energy_params(gpu_core, mesh, repulsion="stress", n_search="cell-list", exclusion=2)
+    np.copyto(mesh.points(), v)
+    pm.x[:] = v
+    es2 = gpu_core.EnergyManager(mesh, ep2)
+    pe2 = port.EnergyManager(pm, port.params_from(ep2))
+    np.copyto(mesh.points(), v + dx)
+    pm.x[:] = v + dx
+    assert abs(es2.energy(mesh) - pe2.energy(pm)) <= 1e-10 * abs(pe2.energy(pm))
+    g, gp = es2.gradient(mesh), pe2.gradient(pm)
+    assert np.linalg.norm(g - gp) <= 1e-10 * np.linalg.norm(gp)
 
 
 def test_errors(gpu_core):
