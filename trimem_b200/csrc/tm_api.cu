@@ -129,7 +129,7 @@ int fetch_sums(tm_mesh* m, double out[6]) {
 extern "C" {
 
 const char* tm_last_error(void) { return g_err; }
-int tm_abi_version(void) { return 1; }
+int tm_abi_version(void) { return 2; }
 
 int tm_device_count(void) {
     int n = 0;
