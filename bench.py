@@ -367,7 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--subdiv", type=int, default=8, help="icosphere subdivisions (8 = 655,362 vertices, the headline)")
-    ap.add_argument("--cpu-steps", type=int, default=3, help="E+G evaluations of the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=20, help="E+G evaluations of the bounded cpu_baseline sample (~10 s of host work with the setup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--part-subdiv", type=int, default=10,
                     help="icosphere subdivisions of the ONE mesh partitioned across the ranks (BASELINE config 4: 10 = "
