@@ -213,3 +213,37 @@ def test_partitioned_open_and_irregular_meshes(gpu_core, port, gen, nranks):
     assert abs(out[0][0] - e1) <= 1e-13 * abs(e1)
     g = np.sum([o[1] for o in out], axis=0)
     assert nrm(g, g1) < 1e-13
+
+
+def test_replicated_flip_sweep_on_partitioned_mesh(gpu_core):
+    """Flip sweeps are not partitioned: every rank runs the same sweep over the whole (replicated) mesh after
+    bringing all positions up to date. Same proposals -> the same flips on every rank and the flips of an
+    unpartitioned sweep; the next partitioned evaluation rebuilds its halo lists for the new connectivity."""
+    name = "flip_ico4_cell"
+    gold = cases.load_golden(name)
+    case, edges, u = cases.flip_inputs(name)
+    R = Ranks(gpu_core, case, 2)
+    # move the vertices on the device first, so that the far field of each rank is stale before the sweep
+    p0 = 0.05 * np.random.default_rng(1).normal(size=R.v.shape)
+    R.each(lambda m, nl: m.set_momenta(p0))
+    R.each(lambda m, nl: m.vv_integrate_async(nl, R.par, 1.0, 1.0e-5, 3, with_energies=False))
+    props0 = R.each(lambda m, nl: m.properties(nl, R.par))
+    assert np.array_equal(props0[0], props0[1])
+    out = R.each(lambda m, nl: m.flip_sweep(nl, R.par, cabi.FLIP_SERIAL, edges, u, props0[0]))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+    topo = R.each(lambda m, nl: m.topology())
+    for a, b in zip(topo[0], topo[1]):
+        assert np.array_equal(a, b)
+    # the same sweep on one device from the same positions
+    x = R.cm[0].positions()
+    one = cabi.Mesh(*R.mesh.halfedge_arrays()[:4], xyz=x)
+    rp = R.es.eparams.repulse_params
+    nl1 = cabi.NList(one, cabi.NLIST_CELL, rp.rlist, rp.exclusion_level)
+    nacc1, flips1, props1 = one.flip_sweep(nl1, R.par, cabi.FLIP_SERIAL, edges, u, one.properties(nl1, R.par))
+    assert nacc1 == out[0][0] and np.array_equal(flips1, out[0][1])
+    # evaluation after the sweep: halo lists follow the new connectivity (prepared locally first: with the
+    # ranks sharing one device, a rank still rebuilding its tables must not meet a peer that already waits)
+    for m, nl in zip(R.cm, R.nl):
+        m.part_prepare(nl)
+    e = R.each(lambda m, nl: m.energy(nl, R.par)[0])
+    assert e[0] == e[1] and abs(e[0] - one.energy(nl1, R.par)[0]) <= 1e-12 * abs(e[0])

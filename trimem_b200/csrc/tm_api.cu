@@ -199,7 +199,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
     cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt); cudaFree(m->ring8);
     cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
-    cudaFree(m->pos); cudaFree(m->pos_alt); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); cudaFree(m->ex2_v);
+    cudaFree(m->pos); cudaFree(m->pos_alt); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); tm_pool_free(m->device, m->ex2_v);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
     cudaFree(m->flush);
     tm_part_release(m);

@@ -382,6 +382,7 @@ int check(tm_mesh* m, const tm_energy_params* p) {
     TM_CHECK(p != nullptr, "null parameter block");
     TM_CHECK(p->bond_type == TM_BOND_EDGE || p->bond_type == TM_BOND_AREA, "Unknown bond potential");
     TM_CUDA(cudaSetDevice(m->device));
+    if (tm_join_pairs(m)) return 1;
     return tm_ensure_layout(m);
 }
 
@@ -418,6 +419,9 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     TM_CHECK(!nl || nl->kind != TM_NLIST_VERLET || nl->rows_count == m->V,
              "flip sweeps read the rows of arbitrary vertices: this verlet list holds a partition's slice only "
              "(use a cell list, or a list built before tm_part_create)");
+    // partitioned mesh: the sweep runs replicated on every rank over the whole mesh (same proposals, same
+    // decisions, same connectivity everywhere), so every rank first needs every position (collective)
+    if (tm_part_make_current(m)) return 1;
     FlipWS* ws = (FlipWS*)m->flipws;
     cudaStream_t st = m->stream;
     const DevParams P = tm_to_dev(*p);

@@ -451,6 +451,7 @@ int tm_part_prepare(tm_mesh* m, tm_nlist* nl) {
     TM_CUDA(cudaSetDevice(m->device));
     if (tm_ensure_layout(m) || tm_check_nlist(m, nl)) return 1;
     if (tm_part_refresh(m, nl ? nl->view() : tm_no_nlist())) return 1;
+    if (nl && nl->kind == TM_NLIST_CELL && nl->excl == 2 && tm_ensure_ring2(m)) return 1;   // the cell sweep's exclusion rows
     if (tm_preload_energy() || tm_preload_integrate() || tm_preload_layout()) return 1;
     TM_PRELOAD(k_publish_pos); TM_PRELOAD(k_wait_pos); TM_PRELOAD(k_ack); TM_PRELOAD(k_wait_acks);
     TM_PRELOAD(k_pull); TM_PRELOAD(k_exchange_sums); TM_PRELOAD(k_store6);

@@ -235,8 +235,11 @@ int tm_ensure_ring2(tm_mesh* m) {
     long long total = 0;
     if (tm_exclusive_scan(m, m->ex2_off, m->ex2_off, V, &total)) return 1;   // syncs the stream
     TM_CHECK(herr == 0, "a vertex has more than %d vertices within two rings", RING2_CAP);
-    if (m->ex2_v) { cudaFree(m->ex2_v); m->ex2_v = nullptr; }
-    TM_CUDA(cudaMalloc(&m->ex2_v, sizeof(int) * (size_t)(total > 0 ? total : 1)));
+    // from the block cache: rebuilt after every flip sweep, and cudaFree would synchronise the whole device
+    // (the stream is idle here: the scan above waited for it)
+    if (m->ex2_v) { tm_pool_free(m->device, m->ex2_v); m->ex2_v = nullptr; }
+    m->ex2_v = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)(total > 0 ? total : 1));
+    TM_CHECK(m->ex2_v != nullptr, "out of device memory for the two-ring rows");
     k_ring2_fill<<<nb, 128, 0, m->stream>>>(V, m->ring_off, m->ring_v, m->ex2_off, m->ex2_v); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     m->ex2_epoch = m->topo_epoch;
