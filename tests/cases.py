@@ -161,12 +161,14 @@ def open_mesh(name):
     return fan_mesh()
 
 
-def open_mesh_params(mod, mesh):
+def open_mesh_params(mod, mesh, bond="Edge"):
     ep = mod.EnergyParams()
     ep.kappa_b, ep.kappa_a, ep.kappa_v, ep.kappa_c, ep.kappa_t, ep.kappa_r = 3.0, 2.0, 1.5, 1.0, 0.5, 0.7
     a, l = mod.avg_tri_props(mesh)
     bp = ep.bond_params
     bp.lc0, bp.lc1, bp.a0 = 1.05 * l, 0.95 * l, a
+    if bond != "Edge":
+        bp.type = getattr(mod.BondType, bond)
     ep.bond_params = bp
     rp = ep.repulse_params
     rp.lc1, rp.rlist, rp.exclusion_level, rp.n_search = 2.2 * l, 2.5 * l, 1, "verlet-list"

@@ -252,6 +252,12 @@ def open_mesh_cases():
         out[f"{name}_props"] = cases.props6(es.properties(mesh))
         out[f"{name}_energy"] = es.energy(mesh)
         out[f"{name}_grad"] = es.gradient(mesh)
+    # the harmonic area bond on an open mesh
+    v, f = cases.open_mesh("rect")
+    mesh = ref.TriMesh(v, f)
+    es = ref.EnergyManager(mesh, cases.open_mesh_params(ref, mesh, bond="Area"))
+    out["rect_area_energy"] = es.energy(mesh)
+    out["rect_area_grad"] = es.gradient(mesh)
     # every half-edge primitive (scalars and gradients, bindings.cpp:249-407) of the small open meshes,
     # boundary half-edges included: the reference evaluates them on the boundary loop's sectors
     for name in ("rect", "fan"):

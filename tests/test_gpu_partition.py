@@ -247,3 +247,13 @@ def test_replicated_flip_sweep_on_partitioned_mesh(gpu_core):
         m.part_prepare(nl)
     e = R.each(lambda m, nl: m.energy(nl, R.par)[0])
     assert e[0] == e[1] and abs(e[0] - one.energy(nl1, R.par)[0]) <= 1e-12 * abs(e[0])
+
+
+def test_open_mesh_area_bond(gpu_core):
+    gold = cases.load_golden("open_meshes")
+    v, f = cases.open_mesh("rect")
+    mesh = gpu_core.TriMesh(v, f)
+    es = gpu_core.EnergyManager(mesh, cases.open_mesh_params(gpu_core, mesh, bond="Area"))
+    e, g = es.energy(mesh), es.gradient(mesh)
+    assert abs(e - float(gold["rect_area_energy"])) <= TOL * abs(e)
+    assert nrm(g, gold["rect_area_grad"]) < 1e-9
