@@ -92,6 +92,15 @@ CASES.update({
 })
 
 
+# sweep-level flip statistics against the reference (tests/golden/make_golden.py flip_statistics):
+# small mesh: (independent chains, sweeps per chain, flip_ratio); large mesh: (sweeps, flip_ratio,
+# [(function, OpenMP threads, chains)])
+FLIPSTAT_SMALL = (240, 30, 0.1)
+FLIPSTAT_LARGE = (100, 0.1, [("flip", 1, 2), ("pflip", 8, 3)])
+CASES["ico6_flip"] = ("jittered_icosphere", (6,), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="physical",
+                                                       n_search="cell-list", exclusion=2))
+
+
 def flip_inputs(name):
     case, n, seed = FLIP_CASES[name]
     v, f = mesh_of(case)

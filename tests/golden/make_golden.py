@@ -295,6 +295,55 @@ def thread_spread():
     save("thread_spread", energy=np.array([res[1][0], res[8][0]]), grad_norm=np.array([res[1][1], res[8][1]]))
 
 
+def flip_statistics():
+    """Sweep-level statistics of the reference's flip / pflip (flips.cpp:22-165; clock-seeded, so distributions
+    rather than sequences): acceptance counts and energies of independent chains of sweeps at fixed vertex
+    positions. Two sizes:
+      * ico3_flip (642 vertices, reference tests/test_flips.py parameters): FLIPSTAT_SMALL chains of sweeps,
+        every chain from the initial mesh; per chain the accepted flips of each sweep and the energy after each.
+      * ico6_flip (40,962 vertices, config 2's physical variant, all kappa = 1): a few chains of 100 sweeps.
+    pflip runs with ONE OpenMP thread here for the small mesh: its conflict handling drops proposals whose patch
+    is locked by another thread (flips.cpp:118-124), so its acceptance COUNT depends on the thread count; with one
+    thread it is the same Markov kernel as flip. The large mesh also records pflip at 8 threads (a conflict there
+    has probability ~0.2 % per proposal)."""
+    import subprocess
+    chains, sweeps, ratio = cases.FLIPSTAT_SMALL
+    out = {}
+    for fn in ("flip", "pflip"):
+        acc = np.zeros((chains, sweeps), np.int32)
+        ener = np.zeros((chains, sweeps))
+        for c in range(chains):
+            mesh, es = cases.build(ref, "ico3_flip")
+            for s in range(sweeps):
+                acc[c, s] = getattr(ref, fn)(mesh, es, ratio)
+                ener[c, s] = es.energy(mesh)
+        out[f"small_{fn}_acc"], out[f"small_{fn}_energy"] = acc, ener
+        print(fn, "small: mean acc/sweep", acc[:, sweeps // 3:].mean(), "final energy", ener[:, -1].mean(), ener[:, -1].std())
+    mesh, es = cases.build(ref, "ico3_flip")
+    out["small_energy0"] = es.energy(mesh)
+    out["small_n_edges"] = mesh.n_edges()
+    # large mesh: separate processes (thread count per run)
+    code = ("import sys,os;sys.path.insert(0,%r);sys.path.insert(0,%r);sys.path.insert(0,%r);"
+            "import trimem.core as ref,cases,numpy as np;m,e=cases.build(ref,'ico6_flip');fn=getattr(ref,sys.argv[1]);"
+            "n=int(sys.argv[2]);r=float(sys.argv[3]);print(repr(e.energy(m)));\n"
+            "for s in range(n): a=fn(m,e,r);print(a,repr(e.energy(m)),flush=True)"
+            % (os.path.join(ROOT, "oracle", "_ref"), ROOT, os.path.join(ROOT, "tests")))
+    nsw, lratio, plan = cases.FLIPSTAT_LARGE
+    for fn, threads, nchains in plan:
+        accs, eners = [], []
+        procs = [subprocess.Popen([sys.executable, "-c", code, fn, str(nsw), str(lratio)], text=True, stdout=subprocess.PIPE,
+                                  env=dict(os.environ, OMP_NUM_THREADS=str(threads))) for _ in range(nchains)]
+        for pr in procs:
+            lines = pr.communicate()[0].split("\n")
+            out["large_energy0"] = float(lines[0])
+            rows = [l.split() for l in lines[1:] if l.strip()]
+            accs.append([int(r[0]) for r in rows]); eners.append([float(r[1]) for r in rows])
+        out[f"large_{fn}{threads}_acc"] = np.array(accs, np.int32)
+        out[f"large_{fn}{threads}_energy"] = np.array(eners)
+        print(fn, threads, "large: acc/sweep", np.mean(accs), "energy after", nsw, "sweeps", [e[-1] for e in eners])
+    save("flip_statistics", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc", "open"]
     if "topology" in which: topology_cases()
@@ -307,3 +356,4 @@ if __name__ == "__main__":
     if "trajectory" in which: trajectory_cases()
     if "hmc" in which: hmc_chain_cases()
     if "open" in which: open_mesh_cases()
+    if "flipstats" in which: flip_statistics()

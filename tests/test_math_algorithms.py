@@ -5,38 +5,38 @@ import numpy as np
 
 ATAN_C = np.array([5.8823529411764705e-02, -6.6666666666666666e-02, 7.6923076923076927e-02, -9.0909090909090912e-02,
                    1.1111111111111111e-01, -1.4285714285714285e-01, 2.0e-01, -3.3333333333333331e-01])
-AK = np.array([0.0, 0.24497866312686414, 0.46364760900080615, 0.6435011087932844, 0.7853981633974483])
+ATAN_T = np.array([
+    [0.0, 0.24497866312686414, 0.46364760900080615, 0.6435011087932844, 0.7853981633974483],
+    [1.5707963267948966, 1.3258176636680326, 1.1071487177940904, 0.9272952180016122, 0.7853981633974483],
+    [3.141592653589793, 2.896613990462929, 2.677945044588987, 2.498091544796509, 2.356194490192345],
+    [1.5707963267948966, 1.8157749899217608, 2.0344439357957027, 2.214297435588181, 2.356194490192345]])
 
 
 def rcp_newton(x, seed):
-    r = seed
-    for _ in range(2):
-        e = 1.0 - x * r            # fma(-x, r, 1)
-        r = r + r * e              # fma(r, e, r)
-    return r
+    """rcp_pos (tm_common.cuh): one third-order step on a 2^-20 seed"""
+    e = 1.0 - x * seed             # fma(-x, r, 1)
+    return seed + seed * (e + e * e)
 
 
 def atan2_fast(y, x, rng):
     ax, ay = np.abs(x), np.abs(y)
     swap = ay > ax
-    mx, mn = np.where(swap, ay, ax), np.where(swap, ax, ay)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        # MUFU.RCP64H: a ~20-bit reciprocal seed (modelled as the exact reciprocal with a 2^-20 relative error)
-        seed = (1.0 / mx) * (1.0 + rng.uniform(-1, 1, size=mx.shape) * 2.0 ** -20)
-        M = 1688849860263936.0
-        t = mn * seed + M
-        c = t - M
-        k = np.clip(np.rint(4.0 * c).astype(int), 0, 4)
-        den = mx + c * mn
-        r = (mn - c * mx) * rcp_newton(den, (1.0 / den) * (1.0 + rng.uniform(-1, 1, size=mx.shape) * 2.0 ** -20))
-        s = r * r
-        p = np.full_like(s, ATAN_C[0])
-        for coef in ATAN_C[1:]:
-            p = p * s + coef
-        a = r * s * p + r + AK[k]
-    a = np.where(swap, 1.5707963267948966 - a, a)
-    a = np.where(np.signbit(x), 3.141592653589793 - a, a)
-    a = np.where(mx > 0.0, a, 0.0)
+    mx, mn = np.where(swap, ay, ax) + 1.0e-300, np.where(swap, ax, ay)
+    # MUFU.RCP64H: a ~20-bit reciprocal seed (modelled as the exact reciprocal with a 2^-20 relative error)
+    seed = (1.0 / mx) * (1.0 + rng.uniform(-1, 1, size=mx.shape) * 2.0 ** -20)
+    M = 1688849860263936.0
+    t = mn * seed + M
+    c = t - M
+    k = np.clip(np.rint(4.0 * c).astype(int), 0, 4)
+    o = swap.astype(int) + 2 * np.signbit(x).astype(int)
+    den = mx + c * mn
+    r = (mn - c * mx) * rcp_newton(den, (1.0 / den) * (1.0 + rng.uniform(-1, 1, size=mx.shape) * 2.0 ** -20))
+    r = np.where((o == 1) | (o == 2), -r, r)
+    s = r * r
+    p = np.full_like(s, ATAN_C[0])
+    for coef in ATAN_C[1:]:
+        p = p * s + coef
+    a = (r * s * p + r) + ATAN_T[o, k]
     return np.copysign(a, y)
 
 
@@ -77,3 +77,16 @@ def test_exp_nonpos_algorithm_accuracy():
     got = np.ldexp(p, kd.astype(int))
     want = np.exp(t)
     assert np.max(np.abs(got - want) / want) < 4.0e-16
+
+
+def test_rsqrt_rcp_refinement_accuracy():
+    """One cubic step on a seed of relative error <= 2^-20 (what MUFU delivers on B200, scripts/ubench/seed_accuracy.cu)."""
+    rng = np.random.default_rng(2)
+    x = 10.0 ** rng.uniform(-30, 30, 400000)
+    err = (1.0 + rng.uniform(-1, 1, size=x.shape) * 2.0 ** -20)
+    r = rcp_newton(x, (1.0 / x) * err)
+    assert np.max(np.abs(r * x - 1.0)) < 5e-16
+    y = (1.0 / np.sqrt(x)) * err
+    e = 1.0 - (x * y) * y
+    y = y + (y * e) * (0.375 * e + 0.5)
+    assert np.max(np.abs(y * np.sqrt(x) - 1.0)) < 5e-16

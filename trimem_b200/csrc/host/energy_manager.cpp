@@ -206,8 +206,12 @@ int flip_sweep(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, lon
     std::vector<int> flipped(2 * (size_t)nflips);
     int nacc = 0, napplied = 0;
     if (tm_flip_sweep(dm, estore.nlist_handle(), &p, mode, nflips, edges.data(), u.data(), &nacc,
-                      &napplied, flipped.data(), props))
+                      &napplied, flipped.data(), props)) {
+        // the device may hold a half-finished sweep: the next device() call uploads this mesh's (pre-sweep)
+        // connectivity again, so host and device agree and the failed sweep is rolled back as a whole
+        mesh.invalidate_device_topology();
         fail();
+    }
     // replay every applied flip (trial flips and flip-backs) on the host mirror, in order
     for (int k = 0; k < napplied; k++) mesh.flip(flipped[k]);
     mesh.mark_device_in_sync();

@@ -77,6 +77,7 @@ public:
     // the device connectivity was mutated by a flip sweep and the host replayed the same
     // flips: mark both sides as in sync without a re-upload
     void mark_device_in_sync() { dev_topo_version_ = topo_version_; }
+    void invalidate_device_topology() { dev_topo_version_ = 0; }
 
 private:
     void set_next(int h, int n) { he_next_[h] = n; he_prev_[n] = h; }

@@ -198,6 +198,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     tm_flips_release(m);
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
     cudaFree(m->ring_off); cudaFree(m->ring_v); cudaFree(m->ring_cnt); cudaFree(m->ring8);
+    cudaFree(m->aux); tm_pool_free(m->device, m->gen_list);
     cudaFree(m->he_to_h); cudaFree(m->v_he_h); cudaFree(m->d2h); cudaFree(m->h2d);
     cudaFree(m->pos); cudaFree(m->pos_alt); cudaFree(m->xio3); cudaFree(m->xout3); cudaFree(m->vprops); cudaFree(m->grad); cudaFree(m->frep); cudaFree(m->ex2_off); tm_pool_free(m->device, m->ex2_v);
     cudaFree(m->partials); cudaFree(m->sums); cudaFree(m->ticket); cudaFree(m->scan_tmp);
@@ -229,6 +230,7 @@ int tm_mesh_set_topology(tm_mesh* m, int V, int HE, const int* he_to, const int*
             dev_alloc(&m->grad, 3 * (size_t)V))
             return 1;
         if (m->vprops) { cudaFree(m->vprops); m->vprops = nullptr; }
+        if (m->aux) { cudaFree(m->aux); m->aux = nullptr; }
         if (m->mom) { cudaFree(m->mom); m->mom = nullptr; }
         if (m->grad_prev) { cudaFree(m->grad_prev); m->grad_prev = nullptr; }
         m->grad_epoch = 0;
@@ -343,6 +345,8 @@ int tm_gradient_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
 
 int tm_fetch_energy(tm_mesh* m, const tm_energy_params* p, double* energy, double props[6]) {
     if (check_mesh(m, false) || check_params(p)) return 1;
+    TM_CHECK(m->sums_full, "the last property sweep was the gradient's geometry-only one (no tether / repulsion sums): "
+             "call tm_energy_async before tm_fetch_energy");
     double s[6];
     if (fetch_sums(m, s)) return 1;
     if (props) for (int q = 0; q < 6; q++) props[q] = s[q];
@@ -400,7 +404,7 @@ int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* gra
     // normal path runs. Saves the upload's 0.3 ms of the 0.7 ms call at 655,362 vertices.
     const NlView nv = view_of(nl);
     const bool spec = m->stage_pending && !m->part && m->perm_valid && m->topo_dev_valid && m->rings_valid &&
-                      m->geo_epoch == m->pos_epoch && tm_check_nlist(m, nl) == 0 &&
+                      m->geo_epoch == m->pos_epoch && (!props || m->sums_full) && tm_check_nlist(m, nl) == 0 &&
                       (!(p->rep_lc1 > 0.0 && p->kappa_r != 0.0) || tm_pair_force_valid(m, nv, *p));
     const unsigned long long epoch0 = m->pos_epoch;
     if (spec) {
@@ -416,6 +420,10 @@ int tm_gradient(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, double* gra
             return 0;
         }
     }
+    // `props` = all six reduced sums at the gradient's positions: the gradient's own property sweep is
+    // geometry-only (tether = repulsion = 0), so a request for them takes the full sweep instead
+    if (props && !(m->geo_epoch == m->pos_epoch && m->sums_full) &&
+        (tm_check_nlist(m, nl) || tm_launch_props(m, nv, *p, true, false))) return 1;
     if (tm_gradient_async(m, nl, p)) return 1;
     if (props) {
         if (tm_part_quiesce(m)) return 1;

@@ -36,17 +36,18 @@ extern thread_local unsigned long long tl_tm_launches;     // this thread (per-c
 constexpr int TM_RING_FACE  = 1 << 30;          // slot's outgoing half-edge has a face
 constexpr int TM_RING_OFACE = (int)0x80000000u;         // its opposite half-edge has a face
 constexpr int TM_RING_MASK  = (1 << 30) - 1;
-// fixed-width one-ring rows (R8): unused slots hold TM_RING_PAD; a vertex whose ring does not fit
-// (valence > 8) or is degenerate (valence < 3) has TM_RING_GENERIC in slot 0 and is evaluated
-// from the CSR row instead
+// fixed-width one-ring rows (R8) of the vertices with a CLOSED fan of valence 3..8 (every spoke has
+// a face on both sides): plain neighbour ids, unused slots hold TM_RING_PAD. Every other vertex
+// (valence > 8 or < 3, or on the boundary of an open mesh) has TM_RING_GENERIC in slot 0 and is
+// evaluated from the CSR row instead
 constexpr int TM_RING_PAD     = TM_RING_MASK;
 constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 // launch shapes of the two sweeps (overridable with -D for timing experiments, scripts/build_variant.py)
 #ifndef TM_PROPS_NT
-#define TM_PROPS_NT 64
+#define TM_PROPS_NT 128
 #endif
 #ifndef TM_GRAD_NT
-#define TM_GRAD_NT 64
+#define TM_GRAD_NT 128
 #endif
 // resident blocks per SM the register allocation aims at (measured on B200 at 655k vertices,
 // profiles/r01, r01g). With the ring records staged in shared memory the property sweep needs
@@ -55,10 +56,10 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 // 64-thread blocks at the same number of resident warps drain a little more evenly than 128-thread ones
 // (property sweep 54.6 -> 52.6 us, ring gradient 81.3 -> 78.9 us).
 #ifndef TM_PROPS_MINB
-#define TM_PROPS_MINB 12
+#define TM_PROPS_MINB 5
 #endif
 #ifndef TM_GRAD_MINB
-#define TM_GRAD_MINB 8
+#define TM_GRAD_MINB 5
 #endif
 constexpr int TM_PROPS_THREADS = TM_PROPS_NT;
 constexpr int TM_GRAD_THREADS  = TM_GRAD_NT;
@@ -91,6 +92,10 @@ struct MeshView {
     const P4* pos;         // V packed (x, y, z, rho) records, device vertex numbering
     const int* ex2_off;    // sorted two-ring rows (exclusion level 2), valid after tm_ensure_ring2
     const int* ex2_v;
+    // per ring slot, written by the property sweep and read by the gradient sweep (slot-major, [8][aux_vs]):
+    // aux[s][i] = (theta_s / l_s of spoke s of vertex i, 1 / |n_{s+1}| of the face between spokes s and s+1)
+    double2* aux;
+    int aux_vs;            // V rounded up to a multiple of 32
 };
 
 // Vertices one sweep launch covers: device slots [first, first + count), or the explicit list
@@ -121,7 +126,16 @@ struct NlView {
     const int* row_j;      // ceil(V/32) * row_cap * 32
     int row_cap;
     unsigned long long serial;   // identity of the list (pair-force cache)
+    // tile lists of a verlet list (tm_nlist.cu, build_tiles): the rows once more, per tile of TM_TILE consecutive
+    // vertices, with LOCAL neighbour indices (tile vertex, or TM_TILE + index into the tile's halo list); tile_T = 0: none
+    int tile_T, tile_hcap, tile_hmax, tile_slmax;   // tile size, halo stride, largest halo / in-tile pair count
+    const int* tile_halo;        // n_tiles * tile_hcap distinct out-of-tile neighbours of the tile (ascending ids)
+    const int* tile_info;        // n_tiles * 2: halo entries, in-tile undirected pairs
+    const unsigned* tile_ent;    // row_j's layout: local index | slot of the pair's slope << 16; upper, halo, lower
+    const unsigned* tile_cnt;    // V: n_upper | n_halo << 8 | n_lower << 16
+    const unsigned short* tile_lo;   // V: start of the vertex's lower entries in the tile's slope array
 };
+constexpr int TM_TILE = 256;
 
 // ----------------------------------------------------------------- handles --
 struct tm_mesh {
@@ -139,6 +153,9 @@ struct tm_mesh {
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
     R8* ring8 = nullptr;
+    double2* aux = nullptr;      // 8 * aux_vs slot quantities handed from the property to the gradient sweep
+    int* gen_list = nullptr;     // vertices without a fixed-width row (TM_RING_GENERIC), ascending (tm_rings.cu)
+    int n_generic = 0;
     bool rings_valid = false;
     bool has_boundary = false;   // the uploaded connectivity has boundary half-edges (open mesh)
     // host-numbered connectivity as uploaded (he_to_h, v_he_h) and the vertex permutation
@@ -152,6 +169,7 @@ struct tm_mesh {
     unsigned long long layout_epoch = 0;   // bumped whenever the permutation changes
     unsigned long long pos_epoch = 1;      // bumped whenever positions or connectivity change
     unsigned long long geo_epoch = 0;      // pos_epoch at which sums[0..2] and rho were evaluated
+    bool sums_full = false;                // the last property sweep also reduced tether and repulsion (sums[4..5])
     P4* pos = nullptr;           // V   (x, y, z, rho), device numbering
     P4* pos_alt = nullptr;       // V   second record array: a trajectory step writes x_{n+1} here while the gradient
                                  //     sweep still gathers x_n from `pos`, then the two swap (tm_integrate.cu)
@@ -194,6 +212,7 @@ struct tm_mesh {
         v.he_to = he_to; v.he_next = he_next; v.he_face = he_face; v.v_he = v_he;
         v.ring_off = ring_off; v.ring_v = ring_v; v.ring8 = ring8; v.pos = pos;
         v.ex2_off = ex2_off; v.ex2_v = ex2_v;
+        v.aux = aux; v.aux_vs = (V + 31) & ~31;
         return v;
     }
 };
@@ -212,6 +231,11 @@ struct tm_nlist {
     int row_cap = 0;
     int rows_first = 0, rows_count = 0;   // vertices whose verlet rows were built (all, or a partition's slice)
     unsigned long long serial = 0;
+    // tile lists (verlet lists over the whole mesh; see NlView)
+    int tile_T = 0, tile_hcap = 0, tile_hmax = 0, tile_slmax = 0;
+    int *tile_halo = nullptr, *tile_info = nullptr;
+    unsigned *tile_ent = nullptr, *tile_cnt = nullptr;
+    unsigned short* tile_lo = nullptr;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
     double* x_build = nullptr;   // V*3 positions the verlet rows were built from (device numbering): skin criterion
     long long n_entries = 0;
@@ -225,6 +249,8 @@ struct tm_nlist {
         }
         v.cell_start = cell_start; v.cell_items = cell_items; v.cell_rec = cell_rec;
         v.row_cnt = row_cnt; v.row_j = row_j; v.row_cap = row_cap; v.serial = serial;
+        v.tile_T = tile_T; v.tile_hcap = tile_hcap; v.tile_hmax = tile_hmax; v.tile_slmax = tile_slmax; v.tile_halo = tile_halo; v.tile_info = tile_info;
+        v.tile_ent = tile_ent; v.tile_cnt = tile_cnt; v.tile_lo = tile_lo;
         return v;
     }
 };
@@ -260,6 +286,7 @@ int tm_ensure_ring2(tm_mesh* m);                                 // tm_rings.cu
 void* tm_pool_alloc(int device, size_t bytes);
 void tm_pool_free(int device, void* p);
 int tm_exclusive_scan(tm_mesh* m, const int* in, int* out, int n, long long* total);  // tm_rings.cu
+int tm_props_workspace(tm_mesh* m);                              // tm_energy.cu: partials + slot arrays
 int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
                     bool full, bool write_vprops);               // tm_energy.cu
 // Velocity-Verlet update fused into the gradient sweep's epilogue (tm_integrate.cu): mode 1 = momentum
@@ -338,24 +365,40 @@ __device__ __forceinline__ P4 ldrec(const P4* __restrict__ pos, int i) {
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(pos + i));
     return r;
 }
-// 1/x and 1/sqrt(x) for normal, positive x: MUFU seed + two Newton steps, branch-free (the
-// compiler's own sequences carry a slow-path call for denormals/inf that these arguments never take)
+// 1/x and 1/sqrt(x) for normal, positive x, branch-free (the compiler's own sequences carry a slow-path call
+// for denormals/inf that these arguments never take). The MUFU seeds are good to 2^-20 on B200
+// (scripts/ubench/seed_accuracy.cu: 9.4e-7), so ONE third-order step reaches the rounding level
+// (measured max relative error 2.2e-16 for rcp, 2.7e-16 for rsqrt, the same as two Newton steps) with
+// 3 / 5 dependent fp64 operations instead of 4 / 7.
+#ifndef TM_CUBIC
+#define TM_CUBIC 1
+#endif
 __device__ __forceinline__ double rcp_pos(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if TM_CUBIC
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);          // r (1 + e + e^2)
+#else
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
+#endif
 }
 __device__ __forceinline__ double rsqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if TM_CUBIC
+    const double e = fma(-x * y, y, 1.0);    // 1 - x y^2
+    return fma(y * e, fma(0.375, e, 0.5), y);   // y (1 + e/2 + 3 e^2 / 8)
+#else
     const double hx = 0.5 * x;
     double e = fma(-hx * y, y, 0.5);     // 0.5 (1 - x y^2)
     y = fma(y, e, y);
     e = fma(-hx * y, y, 0.5);
     return fma(y, e, y);
+#endif
 }
 // x^r for the small integer exponents of the potentials (std::pow(l, r_) in the reference)
 __device__ __forceinline__ double ipow(double x, int r) {

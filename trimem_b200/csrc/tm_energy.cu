@@ -135,60 +135,175 @@ __device__ __forceinline__ void props_slot(const DevParams& P, d3 xi, int word, 
     }
 }
 
-template <bool FULL>
-__device__ __forceinline__ void ring_props_fast(const P4* pos, const DevParams& P, const R8& row, int d, d3 xi,
-                                                double& area, double& vol, double& curv, double& teth) {
-    d3 e[8];
-#pragma unroll
-    for (int s = 0; s < 8; s++)
-        if (s < d) e[s] = ldpos(pos, row.v[s] & TM_RING_MASK) - xi;
-    d3 el = e[2];                              // e_{d-1}, d >= 3 on this path
-#pragma unroll
-    for (int s = 3; s < 8; s++)
-        if (s < d) el = e[s];
-    d3 n_cur = cross3(e[0], el);
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < d) {
-            const d3 en = (s == 7 || s + 1 == d) ? e[0] : e[(s + 1) & 7];
-            const d3 n_next = cross3(en, e[s]);
-            props_slot<FULL>(P, xi, row.v[s], e[s], n_cur, en, n_next, area, vol, curv, teth);
-            n_cur = n_next;
+// ---- ring records in shared memory: the block's tile + staged far neighbours ---------------------------
+// The vertices of a block are NT consecutive device slots = a compact surface patch (Morton order), so
+// most ring neighbours of its vertices are vertices of the block itself (72 % at NT = 64, 80 % at 128, 86 %
+// at 256 on the headline mesh). A per-lane gather of a 32-byte record costs one L1 tag look-up per lane
+// (the 192 ring gathers of a warp touch only ~73 distinct records in ~33 lines), and that look-up rate,
+// not DRAM or the fp64 pipe, bounded the sweeps. So: every thread loads its own record once (coalesced,
+// 8 lines per warp) into the block's tile; a neighbour inside the tile is read from there; only the far
+// neighbours are gathered from global memory, with cp.async into a per-thread staging column.
+//   record index of slot s: idx < NT -> tile[idx], else the staging slot NT * (1 + s) + tid
+// xy and zr halves live in two arrays (conflict-free 16-byte accesses for the staging columns).
+#ifndef TM_RING_KS
+#define TM_RING_KS 4
+#endif
+constexpr int RING_KS = TM_RING_KS;      // staging columns per thread: a vertex with more far neighbours reads the rest
+                                         // from global memory when the walk gets there (a few percent of the vertices)
+template <int NT>
+struct RingSmem {
+    double2* xy;
+    double2* zr;
+    __device__ __forceinline__ RingSmem(double2* base) : xy(base), zr(base + (1 + RING_KS) * NT) {}
+    static constexpr size_t bytes() { return sizeof(double2) * 2 * (1 + RING_KS) * NT; }
+    // record k: k >= 0 a shared-memory record (tile or staging column), k < 0 the global record ~k
+    __device__ __forceinline__ void fetch(const P4* pos, int k, double2& a, double2& b) const {
+        if (k >= 0) { a = xy[k]; b = zr[k]; }
+        else {
+            const double2* src = reinterpret_cast<const double2*>(pos + ~k);
+            a = src[0]; b = src[1];
         }
     }
+};
+
+// stages the ring of one closed-fan vertex; idx[s] = record index of slot s (s < d)
+template <int NT>
+__device__ __forceinline__ void stage_ring(const RingSmem<NT>& S, const P4* pos, const R8& row, int d, int tile0,
+                                           int tile_n, int (&idx)[9]) {
+    const int tid = threadIdx.x;
+    int far = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        if (s < 3 || s < d) {
+            const int j = row.v[s];
+            const unsigned rel = (unsigned)(j - tile0);
+            if (rel < (unsigned)tile_n) idx[s] = (int)rel;
+            else if (far < RING_KS) {
+                idx[s] = NT * (1 + far) + tid;
+                ++far;
+                const P4* src = pos + j;
+                cp_async16(&S.xy[idx[s]], src);
+                cp_async16(&S.zr[idx[s]], reinterpret_cast<const char*>(src) + 16);
+            } else idx[s] = ~j;
+        }
+    }
+    idx[8] = idx[0];
 }
 
-template <bool FULL>
-__device__ __forceinline__ void ring_props_smem(const P4* pos, const DevParams& P, const R8& row, int d, d3 xi,
-                                                double& area, double& vol, double& curv, double& teth) {
-    __shared__ double2 s_xy[8][TM_PROPS_THREADS];
-    __shared__ double s_z[8][TM_PROPS_THREADS];
-    __shared__ int s_w[8][TM_PROPS_THREADS];
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < d) {
-            // (x, y) and z only: rho (.w) of other vertices is being written by this very sweep
-            const P4* src = pos + (row.v[s] & TM_RING_MASK);
-            cp_async16(&s_xy[s][tid], src);
-            cp_async8(&s_z[s][tid], &src->z);
-            s_w[s][tid] = row.v[s];
+// Closed fan of valence d = 3..8 (the fixed-width row): the fast path of the property sweep.
+//
+// Slot s owns spoke s and face s+1 (between spokes s and s+1; face d is face 0): with the
+// un-normalised normal n_s handed over by slot s-1 it evaluates
+//   n_{s+1} = e_{s+1} x e_s, |n_{s+1}|, 1/|n_{s+1}|      (area, volume, AREA bonds)
+//   l_s, 1/l_s, theta_s = atan2(-l_s (e_{s+1} . n_s), n_s . n_{s+1})   (curvature, EDGE bonds)
+// and hands (tau_s = theta_s / l_s, 1/|n_{s+1}|) to the gradient sweep through the slot-major aux array
+// (one coalesced 16-byte store), so that sweep needs no square root, reciprocal or arc tangent.
+// The walk is a chain of slot bodies, each instantiated once per slot index and ending in
+// `if (s + 1 < d) next slot`: straight-line code, no join of the walk state (no register rotation) -- only
+// the accumulators meet again where the threads of different valence reconverge.
+struct PropsAcc {
+    double area2, curv, teth;   // sum |n_f|, sum l theta, tether sum
+    d3 nsum;                    // sum n_f
+    unsigned tmask;             // slots whose EDGE bond is off the flat bottom
+};
+
+template <bool FULL, int NT>
+struct PropsWalk {
+    const DevParams& P;
+    const RingSmem<NT>& S;
+    const int (&idx)[9];
+    d3 xi;
+    int d;
+    double2* aux;               // aux + i, or nullptr
+    int vs;
+    PropsAcc& A;
+
+    const P4* pos;
+    __device__ __forceinline__ d3 spoke(int k) const {          // record index k
+        double2 a, b;
+        S.fetch(pos, k, a, b);
+        return mk3(a.x, a.y, b.x) - xi;
+    }
+    // what one slot adds: spoke e_c with normal n_c of its face and squared length l2_c, next spoke e_n
+    struct SlotOut { d3 n_n; double l2_n, nl, lth, tau, in_n, l; };
+    __device__ __forceinline__ SlotOut eval(const d3 e_c, const d3 n_c, const double l2_c, const d3 e_n) const {
+        SlotOut o;
+        o.n_n = cross3(e_n, e_c);
+        const double nn = dot3(o.n_n, o.n_n);
+        o.l2_n = dot3(e_n, e_n);
+        // (the 1e-300 offset is invisible for a proper face and makes a degenerate one come out as |n| = 0)
+        o.in_n = rsqrt_pos(nn + 1.0e-300);
+        const double il = rsqrt_pos(l2_c);
+        o.nl = __dmul_rn(nn, o.in_n);                     // |n_{s+1}| = 2 A_f
+        o.l = l2_c * il;
+        const double th = tm_math::atan2_fast(-o.l * dot3(e_n, n_c), dot3(n_c, o.n_n));
+        o.lth = __dmul_rn(o.l, th);
+        o.tau = th * il;
+        return o;
+    }
+    // (explicitly rounded sums: the FULL and the geometry-only instantiation must produce the same rho and
+    // slot quantities bit for bit, whatever else the compiler would like to contract into them)
+    __device__ __forceinline__ void add(const SlotOut& o, int s, bool valid) const {
+        A.area2 = __dadd_rn(A.area2, valid ? o.nl : 0.0);
+        A.curv = __dadd_rn(A.curv, valid ? o.lth : 0.0);
+        A.nsum.x = __dadd_rn(A.nsum.x, valid ? o.n_n.x : 0.0);
+        A.nsum.y = __dadd_rn(A.nsum.y, valid ? o.n_n.y : 0.0);
+        A.nsum.z = __dadd_rn(A.nsum.z, valid ? o.n_n.z : 0.0);
+        if (aux && valid) aux[s * vs] = make_double2(o.tau, o.in_n);
+        if (FULL) {
+            // EDGE bonds leave the flat bottom on a fraction of a percent of the edges: those slots are
+            // flagged and evaluated after the walk (one copy of the exp/pow code, outside the chain)
+            if (P.bond_type == TM_BOND_EDGE) A.tmask |= (valid && (o.l > P.lc0 || o.l < P.lc1)) ? (1u << s) : 0u;
+            else { const double q = fma(0.5 * o.nl, P.inv_a0, -1.0); A.teth = __dadd_rn(A.teth, valid ? __dmul_rn(q, q) : 0.0); }
         }
     }
-    cp_async_wait_all();
-    auto spoke = [&](int s) {
-        const double2 a = s_xy[s][tid];
-        return mk3(a.x, a.y, s_z[s][tid]) - xi;
-    };
-    d3 e_cur = spoke(0);
-    d3 n_cur = cross3(e_cur, spoke(d - 1));
-#pragma unroll PROPS_UNROLL
-    for (int s = 0; s < d; s++) {
-        const d3 e_next = spoke(s + 1 == d ? 0 : s + 1);
-        const d3 n_next = cross3(e_next, e_cur);
-        props_slot<FULL>(P, xi, s_w[s][tid], e_cur, n_cur, e_next, n_next, area, vol, curv, teth);
-        e_cur = e_next; n_cur = n_next;
+    // Slots S_ and S_+1 in ONE basic block: their rsqrt / atan2 chains are independent, so the scheduler
+    // interleaves them (the sweep is bound by dependent-issue latency: ~10 cycles per fp64 operation of a chain,
+    // 4-5 warps per scheduler). Slot S_ is valid on entry; slot S_+1 may lie beyond the ring (odd valence): it is
+    // then evaluated on harmless data (spoke 0) and left out of the sums.
+    template <int S_>
+    __device__ __forceinline__ void slot2(const d3 e_c, const d3 n_c, const double l2_c) const {
+        const bool v1 = S_ + 1 < 3 || S_ + 1 < d;             // slot S_+1 exists
+        const bool v2 = S_ + 2 < 3 || S_ + 2 < d;             // slot S_+2 exists (else spoke S_+2 wraps to 0)
+        const d3 e_1 = spoke(v1 ? idx[S_ + 1] : idx[0]);
+        const d3 e_2 = spoke(v2 && S_ + 2 < 8 ? idx[S_ + 2 < 8 ? S_ + 2 : 0] : idx[0]);
+        const SlotOut a = eval(e_c, n_c, l2_c, e_1);
+        const SlotOut b = eval(e_1, a.n_n, a.l2_n, e_2);
+        add(a, S_, true);
+        add(b, S_ + 1, v1);
+        if (S_ + 2 < 8) {
+            if (v2) slot2<(S_ + 2 < 8 ? S_ + 2 : 6)>(e_2, b.n_n, b.l2_n);
+        }
     }
+};
+
+// idx[]: record indices of the staged ring (stage_ring), complete (cp.async waited for, block barrier passed)
+template <bool FULL, int NT>
+__device__ __forceinline__ void ring_props_closed(const MeshView& mv, const DevParams& P, const RingSmem<NT>& S,
+                                                  const int (&idx)[9], int d, int i, d3 xi, bool write_aux,
+                                                  double& area, double& vol, double& curv, double& teth) {
+    PropsAcc A;
+    A.area2 = 0.0; A.curv = 0.0; A.teth = 0.0; A.nsum = mk3(0, 0, 0); A.tmask = 0u;
+    const PropsWalk<FULL, NT> W{P, S, idx, xi, d, write_aux ? mv.aux + i : nullptr, mv.aux_vs, A, mv.pos};
+    int k_last = idx[2];
+#pragma unroll
+    for (int s = 3; s < 8; s++) k_last = s < d ? idx[s] : k_last;
+    const d3 e_0 = W.spoke(idx[0]);
+    W.template slot2<0>(e_0, cross3(e_0, W.spoke(k_last)), dot3(e_0, e_0));
+    if (FULL) {
+        unsigned tmask = A.tmask;
+        while (tmask) {                            // ascending slot order; rare: the spoke is fetched again
+            const int s = __ffs(tmask) - 1;
+            tmask &= tmask - 1;
+            const d3 e = ldpos(mv.pos, mv.ring8[i].v[s]) - xi;
+            const double l2 = dot3(e, e);
+            A.teth += tether_edge(l2 * rsqrt_pos(l2), P);
+        }
+    }
+    area = 0.5 * A.area2;                      // sum of face areas
+    vol = dot3(xi, A.nsum);                    // sum over faces of (x_j x x_k) . x_i
+    curv = A.curv;
+    teth = A.teth;
 }
 
 template <bool FULL>
@@ -211,51 +326,148 @@ __device__ __forceinline__ void ring_props_generic(const MeshView& mv, const Dev
 
 // FULL = also tether and repulsion (what energy()/properties() need); the property
 // sweep inside gradient() only needs area, volume, curvature and rho.
+//
+// Two kernels: k_props walks the closed fans of the fixed-width rows (every vertex of a closed mesh of
+// valence 3..8) and carries no slow path; k_props_generic runs over the short list of the remaining
+// vertices (tm_rings.cu), only when there are any. Ghost sweeps of a partitioned mesh (explicit vertex
+// list, nothing reduced) take the generic walk inline (GEN_INLINE) instead.
 template <bool FULL, bool WRITE_VPROPS>
+__device__ __forceinline__ void props_finish(const DevParams& P, int i, double area, double vol, double curv, double teth,
+                                             P4* pos_rw, double* __restrict__ vprops, double (&acc)[6]) {
+    area = area * (1.0 / 3.0);
+    vol = vol * (1.0 / 18.0);                  // /6 per face, /3 multiplicity
+    curv = curv * 0.25;                        // 0.5 l theta per half-edge, /2 multiplicity
+    if (FULL) teth = teth * (P.bond_type == TM_BOND_EDGE ? 0.5 : (1.0 / 3.0));
+    const double rho = area > 0.0 ? curv * rcp_pos(area) : curv / area;   // rho_i = c_i / a_i
+    acc[0] = area; acc[1] = vol; acc[2] = curv;
+    acc[3] = 2.0 * curv * rho;
+    acc[4] = teth;
+    pos_rw[i].w = rho;                         // rides in the position record
+    if (WRITE_VPROPS) {
+        double* o = vprops + 6 * (size_t)i;
+#pragma unroll
+        for (int q = 0; q < 5; q++) o[q] = acc[q];
+    }
+}
+
+// One partial per warp and quantity. The six sums of a warp are reduced TOGETHER: at every level of the
+// butterfly a lane keeps half of the quantities it still carries and hands the other half to its partner, so
+// the tree takes 3 + 2 + 1 + 1 + 1 shuffles instead of 6 x 5 (the serial chain of shuffle latencies was a tenth
+// of the sweep). Lane q of the first eight ends up with quantity q; fixed tree, bit-reproducible.
+__device__ __forceinline__ void props_warp_partials(const double (&acc)[6], int nq, double* __restrict__ partials,
+                                                    int ncols, int col) {
+    const int lane = threadIdx.x & 31;
+    const unsigned full = 0xffffffffu;
+    // level 16: lanes with bit 4 clear keep quantities {0,1,2,3}' low half ... written out for 8 slots (6 used)
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = q < 6 ? acc[q] : 0.0;
+    double w4[4];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const double send = hi ? v[k] : v[k + 4];
+            const double got = __shfl_xor_sync(full, send, 16);
+            w4[k] = (hi ? v[k + 4] : v[k]) + got;            // hi lanes carry quantities 4..7, lo lanes 0..3
+        }
+    }
+    double w2[2];
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double send = hi ? w4[k] : w4[k + 2];
+            const double got = __shfl_xor_sync(full, send, 8);
+            w2[k] = (hi ? w4[k + 2] : w4[k]) + got;
+        }
+    }
+    double w1;
+    {
+        const bool hi = lane & 4;
+        const double send = hi ? w2[0] : w2[1];
+        const double got = __shfl_xor_sync(full, send, 4);
+        w1 = (hi ? w2[1] : w2[0]) + got;
+    }
+    w1 += __shfl_xor_sync(full, w1, 2);
+    w1 += __shfl_xor_sync(full, w1, 1);
+    // lane l (l & 3 == 0) holds quantity q = 4 * bit4 + 2 * bit3 + bit2
+    const int q = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    if ((lane & 3) == 0 && q < nq && col < ncols) partials[(size_t)q * ncols + col] = w1;
+}
+
+// partials: [6][ncols] warp partials; this launch owns the columns [0, number of its warps). Quantity 5
+// (repulsion) belongs to k_pairs and is written here (as 0) only when no pair sweep runs (nq == 6).
+template <bool FULL, bool WRITE_VPROPS, bool GEN_INLINE>
 __global__ void __launch_bounds__(TM_PROPS_THREADS, TM_PROPS_MINB)
 k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
-        double* __restrict__ partials, int nwarps, int nq, SweepRange R) {
-    const int t = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
-    const int i = R.vlist ? (t < R.count ? R.vlist[t] : 0) : R.first + t;
+        double* __restrict__ partials, int ncols, int nq, SweepRange R, int write_aux) {
+    constexpr int NT = TM_PROPS_THREADS;
+    extern __shared__ double2 ring_smem[];
+    const RingSmem<NT> S(ring_smem);
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * NT + tid;
+    const bool live = t < R.count;
+    const int i = R.vlist ? (live ? R.vlist[t] : 0) : R.first + t;
+    // the block's tile: the records of its own NT consecutive vertices (list-driven launches have none)
+    const int tile0 = R.first + blockIdx.x * NT;
+    const int tile_n = R.vlist ? 0 : min(NT, mv.V - tile0);
+    P4 ri;
+    ri.x = ri.y = ri.z = ri.w = 0.0;
+    if (tid < tile_n) {
+        // coherent load: rho (.w) of other vertices is being written by this very sweep (and never read by it)
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ri.x), "=d"(ri.y), "=d"(ri.z), "=d"(ri.w) : "l"(mv.pos + tile0 + tid));
+        S.xy[tid] = make_double2(ri.x, ri.y);
+        S.zr[tid] = make_double2(ri.z, ri.w);
+    } else if (live) {
+        const d3 x = ldpos(mv.pos, i);
+        ri.x = x.x; ri.y = x.y; ri.z = x.z;
+    }
+    R8 row;
+    row.v[0] = TM_RING_GENERIC;
+    int d = 0;
+    int idx[9];
+    if (live) {
+        row = ldrow(mv.ring8, i);
+        if (row.v[0] != TM_RING_GENERIC) {
+            d = row_valence(row);
+            stage_ring<NT>(S, mv.pos, row, d, tile0, tile_n, idx);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
     double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
-    if (t < R.count) {
-        const R8 row = ldrow(mv.ring8, i);
-        const d3 xi = ldpos(mv.pos, i);
+    if (live) {
+        const d3 xi = mk3(ri.x, ri.y, ri.z);
         double area = 0, vol = 0, curv = 0, teth = 0;
-        if (row.v[0] == TM_RING_GENERIC) ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
-        else {
-            const int d = row_valence(row);
-#if TM_PROPS_SMEM
-            if (d > 0) ring_props_smem<FULL>(mv.pos, P, row, d, xi, area, vol, curv, teth);
-#else
-            if (d > 0) ring_props_fast<FULL>(mv.pos, P, row, d, xi, area, vol, curv, teth);
-#endif
-        }
-        area = area / 3.0;
-        vol = vol / 18.0;                          // /6 per face, /3 multiplicity
-        curv = curv / 4.0;                         // 0.5 l theta per half-edge, /2 multiplicity
-        if (FULL) teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
-        acc[0] = area; acc[1] = vol; acc[2] = curv;
-        acc[3] = 2.0 * curv * curv / area;
-        acc[4] = teth;
-        pos_rw[i].w = curv / area;                 // rho_i = c_i / a_i rides in the position record
-        if (WRITE_VPROPS) {
-            double* o = vprops + 6 * (size_t)i;
-#pragma unroll
-            for (int q = 0; q < 5; q++) o[q] = acc[q];
+        if (row.v[0] != TM_RING_GENERIC) {
+            ring_props_closed<FULL, NT>(mv, P, S, idx, d, i, xi, write_aux != 0, area, vol, curv, teth);
+            props_finish<FULL, WRITE_VPROPS>(P, i, area, vol, curv, teth, pos_rw, vprops, acc);
+        } else if (GEN_INLINE) {
+            ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
+            props_finish<FULL, WRITE_VPROPS>(P, i, area, vol, curv, teth, pos_rw, vprops, acc);
         }
     }
-    // one partial per warp and quantity, fixed shuffle tree; quantity 5 (repulsion) belongs to
-    // k_pairs and is written here (as 0) only when no pair sweep runs (nq == 6)
-    const int lane = threadIdx.x & 31, w = t >> 5;
-#pragma unroll
-    for (int q = 0; q < 6; q++) {
-        if (q >= nq) break;
-        double s = acc[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && w < nwarps) partials[(size_t)q * nwarps + w] = s;
+    if (nq > 0) props_warp_partials(acc, nq, partials, ncols, t >> 5);
+}
+
+// the vertices of `list` (ascending) that fall into [R.first, R.first + R.count): columns col0.. of the partials
+template <bool FULL, bool WRITE_VPROPS>
+__global__ void __launch_bounds__(128)
+k_props_generic(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops, double* __restrict__ partials,
+                int ncols, int col0, int nq, const int* __restrict__ list, int n, SweepRange R) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (t < n) {
+        const int i = list[t];
+        if (i >= R.first && i < R.first + R.count) {
+            const d3 xi = ldpos(mv.pos, i);
+            double area = 0, vol = 0, curv = 0, teth = 0;
+            ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
+            props_finish<FULL, WRITE_VPROPS>(P, i, area, vol, curv, teth, pos_rw, vprops, acc);
+        }
     }
+    props_warp_partials(acc, nq, partials, ncols, col0 + (t >> 5));
 }
 
 // ---- K1b: pair sweep: surface repulsion energy and force per vertex ------------------------
@@ -499,6 +711,90 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
     }
 }
 
+// ---- K1c: pair sweep over the tile lists of a verlet list (tm_nlist.cu, build_tiles) ----------------------
+// One block per tile of TM_TILE consecutive vertices. The tile's own records and its halo records go to shared
+// memory once (SoA x, y, z); every pair evaluation then reads shared memory through its local index. In-tile
+// pairs are evaluated once, by their lower vertex, which leaves the slope factor in the tile's slope array for
+// its partner (second phase: six fp64 operations per entry instead of ~50). Same potential, same cut-off test,
+// fixed summation order.
+template <bool WITH_E, bool R2>
+__global__ void __launch_bounds__(TM_TILE, 3)
+k_pairs_tile(MeshView mv, NlView nl, double lc1, int rr, int hmax, double* __restrict__ force,
+             double* __restrict__ partials, int ncols) {
+    extern __shared__ double pt_smem[];
+    const int np = TM_TILE + hmax;
+    double* sx = pt_smem;
+    double* sy = sx + np;
+    double* sz = sy + np;
+    double* ssl = sz + np;
+    const int tid = threadIdx.x, b = blockIdx.x, tile0 = b * TM_TILE, i = tile0 + tid;
+    const bool live = i < mv.V;
+    d3 xi = mk3(0, 0, 0);
+    if (live) {
+        const P4 r = ldrec(mv.pos, i);
+        xi = mk3(r.x, r.y, r.z);
+        sx[tid] = r.x; sy[tid] = r.y; sz[tid] = r.z;
+    }
+    const int nh = __ldg(nl.tile_info + 2 * b);
+    for (int h = tid; h < nh; h += TM_TILE) {
+        const P4 r = ldrec(mv.pos, __ldg(nl.tile_halo + (size_t)b * nl.tile_hcap + h));
+        sx[TM_TILE + h] = r.x; sy[TM_TILE + h] = r.y; sz[TM_TILE + h] = r.z;
+    }
+    __syncthreads();
+    PairConst C;
+    C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
+#pragma unroll
+    for (int q = 0; q < 12; q++) C.ec[q] = tm_math::EXP_C[q];
+    const unsigned cnt = live ? __ldg(nl.tile_cnt + i) : 0u;
+    const int n_up = cnt & 255, n_halo = (cnt >> 8) & 255, n_lo = (cnt >> 16) & 255;
+    const unsigned* col = nl.tile_ent + tm_row_base(live ? i : 0, nl.row_cap);
+    d3 gr = mk3(0, 0, 0);
+    double rep = 0.0;
+    // phase 1: upper in-tile entries (slope stored for the partner, energy counted for both ends) and halo entries
+    const int n1 = n_up + n_halo;
+    for (int k = 0; k < n1; k += PB) {
+        unsigned ent[PB];
+#pragma unroll
+        for (int u = 0; u < PB; u++) ent[u] = (k + u < n1) ? __ldg(col + (k + u) * 32) : (unsigned)tid;
+        d3 dv[PB];
+        double l2[PB], phi[PB], sl[PB];
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            const int loc = ent[u] & 0xffffu;
+            dv[u] = xi - mk3(sx[loc], sy[loc], sz[loc]);
+            l2[u] = dot3(dv[u], dv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < PB; u++) pair_eval<R2>(C, rr, l2[u], (k + u < n1) && (l2[u] < C.lc1sq), phi[u], sl[u]);
+#pragma unroll
+        for (int u = 0; u < PB; u++) {
+            const bool upper = k + u < n_up;
+            if (WITH_E) rep += upper ? 2.0 * phi[u] : phi[u];
+            axpy3(gr, sl[u], dv[u]);
+            if (upper) ssl[ent[u] >> 16] = sl[u];
+        }
+    }
+    __syncthreads();
+    // phase 2: lower in-tile entries: the partner's slope factor times this end's difference vector
+    const int lo0 = live ? (int)__ldg(nl.tile_lo + i) : 0;
+    for (int k = 0; k < n_lo; k++) {
+        const int loc = __ldg(col + (n1 + k) * 32) & 0xffffu;
+        const d3 dv = xi - mk3(sx[loc], sy[loc], sz[loc]);
+        axpy3(gr, ssl[lo0 + k], dv);
+    }
+    if (live) {
+        double* o = force + 3 * (size_t)i;
+        o[0] = gr.x; o[1] = gr.y; o[2] = gr.z;
+    }
+    if (WITH_E) {
+        const int lane = tid & 31, w = i >> 5;
+        double s = rep;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && w < ncols) partials[(size_t)5 * ncols + w] = s;
+    }
+}
+
 // ---- K2: fixed-order sum of the warp partials ---------------------------------------------
 // grid of nb <= TM_REDUCE_BLOCKS blocks; block b owns the contiguous chunk [b*per, (b+1)*per) of
 // warp partials; the last block to finish adds the nb block sums in index order.
@@ -638,14 +934,6 @@ __device__ __noinline__ void boundary_spoke_terms(const MeshView& mv, double fC,
         if (mm > 0.0) axpy3(g, W * boundary_spoke_cot(mv, xi, xj, j) / sqrt_nn(mm), n_nxt);
     }
 }
-__device__ __forceinline__ bool row_has_boundary_spoke(const R8& r) {
-    bool b = false;
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        b |= r.v[k] != TM_RING_PAD && (r.v[k] & TM_RING_FACE) && !(r.v[k] & TM_RING_OFACE);
-    return b;
-}
-
 // contribution of ring slot s (mesh_properties.cpp:73-134) to g_i
 __device__ __forceinline__ void grad_slot(const DevParams& P, const GradK& K, double rho_i, int word,
                                           const GSlot& prv, const GSlot& cur, const GSlot& nxt,
@@ -688,87 +976,98 @@ __device__ __forceinline__ void grad_slot(const DevParams& P, const GradK& K, do
     esum = esum + (prv.e - cur.e);
 }
 
-__device__ __forceinline__ void ring_grad_fast(const MeshView& mv, const DevParams& P, const GradK& K, const R8& row,
-                                               int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
-    d3 e[8];
-    double rho[8];
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < d) {
-            const P4 q = ldrec(mv.pos, row.v[s] & TM_RING_MASK);
-            e[s] = mk3(q.x, q.y, q.z) - xi;
-            rho[s] = q.w;
-        }
-    }
-    d3 el = e[2];
-    double rhol = rho[2];
-#pragma unroll
-    for (int s = 3; s < 8; s++)
-        if (s < d) { el = e[s]; rhol = rho[s]; }
-    GSlot prv, cur;
-    gslot_point(prv, el, rhol);
-    gslot_point(cur, e[0], rho[0]);
-    gslot_pair(cur, prv);
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < d) {
-            const bool wrap = (s == 7 || s + 1 == d);
-            GSlot nxt;
-            gslot_point(nxt, wrap ? e[0] : e[(s + 1) & 7], wrap ? rho[0] : rho[(s + 1) & 7]);
-            gslot_pair(nxt, cur);
-            grad_slot(P, K, rho_i, row.v[s], prv, cur, nxt, g, nsum, esum);
-            prv = cur;
-            cur = nxt;
-        }
-    }
-}
+// Closed fan of valence d = 3..8: the fast path of the gradient sweep (mesh_properties.cpp:73-134).
+//
+// Collecting the reference's five blocks per basis vector of the fan (e_s spokes, n_s = e_s x e_{s-1}
+// face normals; p_s = e_s . e_{s-1}, a_s = |e_s|^2 - p_s, b_s = |e_{s-1}|^2 - p_s):
+//   g_i = sum_s E_s e_s + C_s n_s
+//   C_s = kb/|n_s|^2 [(rho_i - rho_{s-1}) a_s + (rho_i - rho_s) b_s] + fV/6
+//         (the spoke terms of both edges of face s and its link-edge term; the kappa_c factors cancel, the
+//          volume gradient sum_f n_f / 6 rides along)
+//   E_s = -W_s tau_s - h_s b_s - h_{s+1} a_{s+1} - kt tether'(l_s)/l_s,   W_s = fC/2 + kb (rho_i + rho_s),
+//   h_s = U_s / (2 |n_s|),  U_s = fA - 2/3 kb (rho_i^2 + rho_s^2 + rho_{s-1}^2) [+ AREA bond]
+// tau_s = theta_s / l_s and 1/|n_s| come from the property sweep (aux arrays), so a slot costs ~40 fp64
+// operations and no square root, reciprocal or arc tangent. Ring records (x, y, z, rho) staged
+// global -> shared with cp.async; slot loop unrolled over the 8 slots of the row.
+struct GradC {
+    double W0, U0h, c3, fV6, kb, kt;
+};
 
-#ifndef TM_GRAD_SMEM
-#define TM_GRAD_SMEM 1
-#endif
-#ifndef TM_GRAD_UNROLL
-#define TM_GRAD_UNROLL 1
-#endif
-constexpr int GRAD_UNROLL = TM_GRAD_UNROLL;
+template <int NT>
+struct GradWalk {
+    const DevParams& P;
+    const GradC& K;
+    const RingSmem<NT>& S;
+    const int (&idx)[9];
+    const double2* saux;        // this thread's column of the staged slot quantities: slot s at saux[s * NT]
+    const P4* pos;
+    d3 xi;
+    double rho_i;
+    int d;
+    d3& g;
+    unsigned& tmask;
 
-// The same walk with the ring records staged in shared memory instead of registers: the eight
-// (x, y, z, rho) records of a thread go global -> shared with cp.async (no register staging), in
-// a [slot][thread] layout of 16-byte halves (conflict-free 128-bit accesses), and the slot loop
-// fetches spoke s+1 when it needs it. The register version keeps 8 x 4 doubles of ring data live
-// next to three GSlots and nine accumulators and spills ~200 bytes per thread at 128 registers.
-__device__ __forceinline__ void ring_grad_smem(const MeshView& mv, const DevParams& P, const GradK& K, const R8& row,
-                                               int d, d3 xi, double rho_i, d3& g, d3& nsum, d3& esum) {
-    __shared__ double2 s_xy[8][TM_GRAD_THREADS];
-    __shared__ double2 s_zr[8][TM_GRAD_THREADS];
-    __shared__ int s_w[8][TM_GRAD_THREADS];
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < d) {
-            const P4* src = mv.pos + (row.v[s] & TM_RING_MASK);
-            cp_async16(&s_xy[s][tid], src);
-            cp_async16(&s_zr[s][tid], reinterpret_cast<const char*>(src) + 16);
-            s_w[s][tid] = row.v[s];
+    struct Pt { d3 e; double l2, dr, r2; };        // spoke, |e|^2, rho_i - rho, rho^2
+    __device__ __forceinline__ Pt point(int k) const {          // record index k
+        double2 a, b;
+        S.fetch(pos, k, a, b);
+        Pt t;
+        t.e = mk3(a.x, a.y, b.x) - xi;
+        t.l2 = dot3(t.e, t.e);
+        t.dr = rho_i - b.y;
+        t.r2 = b.y * b.y;
+        return t;
+    }
+    // slot S_: face S_ between spokes S_-1 (pp) and S_; E_p = coefficient of e_{S_-1} gathered so far,
+    // inv = 1/|n_S_|, first = the part of spoke d-1's coefficient that slot 0 produced
+    template <int S_>
+    __device__ __forceinline__ void slot(const Pt pp, const double E_p, const double inv, const double first) const {
+        const Pt pc = point(idx[S_]);
+        const double2 ax = saux[S_ * NT];                // (tau_S, 1/|n_{S+1}|)
+        const double p = dot3(pc.e, pp.e);
+        const d3 n = cross3(pc.e, pp.e);
+        const double a = pc.l2 - p, b = pp.l2 - p;
+        const double C = fma(K.kb * inv * inv, fma(pp.dr, a, pc.dr * b), K.fV6);
+        double Uh = fma(-K.c3, pc.r2 + pp.r2, K.U0h);
+        if (P.bond_type == TM_BOND_AREA) {
+            const double a_f = 0.5 * rcp_pos(inv);
+            Uh = fma(K.kt * P.inv_a0, fma(a_f, P.inv_a0, -1.0), Uh);
         }
+        const double h = Uh * inv;
+        // W_S = fC/2 + kb (rho_i + rho_S) = W0 - kb (rho_i - rho_S) with W0 = fC/2 + 2 kb rho_i
+        const double E_c = fma(-h, b, -fma(-K.kb, pc.dr, K.W0) * ax.x);
+        if (P.bond_type == TM_BOND_EDGE) tmask |= (pc.l2 > P.lc0sq || pc.l2 < P.lc1sq) ? (1u << S_) : 0u;
+        const double f1 = S_ == 0 ? -h * a : first;      // slot 0's share belongs to spoke d-1
+        if (S_ > 0) axpy3(g, fma(-h, a, E_p), pp.e);     // spoke S_-1 is complete
+        axpy3(g, C, n);
+        if (S_ + 1 < 8 && (S_ + 1 < 3 || S_ + 1 < d)) slot<(S_ + 1 < 8 ? S_ + 1 : 7)>(pc, E_c, ax.y, f1);
+        else axpy3(g, E_c + f1, pc.e);                   // last spoke
     }
-    cp_async_wait_all();
-    auto spoke = [&](GSlot& t, int s) {
-        const double2 a = s_xy[s][tid], b = s_zr[s][tid];
-        gslot_point(t, mk3(a.x, a.y, b.x) - xi, b.y);
-    };
-    GSlot prv, cur;
-    spoke(prv, d - 1);
-    spoke(cur, 0);
-    gslot_pair(cur, prv);
-#pragma unroll GRAD_UNROLL
-    for (int s = 0; s < d; s++) {
-        GSlot nxt;
-        spoke(nxt, s + 1 == d ? 0 : s + 1);
-        gslot_pair(nxt, cur);
-        grad_slot(P, K, rho_i, s_w[s][tid], prv, cur, nxt, g, nsum, esum);
-        prv = cur;
-        cur = nxt;
+};
+
+// idx[]: record indices of the staged ring (stage_ring), complete
+template <int NT>
+__device__ __forceinline__ d3 ring_grad_closed(const MeshView& mv, const DevParams& P, const GradC& K,
+                                               const RingSmem<NT>& S, const double2* saux, const int (&idx)[9], int d,
+                                               int i, d3 xi, double rho_i) {
+    d3 g = mk3(0, 0, 0);
+    unsigned tmask = 0;
+    const GradWalk<NT> W{P, K, S, idx, saux, mv.pos, xi, rho_i, d, g, tmask};
+    const double in_0 = saux[(d - 1) * NT].y;            // face 0 = face d, written by slot d-1
+    int k_last = idx[2];
+#pragma unroll
+    for (int s = 3; s < 8; s++) k_last = s < d ? idx[s] : k_last;
+    W.template slot<0>(W.point(k_last), 0.0, in_0, 0.0);
+    // EDGE bonds off the flat bottom (mesh_properties.cpp:132-133): rare, evaluated outside the walk
+    while (tmask) {
+        const int s = __ffs(tmask) - 1;
+        tmask &= tmask - 1;
+        const d3 e = ldpos(mv.pos, mv.ring8[i].v[s]) - xi;
+        const double l2 = dot3(e, e);
+        const double il = rsqrt_pos(l2);
+        axpy3(g, -K.kt * tether_edge_fac(l2 * il, P) * il, e);
     }
+    return g;
 }
 
 __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevParams& P, const GradK& K, int i,
@@ -795,45 +1094,11 @@ __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevP
     }
 }
 
-// Reads only: every ring / list neighbour costs one 256-bit read-only load of its
-// (x, y, z, rho) record.
+// what follows the ring walk of vertex i: repulsion, the gradient row, and the velocity-Verlet update fused
+// into the sweep (tm_integrate.cu)
 template <int UPD>
-__global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
-k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
-       double* __restrict__ grad, SweepRange R, VVFuse U) {
-    const int t = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
-    if (t >= R.count) return;
-    const int i = R.first + t;
-
-    GradK K;
-    K.fA = 2.0 * P.kappa_a / P.ref_area * (sums[0] / P.ref_area - 1.0);
-    K.fV = 2.0 * P.kappa_v / P.ref_volume * (sums[1] / P.ref_volume - 1.0);
-    K.fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
-    K.kb = P.kappa_b; K.kt = P.kappa_t;
-
-    const R8 row = ldrow(mv.ring8, i);
-    const P4 ri = ldrec(mv.pos, i);
-    if (UPD > 0) {
-        // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
-    }
-    const d3 xi = mk3(ri.x, ri.y, ri.z);
-    d3 g = mk3(0, 0, 0);
-    d3 nsum = mk3(0, 0, 0);      // sum of face normals  -> volume gradient
-    d3 esum = mk3(0, 0, 0);      // sum of (e_{s-1} - e_s) over faces (0 for closed fans)
-    if (row.v[0] == TM_RING_GENERIC) ring_grad_generic(mv, P, K, i, xi, ri.w, g, nsum, esum);
-    else {
-        const int d = row_valence(row);
-#if TM_GRAD_SMEM
-        if (d > 0) ring_grad_smem(mv, P, K, row, d, xi, ri.w, g, nsum, esum);
-#else
-        if (d > 0) ring_grad_fast(mv, P, K, row, d, xi, ri.w, g, nsum, esum);
-#endif
-    }
-    // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
-    axpy3(g, K.fV / 6.0, nsum + cross3(xi, esum));
-
+__device__ __forceinline__ void grad_finish(const DevParams& P, int i, const P4& ri, d3 g, const double* __restrict__ force,
+                                            double* __restrict__ grad, const VVFuse& U) {
     // repulsion (mesh_properties.cpp:139-146): 2 kappa_r * pair force of k_pairs
     if (force) {
         const double* f = force + 3 * (size_t)i;
@@ -867,21 +1132,93 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     }
 }
 
-// Open meshes only (launched when the connectivity has boundary half-edges): adds the reference's
-// boundary-spoke terms to the finished gradient rows, so that the closed-mesh sweep carries none of it.
-__global__ void k_grad_boundary(MeshView mv, DevParams P, const double* __restrict__ sums, double* __restrict__ grad,
-                                SweepRange R) {
-    const int t = blockIdx.x * 128 + threadIdx.x;
-    if (t >= R.count) return;
+// chain-rule factors of the global penalties (kernel.h:27-71,124-137)
+__device__ __forceinline__ void penalty_factors(const DevParams& P, const double* __restrict__ sums, double& fA, double& fV,
+                                                double& fC) {
+    fA = 2.0 * P.kappa_a * P.inv_ref_area * fma(sums[0], P.inv_ref_area, -1.0);
+    fV = 2.0 * P.kappa_v * P.inv_ref_volume * fma(sums[1], P.inv_ref_volume, -1.0);
+    fC = 2.0 * P.kappa_c * P.inv_ref_curvature * fma(sums[2], P.inv_ref_curvature, -1.0);
+}
+
+// Closed fans only (vertices without a fixed-width row are left to k_grad_generic). Reads only: every ring
+// neighbour costs one (x, y, z, rho) record, every slot one (tau, 1/|n|) pair of the property sweep.
+template <int UPD>
+__global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
+k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
+       double* __restrict__ grad, SweepRange R, VVFuse U) {
+    constexpr int NT = TM_GRAD_THREADS;
+    extern __shared__ double2 ring_smem[];
+    const RingSmem<NT> S(ring_smem);
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * NT + tid;
+    const bool live = t < R.count;
     const int i = R.first + t;
-    const R8 row = ldrow(mv.ring8, i);
-    if (!(row.v[0] == TM_RING_GENERIC || row_has_boundary_spoke(row))) return;
-    const double fC = 2.0 * P.kappa_c / P.ref_curvature * (sums[2] / P.ref_curvature - 1.0);
+    const int tile0 = R.first + blockIdx.x * NT;
+    const int tile_n = min(NT, mv.V - tile0);
+    P4 ri;
+    ri.x = ri.y = ri.z = ri.w = 0.0;
+    if (tid < tile_n) {
+        ri = ldrec(mv.pos, tile0 + tid);
+        S.xy[tid] = make_double2(ri.x, ri.y);
+        S.zr[tid] = make_double2(ri.z, ri.w);
+    }
+    R8 row;
+    row.v[0] = TM_RING_GENERIC;
+    int d = 0;
+    int idx[9];
+    // the slot quantities of the property sweep, staged beside the ring records: [slot][thread]
+    double2* saux = ring_smem + 2 * (1 + RING_KS) * NT + tid;
+    if (live) {
+        row = ldrow(mv.ring8, i);
+        if (row.v[0] != TM_RING_GENERIC) {
+            d = row_valence(row);
+            stage_ring<NT>(S, mv.pos, row, d, tile0, tile_n, idx);
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < 3 || s < d) cp_async16(saux + s * NT, mv.aux + (size_t)s * mv.aux_vs + i);
+            if (UPD > 0) {
+                // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live || row.v[0] == TM_RING_GENERIC) return;
+    double fA, fV, fC;
+    penalty_factors(P, sums, fA, fV, fC);
+    GradC K;
+    K.kb = P.kappa_b; K.kt = P.kappa_t;
+    K.W0 = fma(2.0 * K.kb, ri.w, 0.5 * fC);       // W_s = W0 - kb (rho_i - rho_s)
+    K.c3 = K.kb * (1.0 / 3.0);
+    K.U0h = fma(-K.c3, ri.w * ri.w, 0.5 * fA);
+    K.fV6 = fV * (1.0 / 6.0);
+    const d3 g = ring_grad_closed<NT>(mv, P, K, S, saux, idx, d, i, mk3(ri.x, ri.y, ri.z), ri.w);
+    grad_finish<UPD>(P, i, ri, g, force, grad, U);
+}
+
+// The vertices of `list` inside [R.first, R.first + R.count): valence > 8 or < 3, and the boundary vertices
+// of open meshes, including the reference's boundary-spoke terms (boundary_spoke_terms above).
+template <int UPD>
+__global__ void __launch_bounds__(128)
+k_grad_generic(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
+               double* __restrict__ grad, const int* __restrict__ list, int n, SweepRange R, VVFuse U) {
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n) return;
+    const int i = list[t];
+    if (i < R.first || i >= R.first + R.count) return;
     const P4 ri = ldrec(mv.pos, i);
-    d3 g = mk3(0, 0, 0);
-    boundary_spoke_terms(mv, fC, P.kappa_b, i, mk3(ri.x, ri.y, ri.z), ri.w, g);
-    double* o = grad + 3 * (size_t)i;
-    o[0] += g.x; o[1] += g.y; o[2] += g.z;
+    const d3 xi = mk3(ri.x, ri.y, ri.z);
+    GradK K;
+    penalty_factors(P, sums, K.fA, K.fV, K.fC);
+    K.kb = P.kappa_b; K.kt = P.kappa_t;
+    d3 g = mk3(0, 0, 0), nsum = mk3(0, 0, 0), esum = mk3(0, 0, 0);
+    ring_grad_generic(mv, P, K, i, xi, ri.w, g, nsum, esum);
+    // volume: sum_f (x_j x x_k)/6 = (sum_f n_f + x_i x sum_f (e_{s-1} - e_s))/6
+    axpy3(g, K.fV / 6.0, nsum + cross3(xi, esum));
+    boundary_spoke_terms(mv, K.fC, K.kb, i, xi, ri.w, g);
+    grad_finish<UPD>(P, i, ri, g, force, grad, U);
 }
 
 }  // namespace
@@ -913,6 +1250,27 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
         TM_CUDA(cudaEventRecord(m->ev_fork, m->stream));
         TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
         st = m->stream2;
+    }
+    if (nl.kind == TM_NLIST_VERLET && nl.tile_T == TM_TILE && !write_vprops && R.first == 0 && R.count == m->V) {
+        // tile lists: one block per tile, the tile's and its halo's records in shared memory
+        const size_t bytes = sizeof(double) * (3 * (size_t)(TM_TILE + nl.tile_hmax) + (size_t)nl.tile_slmax);
+        const int nt = (m->V + TM_TILE - 1) / TM_TILE;
+        const bool r2t = p.rep_r == 2;
+#define TM_PT(E, R2) do { \
+        TM_CUDA(cudaFuncSetAttribute(k_pairs_tile<E, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+        k_pairs_tile<E, R2><<<nt, TM_TILE, bytes, st>>>(mv, nl, p.rep_lc1, p.rep_r, nl.tile_hmax, m->frep, m->partials, nwarps); } while (0)
+        if (with_e) { if (r2t) TM_PT(true, true); else TM_PT(true, false); }
+        else { if (r2t) TM_PT(false, true); else TM_PT(false, false); }
+#undef TM_PT
+        TM_LAUNCHED();
+        TM_CUDA(cudaGetLastError());
+        if (beside) {
+            TM_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+            m->pairs_inflight = true;
+        }
+        m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
+        m->frep_list = nl.serial;
+        return 0;
     }
     const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * (PAIR_QCAP + PAIR_XCAP) * PAIR_THREADS : 0;
     if (nl.kind == TM_NLIST_CELL && !(m->cellrec_epoch == m->pos_epoch && m->cellrec_list == nl.serial)) {
@@ -948,19 +1306,47 @@ int tm_join_pairs(tm_mesh* m) {
     return 0;
 }
 
-int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
-    if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
-    const SweepRange R = tm_owned_range(m);
-    const int nb = (R.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
-    const int nwarps = (R.count + 31) / 32;
-    const size_t need = 6 * (size_t)nwarps + 6 * TM_REDUCE_BLOCKS;
+// dynamic shared memory of the ring sweeps (tile + staging columns); above 48 KB it must be opted into, once
+static const size_t PROPS_SMEM = RingSmem<TM_PROPS_THREADS>::bytes(),
+                    GRAD_SMEM = RingSmem<TM_GRAD_THREADS>::bytes() + sizeof(double2) * 8 * TM_GRAD_THREADS;
+static int ring_smem_optin() {
+    static std::atomic<bool> done{false};
+    if (done.load()) return 0;
+#define TM_OPTIN(k, n) TM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n)))
+    TM_OPTIN((k_props<true, true, false>), PROPS_SMEM); TM_OPTIN((k_props<true, false, false>), PROPS_SMEM);
+    TM_OPTIN((k_props<false, false, false>), PROPS_SMEM); TM_OPTIN((k_props<false, false, true>), PROPS_SMEM);
+    TM_OPTIN(k_grad<0>, GRAD_SMEM); TM_OPTIN(k_grad<1>, GRAD_SMEM); TM_OPTIN(k_grad<2>, GRAD_SMEM);
+#undef TM_OPTIN
+    done.store(true);
+    return 0;
+}
+
+// warp partials of the largest sweep (whole mesh + its generic vertices) and the slot quantities the property
+// sweep hands to the gradient sweep; sized for the whole mesh so that a partitioned mesh never reallocates
+// (cudaFree synchronises the device) while a peer waits on the device
+int tm_props_workspace(tm_mesh* m) {
+    if (ring_smem_optin()) return 1;
+    const size_t need = 12 * (size_t)((m->V + 31) / 32) + 6 * TM_REDUCE_BLOCKS;     // (n_generic <= V)
     if (m->partials_n < need) {
         if (m->partials) cudaFree(m->partials);
         m->partials = nullptr; m->partials_n = 0;
         TM_CUDA(cudaMalloc(&m->partials, need * sizeof(double)));
         m->partials_n = need;
     }
-    double* block_sums = m->partials + 6 * (size_t)nwarps;
+    if (!m->aux) TM_CUDA(cudaMalloc(&m->aux, sizeof(double2) * 8 * (size_t)((m->V + 31) & ~31)));
+    return 0;
+}
+
+int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool full, bool write_vprops) {
+    if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
+    const SweepRange R = tm_owned_range(m);
+    const int nb = (R.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS;
+    const int nwarps = (R.count + 31) / 32;
+    // warp partials: the closed-fan sweep's columns, then those of the generic-vertex sweep
+    const int ngen = m->n_generic, gen_warps = (ngen + 31) / 32;
+    const int ncols = nwarps + gen_warps;
+    if (tm_props_workspace(m)) return 1;
+    double* block_sums = m->partials + 6 * (size_t)ncols;
     DevParams P = tm_to_dev(p);
     MeshView mv = m->view();
     // the repulsion sum is wanted whenever lc1 > 0, whatever kappa_r is (mesh_properties.cpp:46)
@@ -975,36 +1361,45 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
         if (!m->vprops) TM_CUDA(cudaMalloc(&m->vprops, sizeof(double) * 6 * (size_t)m->V));
         TM_CUDA(cudaMemsetAsync(m->vprops, 0, sizeof(double) * 6 * (size_t)m->V, m->stream));
     }
-    if (pairs && launch_pairs(m, nl, p, true, write_vprops, nwarps, true)) return 1;
+    if (pairs && launch_pairs(m, nl, p, true, write_vprops, ncols, true)) return 1;
     if (pairs_for_grad && launch_pairs(m, nl, p, false, false, 0, true)) return 1;
     if (nb <= 0) {
         // a rank of a tiny partitioned mesh may own nothing: it still takes part in the reduction / exchange
     } else if (write_vprops) {
-        k_props<true, true><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, nwarps, nq, R);
+        k_props<true, true, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, ncols, nq, R, 1);
     } else if (full) {
-        k_props<true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
+        k_props<true, false, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R, 1);
     } else {
-        k_props<false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, nwarps, nq, R);
+        k_props<false, false, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R, 1);
     }
     TM_LAUNCHED();
+    if (ngen > 0) {
+        // vertices without a fixed-width row; their columns carry all six quantities (repulsion = 0)
+        const int gb = (ngen + 127) / 128;
+        if (write_vprops) k_props_generic<true, true><<<gb, 128, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, ncols, nwarps, 6, m->gen_list, ngen, R);
+        else if (full) k_props_generic<true, false><<<gb, 128, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nwarps, 6, m->gen_list, ngen, R);
+        else k_props_generic<false, false><<<gb, 128, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nwarps, 6, m->gen_list, ngen, R);
+        TM_LAUNCHED();
+    }
     // partitioned mesh: rho of the non-owned ring neighbours of owned vertices (the gradient
     // sweep reads it) from a second, list-driven launch that reduces nothing
     const SweepRange G = tm_ghost_range(m);
     if (G.count > 0) {
-        k_props<false, false><<<(G.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS, TM_PROPS_THREADS, 0, m->stream>>>(
-            mv, P, m->pos, nullptr, m->partials, 0, 0, G);
+        k_props<false, false, true><<<(G.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(
+            mv, P, m->pos, nullptr, m->partials, 0, 0, G, 0);
         TM_LAUNCHED();
     }
     if (pairs && tm_join_pairs(m)) return 1;            // the reduction adds the pair sweep's partials
-    int rb = (nwarps + 4 * RT - 1) / (4 * RT);
+    int rb = (ncols + 4 * RT - 1) / (4 * RT);
     rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
-    const int per = (nwarps + rb - 1) / rb;
-    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, nwarps, per, full ? 6 : 4, block_sums, m->ticket,
+    const int per = (ncols + rb - 1) / rb;
+    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, ncols, per, full ? 6 : 4, block_sums, m->ticket,
                                             tm_part_local_sums(m));
     TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     if (tm_part_exchange_sums(m, full ? 6 : 4)) return 1;
-    m->geo_epoch = m->pos_epoch;        // sums[0..2] and rho now belong to the current positions
+    m->geo_epoch = m->pos_epoch;        // sums[0..2], rho and the slot quantities now belong to the current positions
+    m->sums_full = full;                // a geometry-only sweep leaves sums[4..5] = 0
     return 0;
 }
 
@@ -1014,28 +1409,38 @@ int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
     return launch_pairs(m, nl, p, false, false, 0);
 }
 
+// the ring gradient of the vertices of R on stream st: the closed-fan sweep, then the generic vertices if any
+static int launch_grad_kernels(tm_mesh* m, const DevParams& P, const double* frc, const SweepRange& R, const VVFuse& U,
+                               cudaStream_t st) {
+    if (ring_smem_optin()) return 1;
+    const int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
+    const MeshView mv = m->view();
+    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    else k_grad<0><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    TM_LAUNCHED();
+    if (m->n_generic > 0) {
+        const int gb = (m->n_generic + 127) / 128;
+        if (U.mode == 2) k_grad_generic<2><<<gb, 128, 0, st>>>(mv, P, m->sums, frc, m->grad, m->gen_list, m->n_generic, R, U);
+        else if (U.mode == 1) k_grad_generic<1><<<gb, 128, 0, st>>>(mv, P, m->sums, frc, m->grad, m->gen_list, m->n_generic, R, U);
+        else k_grad_generic<0><<<gb, 128, 0, st>>>(mv, P, m->sums, frc, m->grad, m->gen_list, m->n_generic, R, U);
+        TM_LAUNCHED();
+    }
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p, const VVFuse* fuse) {
     if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
     if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
     if (tm_join_pairs(m)) return 1;
     const SweepRange R = tm_owned_range(m);
-    int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
-    DevParams P = tm_to_dev(p);
     VVFuse U;
     memset(&U, 0, sizeof(U));
     if (fuse) U = *fuse;
-    const double* frc = pairs ? m->frep : nullptr;
     if (R.count <= 0) { m->grad_epoch = m->pos_epoch; return 0; }       // a rank of a tiny partitioned mesh may own nothing
-    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
-    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
-    else k_grad<0><<<nb, TM_GRAD_THREADS, 0, m->stream>>>(m->view(), P, m->sums, frc, m->grad, R, U);
-    TM_LAUNCHED();
-    if (m->has_boundary) {
-        // (callers do not fuse the update into the sweep on such meshes: U.mode == 0)
-        k_grad_boundary<<<(R.count + 127) / 128, 128, 0, m->stream>>>(m->view(), P, m->sums, m->grad, R); TM_LAUNCHED();
-    }
-    TM_CUDA(cudaGetLastError());
+    if (launch_grad_kernels(m, tm_to_dev(p), pairs ? m->frep : nullptr, R, U, m->stream)) return 1;
     m->grad_epoch = m->pos_epoch;
     return 0;
 }
@@ -1052,14 +1457,9 @@ int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_par
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
     SweepRange R;
     R.first = 0; R.count = m->V; R.vlist = nullptr;
-    const int nb = (m->V + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     VVFuse U;
     memset(&U, 0, sizeof(U));
-    k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(m->view(), tm_to_dev(p), m->sums, pairs ? m->frep : nullptr, m->grad, R, U);
-    TM_LAUNCHED();
-    if (m->has_boundary) {
-        k_grad_boundary<<<(m->V + 127) / 128, 128, 0, st>>>(m->view(), tm_to_dev(p), m->sums, m->grad, R); TM_LAUNCHED();
-    }
+    if (launch_grad_kernels(m, tm_to_dev(p), pairs ? m->frep : nullptr, R, U, st)) return 1;
     k_export_grad<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, m->grad, m->d2h, m->xout3); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     TM_CUDA(cudaMemcpyAsync(grad_host, m->xout3, sizeof(double) * 3 * (size_t)m->V, cudaMemcpyDeviceToHost, st));
@@ -1067,14 +1467,17 @@ int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_par
 }
 
 int tm_preload_energy() {
-    TM_PRELOAD((k_props<true, true>)); TM_PRELOAD((k_props<true, false>)); TM_PRELOAD((k_props<false, false>));
+    TM_PRELOAD((k_props<true, true, false>)); TM_PRELOAD((k_props<true, false, false>)); TM_PRELOAD((k_props<false, false, false>));
+    TM_PRELOAD((k_props<false, false, true>));
+    TM_PRELOAD((k_props_generic<true, true>)); TM_PRELOAD((k_props_generic<true, false>)); TM_PRELOAD((k_props_generic<false, false>));
+    TM_PRELOAD(k_grad_generic<0>); TM_PRELOAD(k_grad_generic<1>); TM_PRELOAD(k_grad_generic<2>);
 #define TM_PL(CL) \
     TM_PRELOAD((k_pairs<true, true, true, true, CL>)); TM_PRELOAD((k_pairs<true, true, true, false, CL>)); \
     TM_PRELOAD((k_pairs<true, true, false, true, CL>)); TM_PRELOAD((k_pairs<true, true, false, false, CL>)); \
     TM_PRELOAD((k_pairs<false, true, false, true, CL>)); TM_PRELOAD((k_pairs<false, true, false, false, CL>))
     TM_PL(false); TM_PL(true);
 #undef TM_PL
-    TM_PRELOAD(k_cell_gather); TM_PRELOAD(k_export_grad); TM_PRELOAD(k_grad_boundary);
+    TM_PRELOAD(k_cell_gather); TM_PRELOAD(k_export_grad);
     TM_PRELOAD(k_reduce_props); TM_PRELOAD(k_grad<0>); TM_PRELOAD(k_grad<1>); TM_PRELOAD(k_grad<2>);
     return 0;
 }

@@ -401,9 +401,10 @@ int tm_flips_release(tm_mesh* m) {
 
 extern "C" {
 
-int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode, int n,
-                  const int* edges, const double* u, int* n_accepted, int* n_flips, int* flipped,
-                  double props_io[6]) {
+// `mutated` is set as soon as a kernel that may change the device connectivity has been enqueued
+static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode, int n,
+                           const int* edges, const double* u, int* n_accepted, int* n_flips, int* flipped,
+                           double props_io[6], bool* mutated) {
     if (check(m, p)) return 1;
     TM_CHECK(mode == TM_FLIP_SERIAL || mode == TM_FLIP_BATCH, "unknown flip mode %d", mode);
     TM_CHECK(n >= 0 && props_io && n_accepted, "bad arguments");
@@ -434,6 +435,7 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     TM_CUDA(cudaMemcpyAsync(ws->state, props_io, sizeof(double) * 6, cudaMemcpyHostToDevice, st));
     TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, st));
     int hc[4] = {0, 0, 0, 0};
+    *mutated = true;
 
     if (mode == TM_FLIP_SERIAL) {
         k_flip_serial<<<1, 32, 0, st>>>(mv, t, nv, P, n, ws->edges, ws->u, ws->state, ws->flips, ws->counters);
@@ -465,16 +467,30 @@ int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode,
     TM_CUDA(cudaMemcpyAsync(hc, ws->counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
     TM_CUDA(cudaMemcpyAsync(props_io, ws->state, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
     TM_CUDA(cudaStreamSynchronize(st));
-    m->rings_valid = false;                 // connectivity changed: the ring table is rebuilt lazily,
-    m->raw_stale = true;                    // the host-numbered copies on request,
-    m->pos_epoch++;                         // and cached per-vertex properties are void
-    m->topo_epoch++;
     TM_CHECK(hc[3] == 0, "flip sweep met a vertex of valence > %d", MAXV);
     if (flipped && hc[1] > 0)
         TM_CUDA(cudaMemcpy(flipped, ws->flips, sizeof(int) * hc[1], cudaMemcpyDeviceToHost));
     if (n_flips) *n_flips = hc[1];
     *n_accepted = hc[2];
     return 0;
+}
+
+int tm_flip_sweep(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int mode, int n,
+                  const int* edges, const double* u, int* n_accepted, int* n_flips, int* flipped,
+                  double props_io[6]) {
+    bool mutated = false;
+    const int rc = flip_sweep_body(m, nl, p, mode, n, edges, u, n_accepted, n_flips, flipped, props_io, &mutated);
+    if (mutated) {
+        // Success or failure: the connectivity on the device is no longer what the derived tables describe.
+        // (After a FAILED sweep it is a half-finished one: the caller must upload its own connectivity again
+        // with tm_mesh_set_topology before the next evaluation -- the host classes do, energy_manager.cpp.)
+        cudaStreamSynchronize(m->stream);
+        m->rings_valid = false;                 // the ring table is rebuilt lazily,
+        m->raw_stale = true;                    // the host-numbered copies on request,
+        m->pos_epoch++;                         // and cached per-vertex properties are void
+        m->topo_epoch++;
+    }
+    return rc;
 }
 
 int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int edge, double out[6]) {

@@ -52,30 +52,42 @@ __device__ __forceinline__ double exp_nonpos(double t) {
 //   atan q = atan c + atan r,  r = (q - c)/(1 + q c) = (mn - c mx)/(mx + c mn),  |r| <= 1/8 (+1e-6)
 //   -> odd series to r^17.
 // c only selects the interval, so it is taken from a 20-bit estimate of q (the MUFU seed alone, no Newton
-// steps), and r needs ONE full-precision reciprocal instead of two: 11 dependent fp64 operations before the
-// polynomial instead of 16 (the sweeps are bound by exactly this kind of dependent latency).
+// steps), and r needs ONE full-precision reciprocal. The octant bookkeeping (swap of the arguments,
+// x < 0) and atan c are folded into one table: with o = swap + 2 (x < 0) the result is
+//   ATAN_T[o][k] + sigma atan r,  sigma = -1 for o = 1, 2  (atan is odd: the sign goes onto r),
+// one indexed constant load instead of a chain of selects. max(|x|,|y|) is offset by 1e-300, which is
+// invisible for normal arguments and makes x = y = 0 come out as atan2(0, +-0) without a guard.
+// ~25 fp64 operations, no branch.
+static __constant__ double ATAN_T[32] = {
+    // o = 0: atan c                       (k = 0 .. 4; 3 pad entries per row)
+    0.0, 0.24497866312686414, 0.46364760900080615, 0.6435011087932844, 0.7853981633974483, 0, 0, 0,
+    // o = 1: pi/2 - atan c
+    1.5707963267948966, 1.3258176636680326, 1.1071487177940904, 0.9272952180016122, 0.7853981633974483, 0, 0, 0,
+    // o = 2: pi - atan c
+    3.141592653589793, 2.896613990462929, 2.677945044588987, 2.498091544796509, 2.356194490192345, 0, 0, 0,
+    // o = 3: pi/2 + atan c
+    1.5707963267948966, 1.8157749899217608, 2.0344439357957027, 2.214297435588181, 2.356194490192345, 0, 0, 0};
+
 __device__ __forceinline__ double atan2_fast(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
-    const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+    const double mx = (swap ? ay : ax) + 1.0e-300, mn = swap ? ax : ay;
     double seed;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(mx));
     const double M = 1688849860263936.0;                     // 1.5 * 2^50: ulp = 1/4
     const double t = fma(mn, seed, M);
-    const int k = __double2loint(t) & 7;                     // 0 .. 4
     const double c = t - M;
-    const double r = fma(-c, mx, mn) * rcp_pos(fma(c, mn, mx));
+    const unsigned neg = (unsigned)__double2hiint(x) >> 31;
+    const unsigned o = (swap ? 1u : 0u) | (neg << 1);
+    const unsigned idx = (o << 3) | ((unsigned)__double2loint(t) & 7u);      // k = 0 .. 4
+    double r = fma(-c, mx, mn) * rcp_pos(fma(c, mn, mx));
+    // sigma = -1 for o = 1, 2
+    r = __hiloint2double(__double2hiint(r) ^ (int)(((o ^ (o >> 1)) & 1u) << 31), __double2loint(r));
     const double s = r * r;
     double p = ATAN_C[0];
 #pragma unroll
     for (int i = 1; i < 8; i++) p = fma(p, s, ATAN_C[i]);
-    double a = fma(r * s, p, r);
-    const double ak = k == 0 ? 0.0 : k == 1 ? 0.24497866312686414 : k == 2 ? 0.46364760900080615
-                    : k == 3 ? 0.6435011087932844 : 0.7853981633974483;
-    a += ak;
-    a = swap ? 1.5707963267948966 - a : a;
-    a = __double2hiint(x) < 0 ? 3.141592653589793 - a : a;
-    a = mx > 0.0 ? a : 0.0;
+    const double a = fma(r * s, p, r) + ATAN_T[idx];
     return copysign(a, y);
 }
 

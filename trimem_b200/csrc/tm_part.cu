@@ -462,13 +462,7 @@ int tm_part_prepare(tm_mesh* m, tm_nlist* nl) {
     if (!m->h_stats) TM_CUDA(cudaHostAlloc(&m->h_stats, 16 * sizeof(double), cudaHostAllocDefault));
     if (!m->dot_part) TM_CUDA(cudaMalloc(&m->dot_part, 1024 * sizeof(double)));
     if (!m->d_stats) TM_CUDA(cudaMalloc(&m->d_stats, 16 * sizeof(double)));
-    const size_t need = 6 * (size_t)((m->V + 31) / 32) + 6 * TM_REDUCE_BLOCKS;
-    if (m->partials_n < need) {
-        if (m->partials) cudaFree(m->partials);
-        m->partials = nullptr; m->partials_n = 0;
-        TM_CUDA(cudaMalloc(&m->partials, need * sizeof(double)));
-        m->partials_n = need;
-    }
+    if (tm_props_workspace(m)) return 1;
     TM_CUDA(cudaStreamSynchronize(m->stream));
     return 0;
 }

@@ -29,7 +29,8 @@ __global__ void k_ring_count(int V, const int* __restrict__ v_he,
 
 __global__ void k_ring_fill(int V, const int* __restrict__ v_he, const int* __restrict__ he_next,
                             const int* __restrict__ he_to, const int* __restrict__ he_face,
-                            const int* __restrict__ off, int* __restrict__ ring_v, R8* __restrict__ ring8) {
+                            const int* __restrict__ off, int* __restrict__ ring_v, R8* __restrict__ ring8,
+                            int* __restrict__ is_generic) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;
     R8 row;
@@ -37,20 +38,32 @@ __global__ void k_ring_fill(int V, const int* __restrict__ v_he, const int* __re
     for (int k = 0; k < 8; k++) row.v[k] = TM_RING_PAD;
     int h0 = v_he[i];
     int o = off[i], end = off[i + 1], h = h0, n = 0;
+    bool closed = true;
     if (h0 >= 0) {
         do {
-            int v = he_to[h];
-            if (he_face[h] >= 0) v |= TM_RING_FACE;
-            if (he_face[h ^ 1] >= 0) v |= TM_RING_OFACE;
+            const int to = he_to[h];
+            int v = to;
+            if (he_face[h] >= 0) v |= TM_RING_FACE; else closed = false;
+            if (he_face[h ^ 1] >= 0) v |= TM_RING_OFACE; else closed = false;
             ring_v[o++] = v;
 #pragma unroll
-            for (int k = 0; k < 8; k++) if (k == n) row.v[k] = v;
+            for (int k = 0; k < 8; k++) if (k == n) row.v[k] = to;
             ++n;
             h = he_next[h ^ 1];
         } while (h != h0 && o < end);
     }
-    if (n > 8 || (n > 0 && n < 3)) row.v[0] = TM_RING_GENERIC;
+    // the fixed-width row serves the closed-fan sweeps only (tm_energy.cu)
+    const bool generic = n > 8 || n < 3 || !closed;
+    if (generic) row.v[0] = TM_RING_GENERIC;
     ring8[i] = row;
+    is_generic[i] = generic ? 1 : 0;
+}
+
+// ascending list of the vertices without a fixed-width row (off = exclusive scan of the flags)
+__global__ void k_generic_list(int V, const R8* __restrict__ ring8, const int* __restrict__ off, int* __restrict__ list) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    if (ring8[i].v[0] == TM_RING_GENERIC) list[off[i]] = i;
 }
 
 // --- sorted two-ring rows ------------------------------------------------------------------
@@ -215,7 +228,18 @@ int tm_ensure_rings(tm_mesh* m) {
     TM_CHECK(total <= m->HE, "one-ring walk visited %lld half-edges but the mesh has %d "
              "(non-manifold vertex or corrupt connectivity)", total, m->HE);
     k_ring_fill<<<nb, 256, 0, m->stream>>>(m->V, m->v_he, m->he_next, m->he_to, m->he_face,
-                                          m->ring_off, m->ring_v, m->ring8); TM_LAUNCHED();
+                                          m->ring_off, m->ring_v, m->ring8, m->ring_cnt); TM_LAUNCHED();
+    // the vertices the closed-fan sweeps skip (valence > 8 or < 3, boundary vertices of open meshes), in
+    // ascending order: the sweeps' generic kernels run over this list and only when it is not empty
+    long long ngen = 0;
+    if (tm_exclusive_scan(m, m->ring_cnt, m->ring_cnt, m->V, &ngen)) return 1;     // syncs the stream
+    if (m->gen_list) { tm_pool_free(m->device, m->gen_list); m->gen_list = nullptr; }
+    m->n_generic = (int)ngen;
+    if (ngen > 0) {
+        m->gen_list = (int*)tm_pool_alloc(m->device, sizeof(int) * (size_t)ngen);
+        TM_CHECK(m->gen_list != nullptr, "out of device memory for the generic-vertex list");
+        k_generic_list<<<nb, 256, 0, m->stream>>>(m->V, m->ring8, m->ring_cnt, m->gen_list); TM_LAUNCHED();
+    }
     TM_CUDA(cudaGetLastError());
     m->rings_valid = true;
     return 0;

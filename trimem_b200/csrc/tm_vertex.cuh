@@ -16,6 +16,8 @@ struct DevParams {
     int bond_r, bond_type;
     double rep_lc1;
     int rep_r;
+    // derived on the host once per launch (the sweeps multiply instead of dividing)
+    double inv_ref_area, inv_ref_volume, inv_ref_curvature, inv_a0, lc0sq, lc1sq;
 };
 
 inline DevParams tm_to_dev(const tm_energy_params& p) {
@@ -26,6 +28,9 @@ inline DevParams tm_to_dev(const tm_energy_params& p) {
     P.lc0 = p.bond_lc0; P.lc1 = p.bond_lc1; P.a0 = p.bond_a0;
     P.bond_r = p.bond_r; P.bond_type = p.bond_type;
     P.rep_lc1 = p.rep_lc1; P.rep_r = p.rep_r;
+    P.inv_ref_area = 1.0 / p.ref_area; P.inv_ref_volume = 1.0 / p.ref_volume;
+    P.inv_ref_curvature = 1.0 / p.ref_curvature; P.inv_a0 = 1.0 / p.bond_a0;
+    P.lc0sq = p.bond_lc0 * p.bond_lc0; P.lc1sq = p.bond_lc1 * p.bond_lc1;
     return P;
 }
 
