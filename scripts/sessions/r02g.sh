@@ -1,0 +1,20 @@
+#!/bin/bash
+# round 2, GPU session G: table exponential in the pair sweep, L1 prefetch, launch shapes; first full bench
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02g_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02g_tests.log
+tail -5 gpurun_out/r02g_tests.log
+: > gpurun_out/r02g_kernels.jsonl
+timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02g_kernels.jsonl 2>gpurun_out/r02g_kb.err
+for v in pf pfg6 g6 pm5 pm5b6 pb6 pm6b3; do
+  TRIMEM_B200_LIB=trimem_b200/lib/variants/$v.so timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02g_kernels.jsonl 2>>gpurun_out/r02g_kb.err
+done
+cat gpurun_out/r02g_kernels.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['lib'][-12:], {k: d[k] for k in d if k.endswith('_us') or k.endswith('_ms')}, d['E'], d['gnorm'])
+"
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02g_bench.json 2> gpurun_out/r02g_bench.err; python - <<'PY'
+import json
+d = json.load(open('gpurun_out/r02g_bench.json'))
+print({k: d[k] for k in ('value', 'ms_per_step', 'e2e', 'roofline')})
+PY

@@ -37,6 +37,12 @@ CASES = {
     "ico8_stress_verlet2": ("jittered_icosphere", (8,), dict(repulsion="stress", n_search="verlet-list", exclusion=2)),
     "ico8_norep": ("jittered_icosphere", (8,), dict(repulsion="none", n_search="verlet-list", exclusion=2)),
 }
+# BASELINE config 4 (10,485,762 vertices): golden made on request only (make_golden.py big; ~5 minutes of the
+# reference on 8 threads), never built by the CPU tests (BIG_CASES are kept out of CASES)
+BIG_CASES = {
+    "ico10_stress_verlet2": ("jittered_icosphere", (10,), dict(repulsion="stress", n_search="verlet-list", exclusion=2)),
+}
+N_SAMPLED_ROWS_BIG = 4096
 FULL_GRADIENT_MAX_V = 3000      # cases up to this size store the whole gradient
 N_SAMPLED_ROWS = 512
 
@@ -56,9 +62,9 @@ def build(mod, case):
     return mesh, mod.EnergyManager(mesh, ep)
 
 
-def sample_rows(n_vertices):
+def sample_rows(n_vertices, n=None):
     rng = np.random.default_rng(7)
-    return np.sort(rng.choice(n_vertices, size=min(N_SAMPLED_ROWS, n_vertices), replace=False))
+    return np.sort(rng.choice(n_vertices, size=min(n or N_SAMPLED_ROWS, n_vertices), replace=False))
 
 
 def props6(p):

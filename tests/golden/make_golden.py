@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import trimem.core as ref          # noqa: E402
 import refprobe                    # noqa: E402
 import cases                       # noqa: E402
-from trimem_b200 import meshgen    # noqa: E402
+from trimem_b200 import meshgen, workload    # noqa: E402
 
 
 def save(name, **arrays):
@@ -59,6 +59,26 @@ def energy_cases():
         if V <= cases.FULL_GRADIENT_MAX_V:
             out["pair_keys"] = key
         save(name, **out)
+
+
+def big_case():
+    """BASELINE config 4: the 10,485,762-vertex mesh on the reference (six sums, energy, 4,096 sampled gradient rows,
+    gradient sum and norm, pair count). Run with OMP_NUM_THREADS=8; ~5 minutes and ~8 GB."""
+    import time
+    for name, (gen, args, kw) in cases.BIG_CASES.items():
+        t0 = time.time()
+        v, f = getattr(meshgen, gen)(*args)
+        mesh = ref.TriMesh(v, f)
+        es = ref.EnergyManager(mesh, workload.energy_params(ref, mesh, **kw))
+        V = mesh.n_vertices()
+        print(name, "built", V, "vertices in", time.time() - t0, "s", flush=True)
+        props = cases.props6(es.properties(mesh))
+        energy = es.energy(mesh)
+        grad = es.gradient(mesh)
+        rows = cases.sample_rows(V, cases.N_SAMPLED_ROWS_BIG)
+        save(name, n_vertices=V, props=props, energy=energy, grad_norm=np.linalg.norm(grad), grad_sum=grad.sum(axis=0),
+             rows=rows, grad_rows=grad[rows], initial_props=cases.props6(es.initial_props))
+        print(name, "done in", time.time() - t0, "s")
 
 
 def neighbour_cases():
@@ -357,3 +377,4 @@ if __name__ == "__main__":
     if "hmc" in which: hmc_chain_cases()
     if "open" in which: open_mesh_cases()
     if "flipstats" in which: flip_statistics()
+    if "big" in which: big_case()

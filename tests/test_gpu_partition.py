@@ -257,3 +257,57 @@ def test_open_mesh_area_bond(gpu_core):
     e, g = es.energy(mesh), es.gradient(mesh)
     assert abs(e - float(gold["rect_area_energy"])) <= TOL * abs(e)
     assert nrm(g, gold["rect_area_grad"]) < 1e-9
+
+
+def test_partition_through_the_drop_in_classes(gpu_core):
+    """core.TriMesh.part_* / EnergyManager.part_prepare: two ranks as two TriMesh / EnergyManager pairs of one
+    process (one host thread per rank; the bindings release the interpreter lock around device work), evaluated
+    through the same calls a trimem user makes, plus one MeshHMC move; against the unpartitioned results."""
+    from trimem_b200 import hmc
+    m, n = gpu_core, 2
+    name = "vv_ico4_stress_verlet2"
+    case, p0, mass, dt, nsteps = cases.vv_inputs(name)
+    mesh1, es1 = cases.build(m, case)
+    e1, g1 = es1.energy(mesh1), es1.gradient(mesh1)
+    x1, pn1, st1 = m.vv_integrate(mesh1, es1, p0, mass, dt, nsteps)
+    pairs = [cases.build(m, case) for _ in range(n)]
+    for r, (mesh, es) in enumerate(pairs):
+        mesh.part_create(r, n)
+    for r, (mesh, es) in enumerate(pairs):
+        for q, (other, _) in enumerate(pairs):
+            if q != r:
+                mesh.part_attach_local(q, other)
+    for mesh, es in pairs:
+        es.part_prepare(mesh)
+    info = [mesh.part_info() for mesh, _ in pairs]
+    assert sum(i["count"] for i in info) == mesh1.n_vertices() and info[1]["rank"] == 1
+
+    def each(fn):
+        import threading
+        out, err = [None] * n, [None] * n
+
+        def run(r):
+            try:
+                out[r] = fn(*pairs[r])
+            except BaseException as exc:      # noqa: BLE001
+                err[r] = exc
+        th = [threading.Thread(target=run, args=(r,)) for r in range(n)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+    res = each(lambda mesh, es: (es.energy(mesh), es.gradient(mesh)))
+    assert res[0][0] == res[1][0] and abs(res[0][0] - e1) <= 1e-13 * abs(e1)
+    assert nrm(res[0][1] + res[1][1], g1) < 1e-13            # every rank delivers the rows it owns, zeros elsewhere
+    traj = each(lambda mesh, es: m.vv_integrate(mesh, es, p0, mass, dt, nsteps))
+    assert np.array_equal(traj[0][0], traj[1][0]) and nrm(traj[0][0] - mesh1.points(), x1 - mesh1.points()) < 1e-12
+    assert nrm(traj[0][1] + traj[1][1], pn1) < 1e-12
+    # potential energies are global sums (same on every rank); a rank's kinetic energy covers the rows it owns
+    assert abs(traj[0][2][2] - st1[2]) <= 1e-12 * abs(st1[2]) and traj[0][2][2] == traj[1][2][2]
+    assert abs(traj[0][2][3] + traj[1][2][3] - st1[3]) <= 1e-12 * abs(st1[3])
+    # collective list rebuild through the manager
+    each(lambda mesh, es: es.update_repulsion(mesh))
+    res2 = each(lambda mesh, es: es.energy(mesh))
+    assert res2[0] == res2[1] and abs(res2[0] - e1) <= 1e-13 * abs(e1)

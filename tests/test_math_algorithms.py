@@ -90,3 +90,19 @@ def test_rsqrt_rcp_refinement_accuracy():
     e = 1.0 - (x * y) * y
     y = y + (y * e) * (0.375 * e + 0.5)
     assert np.max(np.abs(y * np.sqrt(x) - 1.0)) < 5e-16
+
+
+def test_exp_table_algorithm_accuracy():
+    """exp_tab (tm_math.cuh): 2^(j/64) table + degree-5 polynomial, the pair sweep's exponential."""
+    tab = 2.0 ** (np.arange(64) / 64.0)
+    t = -10.0 ** np.random.default_rng(3).uniform(-8, np.log10(700.0), 300000)
+    kd = np.rint(t * 92.33248261689366)
+    k = kd.astype(np.int64)
+    r = (t - kd * 0.010830424609594047) - kd * 8.66550983900947e-11
+    assert np.max(np.abs(r)) < 0.0055
+    p = r * 8.3333333333333332e-03 + 4.1666666666666664e-02
+    for c in (1.6666666666666666e-01, 0.5, 1.0, 1.0):
+        p = p * r + c
+    got = np.ldexp(p * tab[k & 63], (k >> 6).astype(int))
+    want = np.exp(t)
+    assert np.max(np.abs(got - want) / want) < 4.0e-16

@@ -195,6 +195,46 @@ PYBIND11_MODULE(core, m) {
                  return py::make_tuple(a, b, c, d);
              },
              "(he_to, he_next, he_face, v_he) as stored on the device.")
+        // ---- extension: ONE mesh partitioned across devices (include/trimem_b200.h, tm_part_*; one process or
+        // thread per rank, every rank holding the same mesh) --------------------------------------------
+        .def("part_create",
+             [](HalfedgeMesh& mesh, int rank, int nranks) {
+                 if (tm_part_create(mesh.device(), rank, nranks)) throw std::runtime_error(tm_last_error());
+             },
+             py::arg("rank"), py::arg("nranks"),
+             "Make this mesh rank `rank` of `nranks`: it evaluates the vertices of its contiguous device-slot range.")
+        .def("part_export",
+             [](HalfedgeMesh& mesh) {
+                 unsigned char buf[128];
+                 if (tm_part_export(mesh.device(), buf)) throw std::runtime_error(tm_last_error());
+                 return py::bytes(reinterpret_cast<const char*>(buf), 128);
+             },
+             "128-byte handle of this rank's exchange buffers, for the peers' part_attach_ipc (other processes).")
+        .def("part_attach_ipc",
+             [](HalfedgeMesh& mesh, int peer, const std::string& handle) {
+                 if (handle.size() != 128) throw std::runtime_error("partition handles are 128 bytes");
+                 if (tm_part_attach_ipc(mesh.device(), peer, reinterpret_cast<const unsigned char*>(handle.data()))) throw std::runtime_error(tm_last_error());
+             },
+             py::arg("peer"), py::arg("handle"))
+        .def("part_attach_local",
+             [](HalfedgeMesh& mesh, int peer, HalfedgeMesh& other) {
+                 if (tm_part_attach_local(mesh.device(), peer, other.device())) throw std::runtime_error(tm_last_error());
+             },
+             py::arg("peer"), py::arg("other"), "Attach a peer rank living in this process (tests, one process driving several GPUs).")
+        .def("part_info",
+             [](HalfedgeMesh& mesh) {
+                 int v[6];
+                 if (tm_part_info(mesh.device(), v, v + 1, v + 2, v + 3, v + 4, v + 5)) throw std::runtime_error(tm_last_error());
+                 py::dict d;
+                 const char* k[6] = {"rank", "nranks", "first", "count", "n_ghost1", "n_pull"};
+                 for (int q = 0; q < 6; q++) d[k[q]] = v[q];
+                 return d;
+             })
+        .def("part_sync_positions",
+             [](HalfedgeMesh& mesh) {
+                 if (tm_part_sync_positions(mesh.device())) throw std::runtime_error(tm_last_error());
+             },
+             py::call_guard<py::gil_scoped_release>(), "Collective: every rank's whole position array becomes current.")
         .def("is_flip_ok", [](HalfedgeMesh& mesh, int e) { return mesh.is_flip_ok(e); }, py::arg("edge"))
         .def("flip", [](HalfedgeMesh& mesh, int e) { mesh.flip(e); }, py::arg("edge"));
 
@@ -283,24 +323,39 @@ PYBIND11_MODULE(core, m) {
 
     // ---- EnergyManager (src/bindings.cpp:672-837) ----------------------------------------------
     py::class_<EnergyManager>(m, "EnergyManager", "Helfrich functional evaluation (device resident).")
-        .def(py::init<HalfedgeMesh&, const EnergyParams&>(), py::arg("mesh"), py::arg("eparams"))
-        .def("properties", &EnergyManager::properties, py::arg("mesh"),
+        .def(py::init<HalfedgeMesh&, const EnergyParams&>(), py::arg("mesh"), py::arg("eparams"),
+             py::call_guard<py::gil_scoped_release>())
+        .def("properties", &EnergyManager::properties, py::arg("mesh"), py::call_guard<py::gil_scoped_release>(),
              "Evaluate the reduced vertex properties of the mesh.")
         .def("energy", static_cast<double (EnergyManager::*)(HalfedgeMesh&)>(&EnergyManager::energy), py::arg("mesh"),
+             py::call_guard<py::gil_scoped_release>(),
              "Evaluate the Helfrich functional on the mesh.")
         .def("energy", static_cast<double (EnergyManager::*)(const VertexProperties&) const>(&EnergyManager::energy),
              py::arg("vprops"), "Evaluate the Helfrich functional from pre-evaluated reduced properties.")
         .def("gradient",
              [](EnergyManager& self, HalfedgeMesh& mesh) {
                  py::array_t<double> g = pinned_array(mesh.n_vertices(), 3);
-                 self.gradient(mesh, g.mutable_data());
+                 double* out = g.mutable_data();
+                 {
+                     // device work without the interpreter lock: replicas / ranks driven from Python threads overlap
+                     // (one stream and one handle per mesh; the reference never releases it, src/bindings.cpp)
+                     py::gil_scoped_release nogil;
+                     self.gradient(mesh, out);
+                 }
                  return g;
              },
              py::arg("mesh"), "Evaluate the gradient of the Helfrich functional as an (N,3) array.")
         .def("update_reference_properties", &EnergyManager::update_reference_properties,
              "Update reference configurations (parameter continuation).")
-        .def("update_repulsion", &EnergyManager::update_repulsion, py::arg("mesh"),
+        .def("update_repulsion", &EnergyManager::update_repulsion, py::arg("mesh"), py::call_guard<py::gil_scoped_release>(),
              "Rebuild the neighbour list / repulsion penalty from the current mesh state.")
+        .def("part_prepare",
+             [](EnergyManager& self, HalfedgeMesh& mesh) {
+                 if (tm_part_prepare(mesh.device(), self.nlist_handle())) throw std::runtime_error(tm_last_error());
+             },
+             py::arg("mesh"), py::call_guard<py::gil_scoped_release>(),
+             "Extension (partitioned mesh): halo lists, kernels and buffers of this rank for the mesh and this\n"
+             "manager's neighbour list; local, call on every rank before the first collective evaluation.")
         .def("repulsion_outdated", &EnergyManager::repulsion_outdated, py::arg("mesh"),
              "Extension: True when a vertex has moved more than (rlist - lc1)/2 since the last update_repulsion,\n"
              "i.e. when the frozen verlet rows may miss a pair inside the repulsion cut-off.")
@@ -316,12 +371,14 @@ PYBIND11_MODULE(core, m) {
               return flip_serial(mesh, estore, flip_ratio, seed);
           },
           py::arg("mesh"), py::arg("estore"), py::arg("flip_ratio"), py::arg("seed") = -1,
+          py::call_guard<py::gil_scoped_release>(),
           "Serial flip sweep; returns the number of accepted flips.");
     m.def("pflip",
           [](HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed) {
               return flip_parallel_batches(mesh, estore, flip_ratio, seed);
           },
           py::arg("mesh"), py::arg("estore"), py::arg("flip_ratio"), py::arg("seed") = -1,
+          py::call_guard<py::gil_scoped_release>(),
           "Batch-parallel flip sweep; returns the number of accepted flips.");
 
     // ---- neighbour lists (src/bindings.cpp:893-985) -------------------------------------------------
@@ -378,8 +435,12 @@ PYBIND11_MODULE(core, m) {
                   throw std::runtime_error("momenta must have 3 * n_vertices entries");
               py::array_t<double> x = pinned_array(n, 3), pn = pinned_array(n, 3);
               py::array_t<double> st(4);
-              vv_integrate(mesh, estore, p0.data(), mass, dt, n_steps, x.mutable_data(), pn.mutable_data(),
-                           st.mutable_data());
+              const double* pin = p0.data();
+              double *xo = x.mutable_data(), *po = pn.mutable_data(), *so = st.mutable_data();
+              {
+                  py::gil_scoped_release nogil;
+                  vv_integrate(mesh, estore, pin, mass, dt, n_steps, xo, po, so);
+              }
               return py::make_tuple(x, pn, st);
           },
           py::arg("mesh"), py::arg("estore"), py::arg("p"), py::arg("mass"), py::arg("time_step"), py::arg("n_steps"),

@@ -56,7 +56,7 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 // 64-thread blocks at the same number of resident warps drain a little more evenly than 128-thread ones
 // (property sweep 54.6 -> 52.6 us, ring gradient 81.3 -> 78.9 us).
 #ifndef TM_PROPS_MINB
-#define TM_PROPS_MINB 5
+#define TM_PROPS_MINB 6
 #endif
 #ifndef TM_GRAD_MINB
 #define TM_GRAD_MINB 5
@@ -93,8 +93,8 @@ struct MeshView {
     const int* ex2_off;    // sorted two-ring rows (exclusion level 2), valid after tm_ensure_ring2
     const int* ex2_v;
     // per ring slot, written by the property sweep and read by the gradient sweep (slot-major, [8][aux_vs]):
-    // aux[s][i] = (theta_s / l_s of spoke s of vertex i, 1 / |n_{s+1}| of the face between spokes s and s+1)
-    double2* aux;
+    // aux[s][i] = tau = theta_s / l_s of spoke s of vertex i
+    double* aux;
     int aux_vs;            // V rounded up to a multiple of 32
 };
 
@@ -126,16 +126,7 @@ struct NlView {
     const int* row_j;      // ceil(V/32) * row_cap * 32
     int row_cap;
     unsigned long long serial;   // identity of the list (pair-force cache)
-    // tile lists of a verlet list (tm_nlist.cu, build_tiles): the rows once more, per tile of TM_TILE consecutive
-    // vertices, with LOCAL neighbour indices (tile vertex, or TM_TILE + index into the tile's halo list); tile_T = 0: none
-    int tile_T, tile_hcap, tile_hmax, tile_slmax;   // tile size, halo stride, largest halo / in-tile pair count
-    const int* tile_halo;        // n_tiles * tile_hcap distinct out-of-tile neighbours of the tile (ascending ids)
-    const int* tile_info;        // n_tiles * 2: halo entries, in-tile undirected pairs
-    const unsigned* tile_ent;    // row_j's layout: local index | slot of the pair's slope << 16; upper, halo, lower
-    const unsigned* tile_cnt;    // V: n_upper | n_halo << 8 | n_lower << 16
-    const unsigned short* tile_lo;   // V: start of the vertex's lower entries in the tile's slope array
 };
-constexpr int TM_TILE = 256;
 
 // ----------------------------------------------------------------- handles --
 struct tm_mesh {
@@ -153,7 +144,7 @@ struct tm_mesh {
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
     int *ring_off = nullptr, *ring_v = nullptr, *ring_cnt = nullptr;
     R8* ring8 = nullptr;
-    double2* aux = nullptr;      // 8 * aux_vs slot quantities handed from the property to the gradient sweep
+    double* aux = nullptr;       // 8 * aux_vs slot quantities (tau) handed from the property to the gradient sweep
     int* gen_list = nullptr;     // vertices without a fixed-width row (TM_RING_GENERIC), ascending (tm_rings.cu)
     int n_generic = 0;
     bool rings_valid = false;
@@ -231,11 +222,6 @@ struct tm_nlist {
     int row_cap = 0;
     int rows_first = 0, rows_count = 0;   // vertices whose verlet rows were built (all, or a partition's slice)
     unsigned long long serial = 0;
-    // tile lists (verlet lists over the whole mesh; see NlView)
-    int tile_T = 0, tile_hcap = 0, tile_hmax = 0, tile_slmax = 0;
-    int *tile_halo = nullptr, *tile_info = nullptr;
-    unsigned *tile_ent = nullptr, *tile_cnt = nullptr;
-    unsigned short* tile_lo = nullptr;
     int* cell_of = nullptr;      // build-time cell of every vertex (cell lists)
     double* x_build = nullptr;   // V*3 positions the verlet rows were built from (device numbering): skin criterion
     long long n_entries = 0;
@@ -249,8 +235,6 @@ struct tm_nlist {
         }
         v.cell_start = cell_start; v.cell_items = cell_items; v.cell_rec = cell_rec;
         v.row_cnt = row_cnt; v.row_j = row_j; v.row_cap = row_cap; v.serial = serial;
-        v.tile_T = tile_T; v.tile_hcap = tile_hcap; v.tile_hmax = tile_hmax; v.tile_slmax = tile_slmax; v.tile_halo = tile_halo; v.tile_info = tile_info;
-        v.tile_ent = tile_ent; v.tile_cnt = tile_cnt; v.tile_lo = tile_lo;
         return v;
     }
 };

@@ -90,29 +90,6 @@ __device__ __forceinline__ void verlet_pairs(const P4* pos, const NlView& nl, in
     }
 }
 
-// ---- ring records staged in shared memory -----------------------------------------------------
-// The sweeps' ring data (8 records per thread) go global -> shared with cp.async, without
-// passing through registers, into [slot][thread] arrays of 16- and 8-byte parts (conflict-free
-// wide accesses); the slot loops fetch spoke s+1 when they reach it. Keeping the whole ring in
-// registers instead costs 48-64 registers next to the walk's own state: the gradient sweep
-// spilled ~200 bytes per thread at 128 registers (99 -> 82 us at 655,362 vertices, same bits).
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-#ifndef TM_PROPS_SMEM
-#define TM_PROPS_SMEM 1
-#endif
-#ifndef TM_PROPS_UNROLL
-#define TM_PROPS_UNROLL 1
-#endif
-constexpr int PROPS_UNROLL = TM_PROPS_UNROLL;
-
 // ---- K1: per-vertex properties ------------------------------------------------------
 // one ring slot of vertex_properties (mesh_properties.cpp:19-38): spoke e_cur, face
 // (i, j_s, j_{s-1}) with normal n_cur, next spoke / normal for the dihedral of the spoke
@@ -135,106 +112,62 @@ __device__ __forceinline__ void props_slot(const DevParams& P, d3 xi, int word, 
     }
 }
 
-// ---- ring records in shared memory: the block's tile + staged far neighbours ---------------------------
-// The vertices of a block are NT consecutive device slots = a compact surface patch (Morton order), so
-// most ring neighbours of its vertices are vertices of the block itself (72 % at NT = 64, 80 % at 128, 86 %
-// at 256 on the headline mesh). A per-lane gather of a 32-byte record costs one L1 tag look-up per lane
-// (the 192 ring gathers of a warp touch only ~73 distinct records in ~33 lines), and that look-up rate,
-// not DRAM or the fp64 pipe, bounded the sweeps. So: every thread loads its own record once (coalesced,
-// 8 lines per warp) into the block's tile; a neighbour inside the tile is read from there; only the far
-// neighbours are gathered from global memory, with cp.async into a per-thread staging column.
-//   record index of slot s: idx < NT -> tile[idx], else the staging slot NT * (1 + s) + tid
-// xy and zr halves live in two arrays (conflict-free 16-byte accesses for the staging columns).
-#ifndef TM_RING_KS
-#define TM_RING_KS 4
-#endif
-constexpr int RING_KS = TM_RING_KS;      // staging columns per thread: a vertex with more far neighbours reads the rest
-                                         // from global memory when the walk gets there (a few percent of the vertices)
-template <int NT>
-struct RingSmem {
-    double2* xy;
-    double2* zr;
-    __device__ __forceinline__ RingSmem(double2* base) : xy(base), zr(base + (1 + RING_KS) * NT) {}
-    static constexpr size_t bytes() { return sizeof(double2) * 2 * (1 + RING_KS) * NT; }
-    // record k: k >= 0 a shared-memory record (tile or staging column), k < 0 the global record ~k
-    __device__ __forceinline__ void fetch(const P4* pos, int k, double2& a, double2& b) const {
-        if (k >= 0) { a = xy[k]; b = zr[k]; }
-        else {
-            const double2* src = reinterpret_cast<const double2*>(pos + ~k);
-            a = src[0]; b = src[1];
-        }
-    }
-};
-
-// stages the ring of one closed-fan vertex; idx[s] = record index of slot s (s < d)
-template <int NT>
-__device__ __forceinline__ void stage_ring(const RingSmem<NT>& S, const P4* pos, const R8& row, int d, int tile0,
-                                           int tile_n, int (&idx)[9]) {
-    const int tid = threadIdx.x;
-    int far = 0;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-        if (s < 3 || s < d) {
-            const int j = row.v[s];
-            const unsigned rel = (unsigned)(j - tile0);
-            if (rel < (unsigned)tile_n) idx[s] = (int)rel;
-            else if (far < RING_KS) {
-                idx[s] = NT * (1 + far) + tid;
-                ++far;
-                const P4* src = pos + j;
-                cp_async16(&S.xy[idx[s]], src);
-                cp_async16(&S.zr[idx[s]], reinterpret_cast<const char*>(src) + 16);
-            } else idx[s] = ~j;
-        }
-    }
-    idx[8] = idx[0];
-}
-
-// Closed fan of valence d = 3..8 (the fixed-width row): the fast path of the property sweep.
+// ---- closed fans: the fast path of both ring sweeps -----------------------------------------------------
+// What bounds these sweeps on B200 (profiles/r02): an fp64 instruction holds a scheduler's
+// issue port for two cycles and every other instruction for one, and with 4-5 resident warps per scheduler the
+// sweeps run at ~70 % of that issue bound whatever the memory system does (shared-memory tiles, cp.async
+// pipelines and persistent grids were all measured: same time per instruction, more instructions). So the walk is
+// written for INSTRUCTION COUNT: ring records straight from global memory into registers (one 256-bit load per
+// neighbour, no staging, no barrier, no index arithmetic), the whole ring as one basic block instantiated per
+// valence (no loop, no register rotation, all chains of the ring available to the scheduler at once), and a
+// mask-free instantiation for warps whose closed fans all have the same valence (every warp of a regular mesh).
 //
-// Slot s owns spoke s and face s+1 (between spokes s and s+1; face d is face 0): with the
-// un-normalised normal n_s handed over by slot s-1 it evaluates
-//   n_{s+1} = e_{s+1} x e_s, |n_{s+1}|, 1/|n_{s+1}|      (area, volume, AREA bonds)
+// Slot s owns spoke s and face s+1 (between spokes s and s+1; face d is face 0): with the un-normalised normal
+// n_s handed over by slot s-1 it evaluates
+//   n_{s+1} = e_{s+1} x e_s, |n_{s+1}|                          (area, volume, AREA bonds)
 //   l_s, 1/l_s, theta_s = atan2(-l_s (e_{s+1} . n_s), n_s . n_{s+1})   (curvature, EDGE bonds)
-// and hands (tau_s = theta_s / l_s, 1/|n_{s+1}|) to the gradient sweep through the slot-major aux array
-// (one coalesced 16-byte store), so that sweep needs no square root, reciprocal or arc tangent.
-// The walk is a chain of slot bodies, each instantiated once per slot index and ending in
-// `if (s + 1 < d) next slot`: straight-line code, no join of the walk state (no register rotation) -- only
-// the accumulators meet again where the threads of different valence reconverge.
+// and hands tau_s = theta_s / l_s to the gradient sweep through the slot-major aux array (coalesced 8-byte
+// store), so that sweep needs no arc tangent and a single reciprocal square root per face.
+#ifndef TM_GRAD_GROUP
+#define TM_GRAD_GROUP 3
+#endif
+#ifndef TM_PROPS_GROUP
+#define TM_PROPS_GROUP 3
+#endif
 struct PropsAcc {
     double area2, curv, teth;   // sum |n_f|, sum l theta, tether sum
     d3 nsum;                    // sum n_f
     unsigned tmask;             // slots whose EDGE bond is off the flat bottom
 };
 
-template <bool FULL, int NT>
+template <bool FULL>
 struct PropsWalk {
     const DevParams& P;
-    const RingSmem<NT>& S;
-    const int (&idx)[9];
+    const P4* pos;
+    const R8& row;
     d3 xi;
     int d;
-    double2* aux;               // aux + i, or nullptr
+    double* aux;                // tau array + i, or nullptr
     int vs;
     PropsAcc& A;
 
-    const P4* pos;
-    __device__ __forceinline__ d3 spoke(int k) const {          // record index k
-        double2 a, b;
-        S.fetch(pos, k, a, b);
-        return mk3(a.x, a.y, b.x) - xi;
+    // spoke to vertex j. Coherent load (rho (.w) of other vertices is being written by this very sweep and never
+    // read by it), 256 bits in one instruction.
+    __device__ __forceinline__ d3 spoke(int j) const {
+        double x, y, z, w;
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(pos + j));
+        return mk3(x, y, z) - xi;
     }
     // what one slot adds: spoke e_c with normal n_c of its face and squared length l2_c, next spoke e_n
-    struct SlotOut { d3 n_n; double l2_n, nl, lth, tau, in_n, l; };
+    struct SlotOut { d3 n_n; double nl, lth, tau, l; };
     __device__ __forceinline__ SlotOut eval(const d3 e_c, const d3 n_c, const double l2_c, const d3 e_n) const {
         SlotOut o;
         o.n_n = cross3(e_n, e_c);
         const double nn = dot3(o.n_n, o.n_n);
-        o.l2_n = dot3(e_n, e_n);
         // (the 1e-300 offset is invisible for a proper face and makes a degenerate one come out as |n| = 0)
-        o.in_n = rsqrt_pos(nn + 1.0e-300);
+        const double in_n = rsqrt_pos(nn + 1.0e-300);
         const double il = rsqrt_pos(l2_c);
-        o.nl = __dmul_rn(nn, o.in_n);                     // |n_{s+1}| = 2 A_f
+        o.nl = __dmul_rn(nn, in_n);                       // |n_{s+1}| = 2 A_f
         o.l = l2_c * il;
         const double th = tm_math::atan2_fast(-o.l * dot3(e_n, n_c), dot3(n_c, o.n_n));
         o.lth = __dmul_rn(o.l, th);
@@ -243,53 +176,74 @@ struct PropsWalk {
     }
     // (explicitly rounded sums: the FULL and the geometry-only instantiation must produce the same rho and
     // slot quantities bit for bit, whatever else the compiler would like to contract into them)
+    template <bool MASK>
     __device__ __forceinline__ void add(const SlotOut& o, int s, bool valid) const {
+        if (!MASK) valid = true;
         A.area2 = __dadd_rn(A.area2, valid ? o.nl : 0.0);
         A.curv = __dadd_rn(A.curv, valid ? o.lth : 0.0);
         A.nsum.x = __dadd_rn(A.nsum.x, valid ? o.n_n.x : 0.0);
         A.nsum.y = __dadd_rn(A.nsum.y, valid ? o.n_n.y : 0.0);
         A.nsum.z = __dadd_rn(A.nsum.z, valid ? o.n_n.z : 0.0);
-        if (aux && valid) aux[s * vs] = make_double2(o.tau, o.in_n);
+        if (aux && valid) aux[s * vs] = o.tau;
         if (FULL) {
             // EDGE bonds leave the flat bottom on a fraction of a percent of the edges: those slots are
-            // flagged and evaluated after the walk (one copy of the exp/pow code, outside the chain)
+            // flagged and evaluated after the walk (one copy of the exp/pow code, outside the block)
             if (P.bond_type == TM_BOND_EDGE) A.tmask |= (valid && (o.l > P.lc0 || o.l < P.lc1)) ? (1u << s) : 0u;
             else { const double q = fma(0.5 * o.nl, P.inv_a0, -1.0); A.teth = __dadd_rn(A.teth, valid ? __dmul_rn(q, q) : 0.0); }
         }
     }
-    // Slots S_ and S_+1 in ONE basic block: their rsqrt / atan2 chains are independent, so the scheduler
-    // interleaves them (the sweep is bound by dependent-issue latency: ~10 cycles per fp64 operation of a chain,
-    // 4-5 warps per scheduler). Slot S_ is valid on entry; slot S_+1 may lie beyond the ring (odd valence): it is
-    // then evaluated on harmless data (spoke 0) and left out of the sums.
-    template <int S_>
-    __device__ __forceinline__ void slot2(const d3 e_c, const d3 n_c, const double l2_c) const {
-        const bool v1 = S_ + 1 < 3 || S_ + 1 < d;             // slot S_+1 exists
-        const bool v2 = S_ + 2 < 3 || S_ + 2 < d;             // slot S_+2 exists (else spoke S_+2 wraps to 0)
-        const d3 e_1 = spoke(v1 ? idx[S_ + 1] : idx[0]);
-        const d3 e_2 = spoke(v2 && S_ + 2 < 8 ? idx[S_ + 2 < 8 ? S_ + 2 : 0] : idx[0]);
-        const SlotOut a = eval(e_c, n_c, l2_c, e_1);
-        const SlotOut b = eval(e_1, a.n_n, a.l2_n, e_2);
-        add(a, S_, true);
-        add(b, S_ + 1, v1);
-        if (S_ + 2 < 8) {
-            if (v2) slot2<(S_ + 2 < 8 ? S_ + 2 : 6)>(e_2, b.n_n, b.l2_n);
+    // The whole ring in one basic block. DMAX = largest valence among the closed fans of the warp; MASK = the warp
+    // has fans of lower valence too: such a lane evaluates the surplus slots on slot 0's record and leaves them out
+    // of the sums, and finds its last slot (d-1, successor 0) through selects. Without MASK every index is static.
+    template <int DMAX, bool MASK>
+    __device__ __forceinline__ void block() const {
+        int j[DMAX];
+#pragma unroll
+        for (int s = 0; s < DMAX; s++) j[s] = (!MASK || s < 3 || s < d) ? row.v[s] : row.v[0];
+        int j_l = j[DMAX - 1], j_l2 = j[DMAX - 2];
+        if (MASK) {
+            j_l = row.v[2]; j_l2 = row.v[1];
+#pragma unroll
+            for (int s = 3; s < DMAX; s++) { j_l2 = s < d ? row.v[s - 1] : j_l2; j_l = s < d ? row.v[s] : j_l; }
+        }
+        const d3 e_l = spoke(j_l), e_l2 = spoke(j_l2);
+        d3 e_c = spoke(j[0]);
+        d3 n_c = cross3(e_c, e_l);
+        {
+            const SlotOut o = eval(e_l, cross3(e_l, e_l2), dot3(e_l, e_l), e_c);        // last slot; its n_n = n_0: face 0
+            add<false>(o, MASK ? d - 1 : DMAX - 1, true);
+        }
+#pragma unroll
+        for (int s = 0; s + 1 < DMAX; s++) {
+            // (groups of TM_PROPS_GROUP slots between fences: keeps the scheduler from hoisting every load of the
+            // ring to the top and spilling what it then has to hold)
+            if (s > 0 && s % TM_PROPS_GROUP == 0) asm volatile("" ::: "memory");
+            const d3 e_n = spoke(j[s + 1]);
+            const SlotOut o = eval(e_c, n_c, dot3(e_c, e_c), e_n);
+            add<MASK>(o, s, s + 1 < 3 || s + 1 < d);
+            e_c = e_n;
+            n_c = o.n_n;
         }
     }
 };
 
-// idx[]: record indices of the staged ring (stage_ring), complete (cp.async waited for, block barrier passed)
-template <bool FULL, int NT>
-__device__ __forceinline__ void ring_props_closed(const MeshView& mv, const DevParams& P, const RingSmem<NT>& S,
-                                                  const int (&idx)[9], int d, int i, d3 xi, bool write_aux,
-                                                  double& area, double& vol, double& curv, double& teth) {
+// dmax: largest closed-fan valence in the warp; uniform: all of the warp's closed fans have it
+template <bool FULL>
+__device__ __forceinline__ void ring_props_closed(const MeshView& mv, const DevParams& P, const R8& row, int d, int dmax,
+                                                  bool uniform, int i, d3 xi, bool write_aux, double& area, double& vol,
+                                                  double& curv, double& teth) {
     PropsAcc A;
     A.area2 = 0.0; A.curv = 0.0; A.teth = 0.0; A.nsum = mk3(0, 0, 0); A.tmask = 0u;
-    const PropsWalk<FULL, NT> W{P, S, idx, xi, d, write_aux ? mv.aux + i : nullptr, mv.aux_vs, A, mv.pos};
-    int k_last = idx[2];
-#pragma unroll
-    for (int s = 3; s < 8; s++) k_last = s < d ? idx[s] : k_last;
-    const d3 e_0 = W.spoke(idx[0]);
-    W.template slot2<0>(e_0, cross3(e_0, W.spoke(k_last)), dot3(e_0, e_0));
+    const PropsWalk<FULL> W{P, mv.pos, row, xi, d, write_aux ? mv.aux + i : nullptr, mv.aux_vs, A};
+#define TM_WALK(D) do { if (uniform) W.template block<D, false>(); else W.template block<D, true>(); } while (0)
+    switch (dmax) {                            // warp-uniform
+        case 3: case 4: W.template block<4, true>(); break;
+        case 5: TM_WALK(5); break;
+        case 6: TM_WALK(6); break;
+        case 7: TM_WALK(7); break;
+        default: TM_WALK(8); break;
+    }
+#undef TM_WALK
     if (FULL) {
         unsigned tmask = A.tmask;
         while (tmask) {                            // ascending slot order; rare: the spoke is fetched again
@@ -398,57 +352,39 @@ __device__ __forceinline__ void props_warp_partials(const double (&acc)[6], int 
 
 // partials: [6][ncols] warp partials; this launch owns the columns [0, number of its warps). Quantity 5
 // (repulsion) belongs to k_pairs and is written here (as 0) only when no pair sweep runs (nq == 6).
-template <bool FULL, bool WRITE_VPROPS, bool GEN_INLINE>
+// LIST: the vertices of R.vlist (ghost sweeps of a partitioned mesh: rho only, nothing reduced, no slot
+// quantities, generic vertices inline).
+template <bool FULL, bool WRITE_VPROPS, bool LIST>
 __global__ void __launch_bounds__(TM_PROPS_THREADS, TM_PROPS_MINB)
 k_props(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprops,
-        double* __restrict__ partials, int ncols, int nq, SweepRange R, int write_aux) {
-    constexpr int NT = TM_PROPS_THREADS;
-    extern __shared__ double2 ring_smem[];
-    const RingSmem<NT> S(ring_smem);
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x * NT + tid;
+        double* __restrict__ partials, int ncols, int nq, SweepRange R) {
+    const int t = blockIdx.x * TM_PROPS_THREADS + threadIdx.x;
     const bool live = t < R.count;
-    const int i = R.vlist ? (live ? R.vlist[t] : 0) : R.first + t;
-    // the block's tile: the records of its own NT consecutive vertices (list-driven launches have none)
-    const int tile0 = R.first + blockIdx.x * NT;
-    const int tile_n = R.vlist ? 0 : min(NT, mv.V - tile0);
-    P4 ri;
-    ri.x = ri.y = ri.z = ri.w = 0.0;
-    if (tid < tile_n) {
-        // coherent load: rho (.w) of other vertices is being written by this very sweep (and never read by it)
-        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(ri.x), "=d"(ri.y), "=d"(ri.z), "=d"(ri.w) : "l"(mv.pos + tile0 + tid));
-        S.xy[tid] = make_double2(ri.x, ri.y);
-        S.zr[tid] = make_double2(ri.z, ri.w);
-    } else if (live) {
-        const d3 x = ldpos(mv.pos, i);
-        ri.x = x.x; ri.y = x.y; ri.z = x.z;
-    }
+    const int i = LIST ? (live ? R.vlist[t] : 0) : R.first + t;
     R8 row;
     row.v[0] = TM_RING_GENERIC;
-    int d = 0;
-    int idx[9];
+    double xx = 0, xy = 0, xz = 0, xw = 0;
     if (live) {
         row = ldrow(mv.ring8, i);
-        if (row.v[0] != TM_RING_GENERIC) {
-            d = row_valence(row);
-            stage_ring<NT>(S, mv.pos, row, d, tile0, tile_n, idx);
-        }
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(xx), "=d"(xy), "=d"(xz), "=d"(xw) : "l"(mv.pos + i));
     }
-    cp_async_wait_all();
-    __syncthreads();
+    const bool closed = row.v[0] != TM_RING_GENERIC;
+    const int d = closed ? row_valence(row) : 0;
+    const int dmax = __reduce_max_sync(0xffffffffu, d);
+    const bool uniform = __all_sync(0xffffffffu, !closed || d == dmax);
     double acc[6] = {0, 0, 0, 0, 0, 0};   // area volume curvature bending tether repulsion
     if (live) {
-        const d3 xi = mk3(ri.x, ri.y, ri.z);
+        const d3 xi = mk3(xx, xy, xz);
         double area = 0, vol = 0, curv = 0, teth = 0;
-        if (row.v[0] != TM_RING_GENERIC) {
-            ring_props_closed<FULL, NT>(mv, P, S, idx, d, i, xi, write_aux != 0, area, vol, curv, teth);
+        if (closed) {
+            ring_props_closed<FULL>(mv, P, row, d, dmax, uniform, i, xi, !LIST, area, vol, curv, teth);
             props_finish<FULL, WRITE_VPROPS>(P, i, area, vol, curv, teth, pos_rw, vprops, acc);
-        } else if (GEN_INLINE) {
+        } else if (LIST) {
             ring_props_generic<FULL>(mv, P, i, xi, area, vol, curv, teth);
             props_finish<FULL, WRITE_VPROPS>(P, i, area, vol, curv, teth, pos_rw, vprops, acc);
         }
     }
-    if (nq > 0) props_warp_partials(acc, nq, partials, ncols, t >> 5);
+    if (!LIST) props_warp_partials(acc, nq, partials, ncols, t >> 5);
 }
 
 // the vertices of `list` (ascending) that fall into [R.first, R.first + R.count): columns col0.. of the partials
@@ -481,7 +417,7 @@ k_props_generic(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprop
 // per neighbour.
 struct PairConst {
     double lc1, lc1sq, rd;      // cut-off, its square, (double) r
-    double ec[12];              // exp polynomial (tm_math::EXP_C)
+    const double* tab;          // 2^(j/64), in shared memory (tm_math::exp_tab)
 };
 
 // phi = exp(l/(l-lc1)) / l^r and slope = -(lc1/(l-lc1)^2 + r/l) / l^(r+1) * exp(l/(l-lc1)) for l2 < lc1^2,
@@ -494,20 +430,9 @@ __device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2,
     double dl = l - C.lc1;                                    // < 0; guard the rounding corner l2 < lc1^2 <= l^2
     dl = dl < -1.0e-300 ? dl : -1.0e-300;
     const double w = rcp_pos(dl);
-    // exp(l * w), argument <= 0 (tm_math::exp_nonpos with the coefficients in registers)
+    // exp(l * w), argument <= 0
     const double t = l * w;
-    const double MAGIC = 6755399441055744.0;
-    double kd = fma(t, 1.4426950408889634, MAGIC);
-    const int k = __double2loint(kd);
-    kd -= MAGIC;
-    double r = fma(kd, -6.93147180369123816490e-01, t);
-    r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = C.ec[0];
-#pragma unroll
-    for (int q = 1; q < 12; q++) p = fma(p, r, C.ec[q]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    double ex = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    double ex = tm_math::exp_tab(t, C.tab);
     ex = (active && t >= -708.0) ? ex : 0.0;
     const double ilr = R2 ? il * il : powi(il, rr);
     phi = ex * ilr;
@@ -530,10 +455,10 @@ __global__ void k_cell_gather(int V, const int* __restrict__ items, const P4* __
 #define TM_PAIR_NT 128
 #endif
 #ifndef TM_PAIR_MINB
-#define TM_PAIR_MINB 4
+#define TM_PAIR_MINB 6
 #endif
 #ifndef TM_PAIR_BATCH
-#define TM_PAIR_BATCH 4
+#define TM_PAIR_BATCH 3
 #endif
 constexpr int PAIR_THREADS = TM_PAIR_NT;
 constexpr int PAIR_QCAP = 56;                   // queued candidates per thread before an early flush (cell lists)
@@ -548,14 +473,15 @@ template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2, bool CELL>
 __global__ void __launch_bounds__(PAIR_THREADS, CELL ? TM_PAIR_CELL_MINB : TM_PAIR_MINB)
 k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
         double* __restrict__ partials, int nwarps, SweepRange R) {
+    __shared__ double s_exp2[64];
+    if (threadIdx.x < 64) s_exp2[threadIdx.x] = tm_math::EXP2_64[threadIdx.x];
+    __syncthreads();
     const int t = blockIdx.x * PAIR_THREADS + threadIdx.x;
     const int i = R.first + t;
     double rep = 0.0;
     if (t < R.count) {
         PairConst C;
-        C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
-#pragma unroll
-        for (int q = 0; q < 12; q++) C.ec[q] = tm_math::EXP_C[q];
+        C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr; C.tab = s_exp2;
         const P4 ri = ldrec(mv.pos, i);
         const d3 xi = mk3(ri.x, ri.y, ri.z);
         d3 gr = mk3(0, 0, 0);
@@ -708,90 +634,6 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0 && w < nwarps) partials[(size_t)5 * nwarps + w] = s;
-    }
-}
-
-// ---- K1c: pair sweep over the tile lists of a verlet list (tm_nlist.cu, build_tiles) ----------------------
-// One block per tile of TM_TILE consecutive vertices. The tile's own records and its halo records go to shared
-// memory once (SoA x, y, z); every pair evaluation then reads shared memory through its local index. In-tile
-// pairs are evaluated once, by their lower vertex, which leaves the slope factor in the tile's slope array for
-// its partner (second phase: six fp64 operations per entry instead of ~50). Same potential, same cut-off test,
-// fixed summation order.
-template <bool WITH_E, bool R2>
-__global__ void __launch_bounds__(TM_TILE, 3)
-k_pairs_tile(MeshView mv, NlView nl, double lc1, int rr, int hmax, double* __restrict__ force,
-             double* __restrict__ partials, int ncols) {
-    extern __shared__ double pt_smem[];
-    const int np = TM_TILE + hmax;
-    double* sx = pt_smem;
-    double* sy = sx + np;
-    double* sz = sy + np;
-    double* ssl = sz + np;
-    const int tid = threadIdx.x, b = blockIdx.x, tile0 = b * TM_TILE, i = tile0 + tid;
-    const bool live = i < mv.V;
-    d3 xi = mk3(0, 0, 0);
-    if (live) {
-        const P4 r = ldrec(mv.pos, i);
-        xi = mk3(r.x, r.y, r.z);
-        sx[tid] = r.x; sy[tid] = r.y; sz[tid] = r.z;
-    }
-    const int nh = __ldg(nl.tile_info + 2 * b);
-    for (int h = tid; h < nh; h += TM_TILE) {
-        const P4 r = ldrec(mv.pos, __ldg(nl.tile_halo + (size_t)b * nl.tile_hcap + h));
-        sx[TM_TILE + h] = r.x; sy[TM_TILE + h] = r.y; sz[TM_TILE + h] = r.z;
-    }
-    __syncthreads();
-    PairConst C;
-    C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
-#pragma unroll
-    for (int q = 0; q < 12; q++) C.ec[q] = tm_math::EXP_C[q];
-    const unsigned cnt = live ? __ldg(nl.tile_cnt + i) : 0u;
-    const int n_up = cnt & 255, n_halo = (cnt >> 8) & 255, n_lo = (cnt >> 16) & 255;
-    const unsigned* col = nl.tile_ent + tm_row_base(live ? i : 0, nl.row_cap);
-    d3 gr = mk3(0, 0, 0);
-    double rep = 0.0;
-    // phase 1: upper in-tile entries (slope stored for the partner, energy counted for both ends) and halo entries
-    const int n1 = n_up + n_halo;
-    for (int k = 0; k < n1; k += PB) {
-        unsigned ent[PB];
-#pragma unroll
-        for (int u = 0; u < PB; u++) ent[u] = (k + u < n1) ? __ldg(col + (k + u) * 32) : (unsigned)tid;
-        d3 dv[PB];
-        double l2[PB], phi[PB], sl[PB];
-#pragma unroll
-        for (int u = 0; u < PB; u++) {
-            const int loc = ent[u] & 0xffffu;
-            dv[u] = xi - mk3(sx[loc], sy[loc], sz[loc]);
-            l2[u] = dot3(dv[u], dv[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < PB; u++) pair_eval<R2>(C, rr, l2[u], (k + u < n1) && (l2[u] < C.lc1sq), phi[u], sl[u]);
-#pragma unroll
-        for (int u = 0; u < PB; u++) {
-            const bool upper = k + u < n_up;
-            if (WITH_E) rep += upper ? 2.0 * phi[u] : phi[u];
-            axpy3(gr, sl[u], dv[u]);
-            if (upper) ssl[ent[u] >> 16] = sl[u];
-        }
-    }
-    __syncthreads();
-    // phase 2: lower in-tile entries: the partner's slope factor times this end's difference vector
-    const int lo0 = live ? (int)__ldg(nl.tile_lo + i) : 0;
-    for (int k = 0; k < n_lo; k++) {
-        const int loc = __ldg(col + (n1 + k) * 32) & 0xffffu;
-        const d3 dv = xi - mk3(sx[loc], sy[loc], sz[loc]);
-        axpy3(gr, ssl[lo0 + k], dv);
-    }
-    if (live) {
-        double* o = force + 3 * (size_t)i;
-        o[0] = gr.x; o[1] = gr.y; o[2] = gr.z;
-    }
-    if (WITH_E) {
-        const int lane = tid & 31, w = i >> 5;
-        double s = rep;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && w < ncols) partials[(size_t)5 * ncols + w] = s;
     }
 }
 
@@ -993,14 +835,13 @@ struct GradC {
     double W0, U0h, c3, fV6, kb, kt;
 };
 
-template <int NT>
 struct GradWalk {
     const DevParams& P;
     const GradC& K;
-    const RingSmem<NT>& S;
-    const int (&idx)[9];
-    const double2* saux;        // this thread's column of the staged slot quantities: slot s at saux[s * NT]
     const P4* pos;
+    const R8& row;
+    const double* tau;          // aux + i: tau of slot s at tau[s * vs]
+    int vs;
     d3 xi;
     double rho_i;
     int d;
@@ -1008,24 +849,23 @@ struct GradWalk {
     unsigned& tmask;
 
     struct Pt { d3 e; double l2, dr, r2; };        // spoke, |e|^2, rho_i - rho, rho^2
-    __device__ __forceinline__ Pt point(int k) const {          // record index k
-        double2 a, b;
-        S.fetch(pos, k, a, b);
+    __device__ __forceinline__ Pt point(int j) const {
+        const P4 r = ldrec(pos, j);
         Pt t;
-        t.e = mk3(a.x, a.y, b.x) - xi;
+        t.e = mk3(r.x, r.y, r.z) - xi;
         t.l2 = dot3(t.e, t.e);
-        t.dr = rho_i - b.y;
-        t.r2 = b.y * b.y;
+        t.dr = rho_i - r.w;
+        t.r2 = r.w * r.w;
         return t;
     }
-    // slot S_: face S_ between spokes S_-1 (pp) and S_; E_p = coefficient of e_{S_-1} gathered so far,
-    // inv = 1/|n_S_|, first = the part of spoke d-1's coefficient that slot 0 produced
-    template <int S_>
-    __device__ __forceinline__ void slot(const Pt pp, const double E_p, const double inv, const double first) const {
-        const Pt pc = point(idx[S_]);
-        const double2 ax = saux[S_ * NT];                // (tau_S, 1/|n_{S+1}|)
+    // face between spokes pp (s-1) and pc (s): adds C n_s, the face's share of both spokes and spoke s's own term;
+    // `valid` masks the surplus slots of a lane of lower valence
+    template <bool MASK>
+    __device__ __forceinline__ void face(const Pt& pp, const Pt& pc, double ta, bool valid, int s) const {
+        if (!MASK) valid = true;
         const double p = dot3(pc.e, pp.e);
         const d3 n = cross3(pc.e, pp.e);
+        const double inv = rsqrt_pos(dot3(n, n) + 1.0e-300);          // 1/|n_s|
         const double a = pc.l2 - p, b = pp.l2 - p;
         const double C = fma(K.kb * inv * inv, fma(pp.dr, a, pc.dr * b), K.fV6);
         double Uh = fma(-K.c3, pc.r2 + pp.r2, K.U0h);
@@ -1034,30 +874,49 @@ struct GradWalk {
             Uh = fma(K.kt * P.inv_a0, fma(a_f, P.inv_a0, -1.0), Uh);
         }
         const double h = Uh * inv;
-        // W_S = fC/2 + kb (rho_i + rho_S) = W0 - kb (rho_i - rho_S) with W0 = fC/2 + 2 kb rho_i
-        const double E_c = fma(-h, b, -fma(-K.kb, pc.dr, K.W0) * ax.x);
-        if (P.bond_type == TM_BOND_EDGE) tmask |= (pc.l2 > P.lc0sq || pc.l2 < P.lc1sq) ? (1u << S_) : 0u;
-        const double f1 = S_ == 0 ? -h * a : first;      // slot 0's share belongs to spoke d-1
-        if (S_ > 0) axpy3(g, fma(-h, a, E_p), pp.e);     // spoke S_-1 is complete
-        axpy3(g, C, n);
-        if (S_ + 1 < 8 && (S_ + 1 < 3 || S_ + 1 < d)) slot<(S_ + 1 < 8 ? S_ + 1 : 7)>(pc, E_c, ax.y, f1);
-        else axpy3(g, E_c + f1, pc.e);                   // last spoke
+        // W_s = fC/2 + kb (rho_i + rho_s) = W0 - kb (rho_i - rho_s) with W0 = fC/2 + 2 kb rho_i
+        const double E_c = fma(-h, b, -fma(-K.kb, pc.dr, K.W0) * ta);
+        if (P.bond_type == TM_BOND_EDGE) tmask |= (valid && (pc.l2 > P.lc0sq || pc.l2 < P.lc1sq)) ? (1u << s) : 0u;
+        axpy3(g, valid ? C : 0.0, n);
+        axpy3(g, valid ? E_c : 0.0, pc.e);
+        axpy3(g, valid ? -h * a : 0.0, pp.e);
+    }
+    // the whole ring in one basic block (see PropsWalk::block): face 0 lies between the last spoke and spoke 0
+    template <int DMAX, bool MASK>
+    __device__ __forceinline__ void block() const {
+        int j_l = row.v[DMAX - 1];
+        if (MASK) {
+            j_l = row.v[2];
+#pragma unroll
+            for (int s = 3; s < DMAX; s++) j_l = s < d ? row.v[s] : j_l;
+        }
+        Pt pp = point(j_l);
+#pragma unroll
+        for (int s = 0; s < DMAX; s++) {
+            if (s > 0 && s % TM_GRAD_GROUP == 0) asm volatile("" ::: "memory");
+            const bool valid = !MASK || s < 3 || s < d;
+            const Pt pc = point(valid ? row.v[s] : row.v[0]);
+            const double ta = valid ? __ldg(tau + s * vs) : 0.0;
+            face<MASK>(pp, pc, ta, valid, s);
+            pp = pc;
+        }
     }
 };
 
-// idx[]: record indices of the staged ring (stage_ring), complete
-template <int NT>
-__device__ __forceinline__ d3 ring_grad_closed(const MeshView& mv, const DevParams& P, const GradC& K,
-                                               const RingSmem<NT>& S, const double2* saux, const int (&idx)[9], int d,
-                                               int i, d3 xi, double rho_i) {
+__device__ __forceinline__ d3 ring_grad_closed(const MeshView& mv, const DevParams& P, const GradC& K, const R8& row,
+                                               int d, int dmax, bool uniform, int i, d3 xi, double rho_i) {
     d3 g = mk3(0, 0, 0);
     unsigned tmask = 0;
-    const GradWalk<NT> W{P, K, S, idx, saux, mv.pos, xi, rho_i, d, g, tmask};
-    const double in_0 = saux[(d - 1) * NT].y;            // face 0 = face d, written by slot d-1
-    int k_last = idx[2];
-#pragma unroll
-    for (int s = 3; s < 8; s++) k_last = s < d ? idx[s] : k_last;
-    W.template slot<0>(W.point(k_last), 0.0, in_0, 0.0);
+    const GradWalk W{P, K, mv.pos, row, mv.aux + i, mv.aux_vs, xi, rho_i, d, g, tmask};
+#define TM_WALK(D) do { if (uniform) W.template block<D, false>(); else W.template block<D, true>(); } while (0)
+    switch (dmax) {                            // warp-uniform
+        case 3: case 4: W.template block<4, true>(); break;
+        case 5: TM_WALK(5); break;
+        case 6: TM_WALK(6); break;
+        case 7: TM_WALK(7); break;
+        default: TM_WALK(8); break;
+    }
+#undef TM_WALK
     // EDGE bonds off the flat bottom (mesh_properties.cpp:132-133): rare, evaluated outside the walk
     while (tmask) {
         const int s = __ffs(tmask) - 1;
@@ -1141,51 +1000,33 @@ __device__ __forceinline__ void penalty_factors(const DevParams& P, const double
 }
 
 // Closed fans only (vertices without a fixed-width row are left to k_grad_generic). Reads only: every ring
-// neighbour costs one (x, y, z, rho) record, every slot one (tau, 1/|n|) pair of the property sweep.
+// neighbour costs one (x, y, z, rho) record, every slot one tau of the property sweep.
 template <int UPD>
 __global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
 k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
        double* __restrict__ grad, SweepRange R, VVFuse U) {
-    constexpr int NT = TM_GRAD_THREADS;
-    extern __shared__ double2 ring_smem[];
-    const RingSmem<NT> S(ring_smem);
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x * NT + tid;
+    const int t = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
     const bool live = t < R.count;
     const int i = R.first + t;
-    const int tile0 = R.first + blockIdx.x * NT;
-    const int tile_n = min(NT, mv.V - tile0);
-    P4 ri;
-    ri.x = ri.y = ri.z = ri.w = 0.0;
-    if (tid < tile_n) {
-        ri = ldrec(mv.pos, tile0 + tid);
-        S.xy[tid] = make_double2(ri.x, ri.y);
-        S.zr[tid] = make_double2(ri.z, ri.w);
-    }
     R8 row;
     row.v[0] = TM_RING_GENERIC;
-    int d = 0;
-    int idx[9];
-    // the slot quantities of the property sweep, staged beside the ring records: [slot][thread]
-    double2* saux = ring_smem + 2 * (1 + RING_KS) * NT + tid;
+    P4 ri;
+    ri.x = ri.y = ri.z = ri.w = 0.0;
     if (live) {
         row = ldrow(mv.ring8, i);
-        if (row.v[0] != TM_RING_GENERIC) {
-            d = row_valence(row);
-            stage_ring<NT>(S, mv.pos, row, d, tile0, tile_n, idx);
-#pragma unroll
-            for (int s = 0; s < 8; s++)
-                if (s < 3 || s < d) cp_async16(saux + s * NT, mv.aux + (size_t)s * mv.aux_vs + i);
-            if (UPD > 0) {
-                // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
-            }
-        }
+        ri = ldrec(mv.pos, i);
     }
-    cp_async_wait_all();
-    __syncthreads();
-    if (!live || row.v[0] == TM_RING_GENERIC) return;
+    const bool closed = row.v[0] != TM_RING_GENERIC;
+    const int d = closed ? row_valence(row) : 0;
+    const int dmax = __reduce_max_sync(0xffffffffu, d);
+    const bool uniform = __all_sync(0xffffffffu, !closed || d == dmax);
+    if (!closed) return;
+    // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
+    if (force) asm volatile("prefetch.global.L2 [%0];" ::"l"(force + 3 * (size_t)i));
+    if (UPD > 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
+    }
     double fA, fV, fC;
     penalty_factors(P, sums, fA, fV, fC);
     GradC K;
@@ -1194,7 +1035,7 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     K.c3 = K.kb * (1.0 / 3.0);
     K.U0h = fma(-K.c3, ri.w * ri.w, 0.5 * fA);
     K.fV6 = fV * (1.0 / 6.0);
-    const d3 g = ring_grad_closed<NT>(mv, P, K, S, saux, idx, d, i, mk3(ri.x, ri.y, ri.z), ri.w);
+    const d3 g = ring_grad_closed(mv, P, K, row, d, dmax, uniform, i, mk3(ri.x, ri.y, ri.z), ri.w);
     grad_finish<UPD>(P, i, ri, g, force, grad, U);
 }
 
@@ -1251,27 +1092,6 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
         TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
         st = m->stream2;
     }
-    if (nl.kind == TM_NLIST_VERLET && nl.tile_T == TM_TILE && !write_vprops && R.first == 0 && R.count == m->V) {
-        // tile lists: one block per tile, the tile's and its halo's records in shared memory
-        const size_t bytes = sizeof(double) * (3 * (size_t)(TM_TILE + nl.tile_hmax) + (size_t)nl.tile_slmax);
-        const int nt = (m->V + TM_TILE - 1) / TM_TILE;
-        const bool r2t = p.rep_r == 2;
-#define TM_PT(E, R2) do { \
-        TM_CUDA(cudaFuncSetAttribute(k_pairs_tile<E, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
-        k_pairs_tile<E, R2><<<nt, TM_TILE, bytes, st>>>(mv, nl, p.rep_lc1, p.rep_r, nl.tile_hmax, m->frep, m->partials, nwarps); } while (0)
-        if (with_e) { if (r2t) TM_PT(true, true); else TM_PT(true, false); }
-        else { if (r2t) TM_PT(false, true); else TM_PT(false, false); }
-#undef TM_PT
-        TM_LAUNCHED();
-        TM_CUDA(cudaGetLastError());
-        if (beside) {
-            TM_CUDA(cudaEventRecord(m->ev_join, m->stream2));
-            m->pairs_inflight = true;
-        }
-        m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
-        m->frep_list = nl.serial;
-        return 0;
-    }
     const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * (PAIR_QCAP + PAIR_XCAP) * PAIR_THREADS : 0;
     if (nl.kind == TM_NLIST_CELL && !(m->cellrec_epoch == m->pos_epoch && m->cellrec_list == nl.serial)) {
         // the candidates' records at the current positions, in cell order
@@ -1306,26 +1126,10 @@ int tm_join_pairs(tm_mesh* m) {
     return 0;
 }
 
-// dynamic shared memory of the ring sweeps (tile + staging columns); above 48 KB it must be opted into, once
-static const size_t PROPS_SMEM = RingSmem<TM_PROPS_THREADS>::bytes(),
-                    GRAD_SMEM = RingSmem<TM_GRAD_THREADS>::bytes() + sizeof(double2) * 8 * TM_GRAD_THREADS;
-static int ring_smem_optin() {
-    static std::atomic<bool> done{false};
-    if (done.load()) return 0;
-#define TM_OPTIN(k, n) TM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(n)))
-    TM_OPTIN((k_props<true, true, false>), PROPS_SMEM); TM_OPTIN((k_props<true, false, false>), PROPS_SMEM);
-    TM_OPTIN((k_props<false, false, false>), PROPS_SMEM); TM_OPTIN((k_props<false, false, true>), PROPS_SMEM);
-    TM_OPTIN(k_grad<0>, GRAD_SMEM); TM_OPTIN(k_grad<1>, GRAD_SMEM); TM_OPTIN(k_grad<2>, GRAD_SMEM);
-#undef TM_OPTIN
-    done.store(true);
-    return 0;
-}
-
 // warp partials of the largest sweep (whole mesh + its generic vertices) and the slot quantities the property
 // sweep hands to the gradient sweep; sized for the whole mesh so that a partitioned mesh never reallocates
 // (cudaFree synchronises the device) while a peer waits on the device
 int tm_props_workspace(tm_mesh* m) {
-    if (ring_smem_optin()) return 1;
     const size_t need = 12 * (size_t)((m->V + 31) / 32) + 6 * TM_REDUCE_BLOCKS;     // (n_generic <= V)
     if (m->partials_n < need) {
         if (m->partials) cudaFree(m->partials);
@@ -1333,7 +1137,7 @@ int tm_props_workspace(tm_mesh* m) {
         TM_CUDA(cudaMalloc(&m->partials, need * sizeof(double)));
         m->partials_n = need;
     }
-    if (!m->aux) TM_CUDA(cudaMalloc(&m->aux, sizeof(double2) * 8 * (size_t)((m->V + 31) & ~31)));
+    if (!m->aux) TM_CUDA(cudaMalloc(&m->aux, sizeof(double) * 8 * (size_t)((m->V + 31) & ~31)));
     return 0;
 }
 
@@ -1366,11 +1170,11 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     if (nb <= 0) {
         // a rank of a tiny partitioned mesh may own nothing: it still takes part in the reduction / exchange
     } else if (write_vprops) {
-        k_props<true, true, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, ncols, nq, R, 1);
+        k_props<true, true, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, m->vprops, m->partials, ncols, nq, R);
     } else if (full) {
-        k_props<true, false, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R, 1);
+        k_props<true, false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R);
     } else {
-        k_props<false, false, false><<<nb, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R, 1);
+        k_props<false, false, false><<<nb, TM_PROPS_THREADS, 0, m->stream>>>(mv, P, m->pos, nullptr, m->partials, ncols, nq, R);
     }
     TM_LAUNCHED();
     if (ngen > 0) {
@@ -1385,8 +1189,8 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     // sweep reads it) from a second, list-driven launch that reduces nothing
     const SweepRange G = tm_ghost_range(m);
     if (G.count > 0) {
-        k_props<false, false, true><<<(G.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS, TM_PROPS_THREADS, PROPS_SMEM, m->stream>>>(
-            mv, P, m->pos, nullptr, m->partials, 0, 0, G, 0);
+        k_props<false, false, true><<<(G.count + TM_PROPS_THREADS - 1) / TM_PROPS_THREADS, TM_PROPS_THREADS, 0, m->stream>>>(
+            mv, P, m->pos, nullptr, nullptr, 0, 0, G);
         TM_LAUNCHED();
     }
     if (pairs && tm_join_pairs(m)) return 1;            // the reduction adds the pair sweep's partials
@@ -1412,12 +1216,11 @@ int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p) {
 // the ring gradient of the vertices of R on stream st: the closed-fan sweep, then the generic vertices if any
 static int launch_grad_kernels(tm_mesh* m, const DevParams& P, const double* frc, const SweepRange& R, const VVFuse& U,
                                cudaStream_t st) {
-    if (ring_smem_optin()) return 1;
     const int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     const MeshView mv = m->view();
-    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
-    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
-    else k_grad<0><<<nb, TM_GRAD_THREADS, GRAD_SMEM, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    else k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
     TM_LAUNCHED();
     if (m->n_generic > 0) {
         const int gb = (m->n_generic + 127) / 128;

@@ -243,6 +243,20 @@ __global__ void k_batch_apply(Topo t, int nrem, const int* __restrict__ rem, con
     if (sel[p] == want) d_flip(t, edges[p]);
 }
 
+// trimem_energy (kernel.h:110-122) with the reference sums' reciprocals multiplied in: three independent short
+// chains instead of three IEEE divisions on the ordered scan's critical path (the value differs from energy_of's
+// in the last bit; the batch sweep has no decision-for-decision counterpart in the reference to stay aligned with)
+__device__ __forceinline__ double energy_mul(const DevParams& P, const double* s) {
+    const double da = fma(s[0], P.inv_ref_area, -1.0), dv = fma(s[1], P.inv_ref_volume, -1.0),
+                 dc = fma(s[2], P.inv_ref_curvature, -1.0);
+    double e = P.kappa_a * da * da;
+    e = fma(P.kappa_v * dv, dv, e);
+    e = fma(P.kappa_c * dc, dc, e);
+    e = fma(P.kappa_t, s[4], e);
+    e = fma(P.kappa_r, s[5], e);
+    return fma(P.kappa_b, s[3], e);
+}
+
 // ordered Metropolis scan over the round (the decisions are sequential, ~50 flops per
 // proposal; the warp fetches 32 proposals' data at a time); also compacts the not-yet-processed proposals for the next round and appends
 // the applied / reverted flips to the replay list.
@@ -284,7 +298,7 @@ __global__ void k_batch_metropolis(DevParams P, int nrem, const int* __restrict_
         int ed = 0;
         if (s == 1) {
             for (int q = 0; q < 6; q++) d[q] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q];
-            up = u[p];
+            up = log(u[p]);                              // accept iff log(u) <= -dE: no exponential in the chain
             ed = edges[p];
         }
         unsigned todo = __ballot_sync(FULL, s == 1);
@@ -297,10 +311,9 @@ __global__ void k_batch_metropolis(DevParams P, int nrem, const int* __restrict_
             for (int q = 0; q < 6; q++) { dk[q] = __shfl_sync(FULL, d[q], k); props[q] -= dk[q]; }
             const double uk = __shfl_sync(FULL, up, k);
             const int ek = __shfl_sync(FULL, ed, k);
-            const double en = energy_of(P, props);
+            const double en = energy_mul(P, props);
             const double de = en - e0;
-            const double alpha = de < 0.0 ? 1.0 : exp(-de);
-            if (uk <= alpha) {
+            if (de < 0.0 || uk <= -de) {
                 e0 = en;
                 ++nacc;
             } else {
@@ -325,7 +338,7 @@ __global__ void k_iota(int n, int* a) {
 }
 
 __global__ void k_init_state(DevParams P, double* state) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) state[6] = energy_of(P, state);
+    if (threadIdx.x == 0 && blockIdx.x == 0) state[6] = energy_mul(P, state);
 }
 
 __global__ void k_evp(MeshView mv, Topo t, NlView nl, DevParams P, int e, double* out, int* err) {

@@ -427,181 +427,6 @@ int build_cells(tm_mesh* m, tm_nlist* nl, int** cell_of_out) {
 }
 
 // Verlet rows: tight grid -> counting sort of the vertices by cell -> single search pass.
-// ---- tile lists ---------------------------------------------------------------------------------------
-// The pair sweep over a verlet list gathers ~600 position records per warp that are only ~170 distinct ones
-// (vertices are Morton-ordered, neighbours of neighbours are neighbours), and a per-lane gather costs an L1
-// tag look-up per lane: the sweep was bound by that rate and by the fp64 pipe at once. The tile lists restate
-// the rows per tile of TM_TILE consecutive vertices = one thread block of the sweep:
-//   * halo list: the distinct out-of-tile neighbours of the tile's vertices (ascending). The block loads its
-//     TM_TILE own records and the halo records into shared memory ONCE; every pair then reads shared memory.
-//   * entries hold local indices (tile vertex, or TM_TILE + halo index), per vertex in three groups:
-//     upper in-tile (j > i), halo, lower in-tile (j < i).
-//   * an in-tile pair is evaluated once, by its lower vertex (its "upper" entry), which leaves the slope factor
-//     in the tile's slope array at the slot its partner will read: the entry carries that slot; the partner's
-//     k-th lower entry reads slot lo_off + k. Fixed slots, fixed order: bit-reproducible, no atomics.
-// Rows are ascending in the neighbour id, so a row is [below the tile | lower | upper | above the tile].
-constexpr int TILE_HB = 4096;               // halo entries of a tile before de-duplication
-
-__device__ __forceinline__ int tile_block_scan(int v, int* total, int* wsum /* TM_TILE / 32 + 1 */) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int s = lane < TM_TILE / 32 ? wsum[lane] : 0, is = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, is, o); if (lane >= o) is += t; }
-        if (lane < TM_TILE / 32) wsum[lane] = is - s;
-        if (lane == TM_TILE / 32 - 1) wsum[TM_TILE / 32] = is;
-    }
-    __syncthreads();
-    const int r = inc - v + wsum[w];
-    *total = wsum[TM_TILE / 32];
-    __syncthreads();
-    return r;
-}
-
-// status: [0] a tile did not fit (halo / slope capacity, row too long, asymmetric list), [1] largest halo,
-// [2] largest number of in-tile pairs
-__global__ void __launch_bounds__(TM_TILE)
-k_tile_build(int V, const int* __restrict__ row_cnt, const int* __restrict__ row_j, int cap, int hcap, int slcap,
-             int* __restrict__ tile_halo, int* __restrict__ tile_info, unsigned* __restrict__ tile_ent,
-             unsigned* __restrict__ tile_cnt, unsigned short* __restrict__ tile_lo, int* __restrict__ status) {
-    __shared__ int hbuf[TILE_HB];
-    __shared__ int wsum[TM_TILE / 32 + 1];
-    __shared__ unsigned short s_lo[TM_TILE];
-    __shared__ unsigned char s_nb[TM_TILE];
-    const int tid = threadIdx.x, b = blockIdx.x, tile0 = b * TM_TILE, i = tile0 + tid;
-    const bool live = i < V;
-    const int n = live ? row_cnt[i] : 0;
-    const int* row = row_j + tm_row_base(live ? i : 0, cap);
-    int nb = 0, nlo = 0, nup = 0, nab = 0;
-    for (int k = 0; k < n; k++) {
-        const int j = __ldg(row + k * 32);
-        if (j < tile0) ++nb; else if (j < i) ++nlo; else if (j < tile0 + TM_TILE) ++nup; else ++nab;
-    }
-    const int nh = nb + nab;
-    int htot, lotot;
-    const int hoff = tile_block_scan(nh, &htot, wsum);
-    const int looff = tile_block_scan(nlo, &lotot, wsum);
-    if (__syncthreads_or(n > 255) || htot > TILE_HB || lotot > slcap || lotot > 65535) {
-        if (tid == 0) status[0] = 1;
-        return;
-    }
-    s_lo[tid] = (unsigned short)looff;
-    s_nb[tid] = (unsigned char)nb;
-    {
-        int w = hoff;
-        for (int k = 0; k < n; k++) {
-            const int j = __ldg(row + k * 32);
-            if (j < tile0 || j >= tile0 + TM_TILE) hbuf[w++] = j;
-        }
-    }
-    int npad = 2;
-    while (npad < htot) npad <<= 1;
-    for (int k = htot + tid; k < npad; k += TM_TILE) hbuf[k] = 0x7fffffff;
-    __syncthreads();
-    for (int size = 2; size <= npad; size <<= 1) {            // bitonic sort, ascending
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = tid; k < (npad >> 1); k += TM_TILE) {
-                const int lo = 2 * k - (k & (stride - 1)), hi = lo + stride;
-                const int a = hbuf[lo], c = hbuf[hi];
-                const bool up = (lo & size) == 0;
-                if ((a > c) == up) { hbuf[lo] = c; hbuf[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    // distinct ids, compacted in place: every thread owns a contiguous chunk, reads it, then writes
-    constexpr int CH = TILE_HB / TM_TILE;
-    int mine[CH];
-    int cnt = 0;
-    const int c0 = tid * CH;
-#pragma unroll
-    for (int u = 0; u < CH; u++) {
-        const int k = c0 + u;
-        int v = 0x7fffffff;
-        if (k < htot) { v = hbuf[k]; if (k > 0 && hbuf[k - 1] == v) v = 0x7fffffff; }
-        mine[u] = v;
-        cnt += v != 0x7fffffff;
-    }
-    int ndist;
-    int woff = tile_block_scan(cnt, &ndist, wsum);          // (barriers inside: all reads precede all writes)
-#pragma unroll
-    for (int u = 0; u < CH; u++) if (mine[u] != 0x7fffffff) hbuf[woff++] = mine[u];
-    __syncthreads();
-    if (ndist > hcap) { if (tid == 0) status[0] = 1; return; }
-    for (int k = tid; k < ndist; k += TM_TILE) tile_halo[(size_t)b * hcap + k] = hbuf[k];
-    if (tid == 0) {
-        tile_info[2 * b] = ndist; tile_info[2 * b + 1] = lotot;
-        atomicMax(status + 1, ndist); atomicMax(status + 2, lotot);
-    }
-    if (!live) return;
-    unsigned* col = tile_ent + tm_row_base(i, cap);
-    int iu = 0, ih = nup, il = nup + nh;
-    bool bad = false;
-    for (int k = 0; k < n; k++) {
-        const int j = __ldg(row + k * 32);
-        if (j >= tile0 && j < tile0 + TM_TILE) {
-            const int jl = j - tile0;
-            if (j > i) {
-                // rank of i among the lower in-tile entries of row j
-                const int nj = __ldg(row_cnt + j);
-                const int* rj = row_j + tm_row_base(j, cap);
-                int lo = 0, hi = nj;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(rj + mid * 32) < i) lo = mid + 1; else hi = mid; }
-                if (lo >= nj || __ldg(rj + lo * 32) != i) bad = true;
-                const unsigned slot = (unsigned)s_lo[jl] + (unsigned)(lo - (int)s_nb[jl]);
-                col[(iu++) * 32] = (unsigned)jl | (slot << 16);
-            } else col[(il++) * 32] = (unsigned)jl;
-        } else {
-            int lo = 0, hi = ndist;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (hbuf[mid] < j) lo = mid + 1; else hi = mid; }
-            col[(ih++) * 32] = (unsigned)(TM_TILE + lo);
-        }
-    }
-    if (bad) status[0] = 1;
-    tile_cnt[i] = (unsigned)nup | ((unsigned)nh << 8) | ((unsigned)nlo << 16);
-    tile_lo[i] = (unsigned short)looff;
-}
-
-static void free_tiles(tm_nlist* nl) {
-    tm_pool_free(nl->device, nl->tile_halo); tm_pool_free(nl->device, nl->tile_info);
-    tm_pool_free(nl->device, nl->tile_ent); tm_pool_free(nl->device, nl->tile_cnt); tm_pool_free(nl->device, nl->tile_lo);
-    nl->tile_halo = nl->tile_info = nullptr; nl->tile_ent = nl->tile_cnt = nullptr; nl->tile_lo = nullptr;
-    nl->tile_T = 0;
-}
-
-// tile lists of a freshly built verlet list over the whole mesh; a list that does not fit the capacities simply
-// has none (the sweep then reads the rows)
-int build_tiles(tm_mesh* m, tm_nlist* nl) {
-    const int V = m->V, dev = m->device, nt = (V + TM_TILE - 1) / TM_TILE;
-    if (nl->rows_count != V || nl->row_cap > 255 || getenv("TRIMEM_B200_NO_TILES")) return 0;
-    const int hcap = 1024, slcap = 6144;
-    nl->tile_hcap = hcap;
-    nl->tile_halo = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)nt * hcap);
-    nl->tile_info = (int*)tm_pool_alloc(dev, sizeof(int) * (2 * (size_t)nt + 4));
-    nl->tile_ent = (unsigned*)tm_pool_alloc(dev, sizeof(unsigned) * (size_t)nl->row_cap * 32 * ((V + 31) / 32));
-    nl->tile_cnt = (unsigned*)tm_pool_alloc(dev, sizeof(unsigned) * (size_t)V);
-    nl->tile_lo = (unsigned short*)tm_pool_alloc(dev, sizeof(unsigned short) * (size_t)V);
-    if (!nl->tile_halo || !nl->tile_info || !nl->tile_ent || !nl->tile_cnt || !nl->tile_lo) { free_tiles(nl); return 0; }
-    int* status = nl->tile_info + 2 * (size_t)nt;
-    TM_CUDA(cudaMemsetAsync(status, 0, sizeof(int) * 4, m->stream));
-    k_tile_build<<<nt, TM_TILE, 0, m->stream>>>(V, nl->row_cnt, nl->row_j, nl->row_cap, hcap, slcap, nl->tile_halo,
-                                               nl->tile_info, nl->tile_ent, nl->tile_cnt, nl->tile_lo, status);
-    TM_LAUNCHED();
-    TM_CUDA(cudaGetLastError());
-    int hs[4] = {0, 0, 0, 0};
-    TM_CUDA(cudaMemcpyAsync(hs, status, sizeof(hs), cudaMemcpyDeviceToHost, m->stream));
-    TM_CUDA(cudaStreamSynchronize(m->stream));
-    if (getenv("TRIMEM_B200_DEBUG")) fprintf(stderr, "[trimem_b200] tile lists: %d tiles, overflow %d, largest halo %d, most in-tile pairs %d\n", nt, hs[0], hs[1], hs[2]);
-    if (hs[0]) { free_tiles(nl); return 0; }
-    nl->tile_T = TM_TILE; nl->tile_hmax = hs[1]; nl->tile_slmax = hs[2];
-    return 0;
-}
-
 int build_verlet(tm_mesh* m, tm_nlist* nl) {
     const int V = m->V, vb = (V + NT - 1) / NT, dev = m->device;
     if (nl->excl == 2 && tm_ensure_ring2(m)) return 1;
@@ -689,7 +514,7 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
     k_save_positions<<<vb, NT, 0, m->stream>>>(V, m->pos, nl->x_build); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     nl->n_entries = -1;                 // counted on demand (tm_nlist_info)
-    return build_tiles(m, nl);
+    return 0;
 }
 
 }  // namespace
@@ -713,7 +538,7 @@ int tm_nlist_create(tm_mesh* m, int kind, double rlist, int exclusion_level, dou
     nl->device = m->device;
     nl->kind = kind; nl->excl = exclusion_level; nl->rlist = rlist; nl->box_eps = box_eps; nl->V = m->V;
     nl->layout_epoch = m->layout_epoch;
-    static unsigned long long g_serial = 0;
+    static std::atomic<unsigned long long> g_serial{0};      // (lists are created from several host threads)
     nl->serial = ++g_serial;
     if (kind == TM_NLIST_VERLET) {
         if (build_verlet(m, nl)) { tm_nlist_destroy(nl); return 1; }
@@ -735,7 +560,6 @@ int tm_nlist_destroy(tm_nlist* nl) {
     tm_pool_free(nl->device, nl->row_cnt); tm_pool_free(nl->device, nl->row_j);
     tm_pool_free(nl->device, nl->cell_of);
     tm_pool_free(nl->device, nl->x_build);
-    free_tiles(nl);
     delete nl;
     return 0;
 }

@@ -47,9 +47,10 @@ class MeshHMC:
         callback: ``callback(x, counter)`` after every step (default: no-op).
         counter: step counters shared with a flip proposal (default: fresh counters).
         options: see ``trimem.mc.hmc.HMC``.
+        rng: ``numpy.random.RandomState`` of this chain (default: numpy's global state, as in the reference).
     """
 
-    def __init__(self, mesh, estore, callback=None, counter=None, options={}, verbose=True):
+    def __init__(self, mesh, estore, callback=None, counter=None, options={}, verbose=True, rng=None):
         self.trimesh = getattr(mesh, "trimesh", mesh)
         self.mesh = mesh
         self.estore = estore
@@ -75,6 +76,9 @@ class MeshHMC:
         self.T = self.Tinit
         self.x = self.trimesh.points().copy()
         self.last = None            # (dh, accepted, [U0, K0, U1, K1]) of the last step
+        # source of the momenta and the Metropolis variate: numpy's global state like the reference, or the chain's
+        # own numpy.random.RandomState (independent chains driven from several threads, ranks of a partitioned mesh)
+        self.rng = np.random if rng is None else rng
 
     def _set_mesh(self, x):
         np.copyto(self.trimesh.points(), x)
@@ -82,13 +86,13 @@ class MeshHMC:
     def _step(self):
         """Metropolis step (hmc.py:133-155)."""
         p_var = self.m * self.T
-        p = np.random.normal(size=self.x.shape) * np.sqrt(p_var)
+        p = self.rng.normal(size=self.x.shape) * np.sqrt(p_var)
         self._set_mesh(self.x)
         xn, pn, st = m.vv_integrate(self.trimesh, self.estore, p, self.m, self.dt, self.L)
         # (nlog_prob(xn) + K(pn)) - (nlog_prob(x) + K(p)), in the reference's order of operations
         dh = ((st[2] + st[3]) - (st[0] + st[1])) / self.T
         a = 1.0 if dh <= 0 else np.exp(-dh)
-        u = np.random.uniform()
+        u = self.rng.uniform()
         acc = u <= a
         if acc:
             self.x = xn

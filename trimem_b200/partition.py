@@ -39,6 +39,22 @@ def setup(mesh, rank, nranks, allgather, nlist_factory=None):
     return nl
 
 
+def setup_core(mesh, estore, rank, nranks, allgather):
+    """The same for the drop-in classes: ``mesh`` a ``core.TriMesh`` holding the same topology and positions on
+    every rank, ``estore`` its ``core.EnergyManager`` (built before the mesh is partitioned: reference sums and
+    neighbour list of the whole mesh). Afterwards ``estore.energy / gradient / update_repulsion``, ``core.vv_integrate``
+    and ``hmc.MeshHMC.step`` are collective: every rank makes the same calls (seed the chains identically)."""
+    if not 0 <= rank < nranks:
+        raise ValueError(f"rank {rank} out of range for {nranks} ranks")
+    mesh.part_create(rank, nranks)
+    handles = allgather(mesh.part_export())
+    for peer, h in enumerate(handles):
+        if peer != rank:
+            mesh.part_attach_ipc(peer, h)
+    estore.part_prepare(mesh)
+    allgather(b"ready")
+
+
 def combine_rows(allgather, rows):
     """Full (V,3) array from the ranks' owned rows (each rank reports zeros elsewhere)."""
     parts = allgather(rows)
