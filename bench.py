@@ -32,6 +32,11 @@ sys.path.insert(0, ROOT)
 
 FLUSH_BYTES = 512 << 20          # > 126 MB L2
 
+# Counters of the three sweeps from the committed `ncu --set full` capture of this build at 655,362 vertices
+# (per launch; profiles/README.md says how they were taken). They explain the live timings of the roofline object.
+NCU_SOURCE = "profiles/r02_ncu_full_sweeps.txt (per launch, 655,362 vertices)"
+NCU = {}
+
 
 def env_int(name, default):
     try:
@@ -149,61 +154,60 @@ def time_reference(subdiv, steps, warmup, threads=None):
 
 
 def replica_run(args, core, cabi, workload, rank, world, local, barrier):
-    """BASELINE config 5: independent HMC replicas, `--replicas` per GPU, each a 40,962-vertex membrane of
-    the reduced-volume / kappa_b sweep with its own mesh handle and CUDA stream; no communication. Timed:
-    every replica integrates one device-resident trajectory of L steps, all enqueued before the first
-    is waited for; aggregate vertex-steps/s over the whole job."""
+    """BASELINE config 5: independent HMC + flip chains, `--replicas` per GPU, each a 40,962-vertex membrane of the
+    reduced-volume / kappa_b sweep; no communication. Every chain runs through the PUBLIC API (core.TriMesh,
+    core.EnergyManager, trimem_b200.hmc.MeshHMC, core.pflip) on a host thread of its own: per move one MeshHMC.step()
+    (L velocity-Verlet steps on the device + Metropolis, end point and momenta copied back), update_repulsion
+    (mc/evaluators.py:181-182), and every 10th move one pflip(ratio 0.1) (mc/hmc.py:325-372 with the cadence of
+    config 2). The bindings release the interpreter lock around device work, so the chains' kernels overlap on the
+    GPU; timed: host wall clock from the common start to the last chain's finish."""
+    from trimem_b200 import hmc
     R = args.replicas
     L = max(1, args.leapfrog_steps)
-    reps = []
+    chains = []
     for k in range(R):
         gid = rank * R + k                                        # position in the 8 x 8 sweep of config 5
         mesh, estore, x0 = workload.make_case(core, 6, repulsion="physical", n_search="verlet-list", seed=gid,
                                               kappa=(10.0 * (1 + gid % 8), 1.0e6, 1.0e6, 0.0, 1.0e5, 1.0e3),
                                               fracs=(1.0, 0.5 + 0.5 * ((gid // 8) % 8) / 7.0, 1.0))
-        arrs = mesh.halfedge_arrays()[:4]
-        cm = cabi.Mesh(*arrs, xyz=x0, device=local)
-        rp = estore.eparams.repulse_params
-        nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
-        par = workload.abi_params(estore)
-        p0 = np.random.default_rng(1000 + gid).normal(size=x0.shape)
-        reps.append((cm, nl, par, x0, p0))
-    V = reps[0][0].V
-    dt = 1.0e-6
+        ch = hmc.MeshHMC(mesh, estore, options={"time_step": 1.0e-6, "num_integration_steps": L, "info_step": 0},
+                         verbose=False, rng=np.random.RandomState(1000 + gid))
+        chains.append((mesh, estore, ch, gid))
+    V = chains[0][0].n_vertices()
+    stats = [None] * R
 
-    def reset():
-        for cm, nl, par, x0, p0 in reps:
-            cm.set_positions(x0); cm.set_momenta(p0)
-        for r in reps:
-            r[0].sync()
-    for _ in range(6):                  # both record-array parities: direct launch, graph capture, first replay
-        reset()
-        for cm, nl, par, _, _ in reps:
-            cm.vv_integrate_async(nl, par, 1.0, dt, L)
-        for r in reps:
-            r[0].sync()
-    n_rounds = 5
+    def run(k, n_moves, first_move):
+        mesh, estore, ch, gid = chains[k]
+        flips = acc0 = 0
+        for mv in range(first_move, first_move + n_moves):
+            ch.step()
+            estore.update_repulsion(mesh)
+            if (mv + 1) % 10 == 0:
+                flips += core.pflip(mesh, estore, 0.1, seed=977 * gid + mv)
+        stats[k] = (ch.acc, ch.i, flips)
+
+    def all_chains(n_moves, first_move):
+        th = [threading.Thread(target=run, args=(k, n_moves, first_move)) for k in range(R)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    all_chains(10, 0)                   # warm-up: trajectory graphs captured, one flip sweep, list pools filled
+    n_moves = 20
+    launches0 = core.launch_count()
     barrier()
-    wall = 0.0
-    for _ in range(n_rounds):
-        reset()
-        t0 = time.perf_counter()
-        for cm, nl, par, _, _ in reps:
-            cm.vv_integrate_async(nl, par, 1.0, dt, L)
-        for r in reps:
-            r[0].sync()
-        wall += time.perf_counter() - t0
-    # one replica alone, for the concurrency gain
-    cm, nl, par, x0, p0 = reps[0]
-    reset()
-    cm.timer_start(); cm.vv_integrate_async(nl, par, 1.0, dt, L); solo_ms = cm.timer_stop()
-    cm.vv_integrate_async(nl, par, 1.0, dt, L, True)
-    st = cm.vv_stats(par)[0]
-    assert np.isfinite(st).all()
-    for cm, nl, _, _, _ in reps:
-        nl.close(); cm.close()
-    return {"wall_s": wall, "rounds": n_rounds, "L": L, "R": R, "V": V, "solo_ms_per_step": solo_ms / L,
-            "hamiltonian": {"H0": st[0] + st[1], "H1": st[2] + st[3], "time_step": dt}}
+    t0 = time.perf_counter()
+    all_chains(n_moves, 10)
+    wall = time.perf_counter() - t0
+    launches = core.launch_count() - launches0
+    # one chain alone, for the concurrency gain
+    t0 = time.perf_counter()
+    run(0, 10, 30)
+    solo = (time.perf_counter() - t0) / 10
+    e_last = chains[0][1].energy(chains[0][0])
+    assert np.isfinite(e_last)
+    return {"wall_s": wall, "moves": n_moves, "L": L, "R": R, "V": V, "solo_ms_per_move": 1e3 * solo,
+            "hmc_acceptance": float(np.mean([s[0] / max(s[1], 1) for s in stats])),
+            "flips_accepted_per_sweep": float(np.mean([s[2] for s in stats])) / max(1, n_moves // 10),
+            "launches": int(launches)}
 
 
 def hmc_step_run(args, core, workload, rank):
@@ -299,6 +303,21 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
         eg_ms += cm.timer_stop()
     barrier()
     e_part, _ = cm.fetch_energy(par)
+    # parity with the REFERENCE on this mesh (tests/golden/ico10_stress_verlet2.npz: the reference's six sums, energy
+    # and 4,096 sampled gradient rows, tests/golden/make_golden.py big): every rank checks the sampled rows it owns
+    gold_path = os.path.join(ROOT, "tests", "golden", f"ico{args.part_subdiv}_stress_verlet2.npz")
+    gold_cmp = None
+    if os.path.exists(gold_path):
+        gold = np.load(gold_path)
+        g_own = cm.fetch_gradient()
+        lo, hi = info["first"], info["first"] + info["count"]
+        d2h = cm.vertex_order()                       # device slot -> host vertex
+        owned = np.zeros(V, bool); owned[d2h[lo:hi]] = True
+        rows = gold["rows"][owned[gold["rows"]]]
+        want = gold["grad_rows"][owned[gold["rows"]]]
+        num = float(np.sum((g_own[rows] - want) ** 2)); den = float(np.sum(want ** 2))
+        gold_cmp = {"energy_rel_diff": abs(e_part - float(gold["energy"])) / abs(float(gold["energy"])),
+                    "grad_rows_sq_err": num, "grad_rows_sq_norm": den, "rows_checked": int(len(rows))}
     # leapfrog
     L = max(1, args.leapfrog_steps)
     lf_dt = 2.0e-8 * (655362.0 / V)
@@ -345,6 +364,33 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
         dist.all_reduce(halo, op=dist.ReduceOp.MAX)
     eg_ms, lf_ms, rebuild_ms = float(t[0]), float(t[1]), float(t[2])
     nl2.close(); nl.close(); cm.close()
+    if gold_cmp is not None:
+        gt = torch.tensor([gold_cmp["grad_rows_sq_err"], gold_cmp["grad_rows_sq_norm"], gold_cmp["rows_checked"]],
+                          dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(gt, op=dist.ReduceOp.SUM)
+        gold_cmp = {"energy_rel_diff_vs_reference": gold_cmp["energy_rel_diff"],
+                    "grad_rows_rel_diff_vs_reference": float(np.sqrt(float(gt[0]) / float(gt[1]))),
+                    "rows_checked": int(gt[2]), "golden": os.path.relpath(gold_path, ROOT)}
+        assert gold_cmp["energy_rel_diff_vs_reference"] < 1e-10 and gold_cmp["grad_rows_rel_diff_vs_reference"] < 1e-10, gold_cmp
+    # the same partition through the drop-in classes: core.TriMesh.part_* / EnergyManager.part_prepare, then one
+    # MeshHMC move (collective; every rank seeds its chain identically)
+    from trimem_b200 import hmc
+    api = None
+    try:
+        if world > 1:
+            partition.setup_core(mesh, estore, rank, world, allgather)
+        chain = hmc.MeshHMC(mesh, estore, options={"time_step": lf_dt, "num_integration_steps": L, "info_step": 0},
+                            verbose=False, rng=np.random.RandomState(4242))
+        chain.step()
+        barrier()
+        t1 = time.perf_counter()
+        chain.step()
+        barrier()
+        api = {"hmc_move_ms": 1e3 * (time.perf_counter() - t1), "L": L, "accepted": bool(chain.last[1]),
+               "what": "MeshHMC.step() through trimem_b200.core on the partitioned mesh, host buffers in and out"}
+    except Exception as exc:            # noqa: BLE001  (reported, not fatal for the device-resident numbers)
+        api = {"error": repr(exc)[:300]}
     return {"workload": f"ONE icosphere subdiv={args.part_subdiv} ({V} vertices), tether + stress repulsion, verlet-list excl 2, "
                         f"vertices partitioned over {world} rank(s)" + ("" if world > 1 else " (unpartitioned base of the scaling curve)"),
             "scaling": "strong", "n_vertices": V, "ranks": world,
@@ -355,6 +401,7 @@ def partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dis
             "hamiltonian": {"H0": h0, "H1": h1, "time_step": lf_dt},
             "max_owned": int(halo[2]), "max_ghost_ring1": int(halo[0]), "max_pulled_per_update": int(halo[1]),
             "energy_rel_diff_vs_whole_mesh_on_one_device": abs(e_part - e_single) / abs(e_single),
+            "reference_golden": gold_cmp, "public_api": api,
             "exchange": "halo positions pulled over NVLink from the owners' arrays (cudaIpc), six sums added in rank order; "
                         "device-side sequencing, no NCCL / host on the data path" if world > 1 else "none",
             "setup_s": setup_s}
@@ -391,12 +438,12 @@ def main():
         steps = max(1, args.steps)
         # bounded: one E+G takes ~1.4 s on 8 cores at 655k vertices; cap the run at ~3 minutes
         probe_budget = 150.0
-        r = time_reference(args.subdiv, 1, min(args.warmup, 1))
+        r = time_reference(args.subdiv, 1, 1)
         steps = max(1, min(steps, int(probe_budget / max(r["ms_per_step"] / 1e3, 1e-3))))
         if steps > 1:
-            r = time_reference(args.subdiv, steps, 0)
+            r = time_reference(args.subdiv, steps, max(0, args.warmup))
         line = {"impl": "reference", "metric": "energy+gradient evals/s", "value": r["value"], "unit": "evals/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "n_gpus": args.gpus, "steps": steps, "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl, "n_vertices": V, "timing": "host wall clock, working set (~70 MB) exceeds CPU caches"},
                 "cpu_baseline": {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
@@ -552,6 +599,22 @@ def main():
     assert np.isfinite(st).all(), "leapfrog trajectory diverged"
     cm.set_positions(x0)
 
+    # ---- one HMC move (L leapfrog steps + both Hamiltonian evaluations + Metropolis) through the public API with
+    # host buffers: what a trimem user's MeshHMC.step() costs end to end at the headline size
+    from trimem_b200 import hmc as hmc_mod
+    np.copyto(mesh.points(), x0)
+    chain = hmc_mod.MeshHMC(mesh, estore, options={"time_step": lf_dt, "num_integration_steps": L, "info_step": 0},
+                            verbose=False, rng=np.random.RandomState(7 + rank))
+    chain.step(); chain.step()
+    barrier()
+    t0 = time.perf_counter()
+    n_moves_api = 5
+    for _ in range(n_moves_api):
+        chain.step()
+    barrier()
+    hmc_api_ms = 1e3 * (time.perf_counter() - t0) / n_moves_api
+    np.copyto(mesh.points(), x0)
+
     repl = replica_run(args, core, cabi, workload, rank, world, local, barrier) if args.replicas > 0 else None
     hmc2 = hmc_step_run(args, core, workload, rank) if (rank == 0 and not args.no_hmc_step) else None
     part = None
@@ -562,10 +625,10 @@ def main():
     e_dev, _ = cm.energy(nl, p)
 
     # max over ranks
-    t = torch.tensor([total_ms, e2e_s, lf_ms, repl["wall_s"] if repl else 0.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s, lf_ms, repl["wall_s"] if repl else 0.0, hmc_api_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, lf_ms, repl_s = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    total_ms, e2e_s, lf_ms, repl_s, hmc_api_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -585,11 +648,24 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         ms_step = total_ms / args.steps
         value = world * args.steps / (total_ms / 1e3)
-        # k_grad: SURVEY 8(d) gradient sweep 2 without the list (84 B/vertex) + the stored pair force it
-        # reads instead (24 B/vertex); DESIGN.md section 4
-        alg_grad = (workload.bytes_grad_sweep(0.0, False) + 24.0) * V
-        achieved = alg_grad / (k_ms[2] * 1e-3) / 1e9
+        # ALGORITHMIC bytes per launch, per vertex:
+        #   property sweep   x 24 + ring row 28 + rho 8                                  =  60
+        #   pair sweep       x 24 + list 4P+4 + pair force 24                            =  52 + 4P
+        #   gradient sweep   x 24 + ring row 28 + rho 8 + g 24 (+ pair force 24 read)    = 108
+        # (the slot quantity tau the property sweep hands to the gradient sweep, 8 B per ring slot, is an
+        #  implementation choice, not algorithmic traffic: it shows up in `traffic`, not in `achieved`)
+        alg = {"k_props": 60.0 * V, "k_pairs": (52.0 + 4.0 * P) * V, "k_grad": (workload.bytes_grad_sweep(0.0, False) + 24.0) * V}
+        kms = {"k_props": k_ms[1], "k_pairs": k_ms[3], "k_grad": k_ms[2]}
+        kernels = {k: {"ms_per_launch": kms[k], "algorithmic_bytes_per_launch": alg[k],
+                       "achieved_GBps": alg[k] / (kms[k] * 1e-3) / 1e9, "frac": alg[k] / (kms[k] * 1e-3) / 1e9 / peak,
+                       **NCU.get(k, {})} for k in alg}
+        dom = max(kms, key=kms.get)                      # the dominant kernel of the step = the longest one
         alg_eg = workload.bytes_eg(P, True) * V
+        lf_ms_step = lf_ms / n_traj / L
+        # 1 gradient() (its property sweep + its gradient sweep, the list read in both) + the x, p update
+        alg_lf = (workload.bytes_grad_props(P, True) + workload.bytes_grad_sweep(P, True) + 96.0) * V
+        part_compact = None if not part else {k: part[k] for k in ("n_vertices", "ranks", "ms_per_eg", "leapfrog_ms_per_step",
+                                                                   "verlet_rebuild_ms") if k in part}
         line = {
             "metric": "energy+gradient evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -597,38 +673,51 @@ def main():
             "config": {"workload": wl, "n_vertices": V, "verlet_entries": int(n_entries), "entries_per_vertex": P,
                        "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                        "host_cores_bound_per_rank": bound_cpus,
-                       "l2": f"flushed before every timed step ({FLUSH_BYTES >> 20} MiB memset, outside the timed span)"},
+                       "l2": f"flushed before every timed step ({FLUSH_BYTES >> 20} MiB memset, outside the timed span)",
+                       # strong scaling of ONE partitioned mesh (BASELINE config 4), in short; details under "partitioned"
+                       "partitioned": part_compact},
             "clocks": clocks,
             "e2e": {"value": world * e2e_steps / e2e_s, "unit": "evals/s",
                     "h2d_bytes_per_step": 2 * V * 24, "d2h_bytes_per_step": V * 24 + 2 * 48,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
                     "phase_ms": {"np.copyto(mesh.points(), x)": e2e_phase_ms[0], "estore.energy(mesh)": e2e_phase_ms[1],
-                                 "estore.gradient(mesh)": e2e_phase_ms[2]}},
+                                 "estore.gradient(mesh)": e2e_phase_ms[2]},
+                    "hmc_move": {"what": f"MeshHMC.step() through trimem_b200.core / trimem_b200.hmc: {L} leapfrog steps on the device, "
+                                         "both Hamiltonian evaluations, Metropolis; momenta and positions in, end point and momenta out",
+                                 "ms_per_move": hmc_api_ms, "h2d_bytes_per_move": 2 * V * 24, "d2h_bytes_per_move": 2 * V * 24 + 32,
+                                 "mvertex_steps_per_s": world * L * V / (hmc_api_ms * 1e-3) / 1e6}},
             "leapfrog": {"what": f"device-resident velocity-Verlet trajectory of {L} steps (tm_vv_integrate_async): "
                                  f"{L + 1} gradient evaluations + {L} fused update kernels, L2 flushed before each trajectory",
-                         "ms_per_step": lf_ms / n_traj / L, "steps_per_s": world * n_traj * L / (lf_ms / 1e3),
+                         "ms_per_step": lf_ms_step, "steps_per_s": world * n_traj * L / (lf_ms / 1e3),
                          "mvertex_steps_per_s": world * n_traj * L / (lf_ms / 1e3) * V / 1e6,
                          "trajectories": n_traj, "hamiltonian": lf_stats},
             "replicas": None if not repl else {
-                "what": f"{repl['R']} independent {repl['V']}-vertex membranes per GPU (BASELINE config 5 sweep: kappa_b x volume_frac, "
-                        f"physical repulsion, verlet-list), each on its own stream; one {repl['L']}-step device-resident trajectory per "
-                        "replica per round, host wall clock around enqueue + wait, max over ranks",
-                "replicas_total": world * repl["R"], "steps_per_s": world * repl["R"] * repl["rounds"] * repl["L"] / repl_s,
-                "mvertex_steps_per_s": world * repl["R"] * repl["rounds"] * repl["L"] / repl_s * repl["V"] / 1e6,
-                "ms_per_step_per_replica_concurrent": 1e3 * repl_s / (repl["rounds"] * repl["L"]) / repl["R"],
-                "ms_per_step_one_replica_alone": repl["solo_ms_per_step"], "hamiltonian": repl["hamiltonian"]},
+                "what": f"{repl['R']} independent HMC + flip chains per GPU (BASELINE config 5: {repl['V']}-vertex membranes of the kappa_b x "
+                        f"volume_frac sweep, physical repulsion, verlet-list) through trimem_b200.hmc.MeshHMC / core.pflip / "
+                        f"update_repulsion, one host thread per chain; per move {repl['L']} leapfrog steps, every 10th move a "
+                        "pflip(0.1); host wall clock, max over ranks",
+                "chains_total": world * repl["R"], "moves_per_chain": repl["moves"],
+                "moves_per_s": world * repl["R"] * repl["moves"] / repl_s,
+                "mvertex_steps_per_s": world * repl["R"] * repl["moves"] * repl["L"] / repl_s * repl["V"] / 1e6,
+                "ms_per_move_per_chain_concurrent": 1e3 * repl_s / repl["moves"],
+                "ms_per_move_one_chain_alone": repl["solo_ms_per_move"],
+                "hmc_acceptance": repl["hmc_acceptance"], "flips_accepted_per_sweep": repl["flips_accepted_per_sweep"],
+                "gpu_launches": repl["launches"]},
             "hmc_step_config2": hmc2,
             "partitioned": part,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_grad (ring gather gradient sweep; fp64-issue-bound, DESIGN.md section 4)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_grad launch at 655,362 vertices from the
-                         # committed `ncu --set full` capture (profiles/r01l_ncu_full_sweeps.txt: 57.71 + 1.99 MB); below the
-                         # algorithmic bytes because part of the ring records is served by L2
-                         "traffic": 59.70e6 if args.subdiv == 8 else None,
-                         "traffic_source": "profiles/r01l_ncu_full_sweeps.txt (bytes per launch)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_grad, "ms_per_launch": k_ms[2],
+            "roofline": {"bound": "hbm", "kernel": dom + " (longest kernel of the step; all three sweeps are bound by instruction issue, "
+                                                     "fp64 at half rate, not by HBM: DESIGN.md section 4)",
+                         "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                         "traffic": NCU.get(dom, {}).get("dram_bytes_per_launch") if args.subdiv == 8 else None,
+                         "traffic_source": NCU_SOURCE, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": kms[dom],
+                         "kernels": kernels,
+                         # whole step: energy() + gradient() (one property sweep, one pair sweep, one gradient sweep: the
+                         # gradient reuses what the energy evaluated at the same positions) ...
                          "eg_algorithmic_bytes": alg_eg, "eg_frac_of_peak": alg_eg / (ms_step * 1e-3) / 1e9 / peak,
+                         # ... and the production figure: one leapfrog step (gradient only, nothing cached)
+                         "leapfrog_algorithmic_bytes": alg_lf, "leapfrog_frac_of_peak": alg_lf / (lf_ms_step * 1e-3) / 1e9 / peak,
                          "kernel_ms": {"energy_sweeps": k_ms[0], "props_for_gradient": k_ms[1], "ring_grad": k_ms[2],
                                        "pair_sweep": k_ms[3]}},
             "cpu_baseline": cpu,
