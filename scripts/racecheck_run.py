@@ -1,0 +1,18 @@
+"""Small run of the kernels that use shared memory or cross-thread ordering, for
+`compute-sanitizer --tool racecheck` / `--tool memcheck`: verlet build, cell-list pair sweep, ring sweeps, both flip
+modes, a short trajectory (icosphere subdiv 4, stress repulsion)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import trimem_b200.core as core
+from trimem_b200 import workload
+for ns in ("verlet-list", "cell-list"):
+    mesh, es, x0 = workload.make_case(core, 4, repulsion="stress", n_search=ns)
+    e, g = es.energy(mesh), es.gradient(mesh)
+    es.update_repulsion(mesh)
+    a = core.pflip(mesh, es, 0.1, seed=1)
+    b = core.flip(mesh, es, 0.02, seed=2)
+    p0 = np.random.default_rng(0).normal(size=x0.shape)
+    xn, pn, st = core.vv_integrate(mesh, es, p0, 1.0, 1.0e-6, 3)
+    print(ns, "E", e, "|g|", float(np.linalg.norm(g)), "pflip", a, "flip", b, "H", st[0] + st[1], st[2] + st[3])

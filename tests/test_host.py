@@ -140,5 +140,5 @@ def test_product_never_touches_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
                 for line in text.splitlines():
-                    if re.search(r"^\s*(import|from|#include)\b.*oracle", line) and "build_oracle" not in line:
+                    if re.search(r"^\s*(import|from|#include)\b.*oracle", line) or "oracle/" in line or "oracle\"" in line:
                         raise AssertionError(f"{fn}: {line.strip()}")

@@ -86,22 +86,9 @@ def build_host(force=False, verbose=False):
     return _run(cmd, verbose)
 
 
-def build_oracle(verbose=False):
-    """Compile the CPU checkers (test infrastructure): the plain-C restatement always, the
-    reference-source build only where /root/reference exists (this container)."""
-    odir = os.path.join(ROOT, "oracle")
-    log = ""
-    if os.path.exists(os.path.join(odir, "trimem_oracle.c")):
-        log += _run(["make", "-C", odir, "port"], verbose)
-    if os.path.isdir("/root/reference/src"):
-        log += _run(["make", "-C", odir, "-j8", "ref"], verbose)
-    return log
-
-
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_host(force, verbose)
-    build_oracle(verbose)
 
 
 if __name__ == "__main__":

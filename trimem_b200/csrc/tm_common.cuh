@@ -49,14 +49,13 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 #ifndef TM_GRAD_NT
 #define TM_GRAD_NT 128
 #endif
-// resident blocks per SM the register allocation aims at (measured on B200 at 655k vertices,
-// profiles/r01, r01g). With the ring records staged in shared memory the property sweep needs
-// 64-70 registers (6 blocks of 128: 55 us) and the ring gradient 128 without spilling (4 blocks:
-// 82 us; 96 registers / 5 blocks spills and takes 91 us, 80 / 6 blocks 122 us).
-// 64-thread blocks at the same number of resident warps drain a little more evenly than 128-thread ones
-// (property sweep 54.6 -> 52.6 us, ring gradient 81.3 -> 78.9 us).
+// resident blocks per SM the register allocation aims at (measured on B200 at 655,362 vertices, gpurun_out
+// r02f / r02i kernel timings): property sweep 8 blocks of 128 = 64 registers (44 bytes of spills) 42.2 us, 6 blocks
+// / 80 registers 44.6, 5 / 96 47.0, 4 / 120 50.9; ring gradient 6 blocks / 80 registers (84 bytes of spills) 46.3 us,
+// 5 / 96 47.5, 4 / 128 45.2-57 (depending on what the scheduler hoists), 8 / 64 48.7. 64- and 256-thread blocks
+// at the same number of resident warps: within 1 us.
 #ifndef TM_PROPS_MINB
-#define TM_PROPS_MINB 6
+#define TM_PROPS_MINB 8
 #endif
 #ifndef TM_GRAD_MINB
 #define TM_GRAD_MINB 5

@@ -131,6 +131,9 @@ __device__ __forceinline__ void props_slot(const DevParams& P, d3 xi, int word, 
 #ifndef TM_GRAD_GROUP
 #define TM_GRAD_GROUP 3
 #endif
+#ifndef TM_GRAD_TAU_EARLY
+#define TM_GRAD_TAU_EARLY 1
+#endif
 #ifndef TM_PROPS_GROUP
 #define TM_PROPS_GROUP 3
 #endif
@@ -881,9 +884,16 @@ struct GradWalk {
         axpy3(g, valid ? E_c : 0.0, pc.e);
         axpy3(g, valid ? -h * a : 0.0, pp.e);
     }
-    // the whole ring in one basic block (see PropsWalk::block): face 0 lies between the last spoke and spoke 0
+    // the whole ring in one basic block (see PropsWalk::block): face 0 lies between the last spoke and spoke 0.
+    // The slots' tau (coalesced, straight from DRAM: nobody has touched them since the property sweep wrote them)
+    // are all requested before the first face, so the walk pays that latency once and not once per group.
     template <int DMAX, bool MASK>
     __device__ __forceinline__ void block() const {
+#if TM_GRAD_TAU_EARLY
+        double ta[DMAX];
+#pragma unroll
+        for (int s = 0; s < DMAX; s++) ta[s] = (!MASK || s < 3 || s < d) ? __ldg(tau + s * vs) : 0.0;
+#endif
         int j_l = row.v[DMAX - 1];
         if (MASK) {
             j_l = row.v[2];
@@ -891,13 +901,20 @@ struct GradWalk {
             for (int s = 3; s < DMAX; s++) j_l = s < d ? row.v[s] : j_l;
         }
         Pt pp = point(j_l);
+#if TM_GRAD_TAU_EARLY
+        asm volatile("" ::: "memory");
+#endif
 #pragma unroll
         for (int s = 0; s < DMAX; s++) {
             if (s > 0 && s % TM_GRAD_GROUP == 0) asm volatile("" ::: "memory");
             const bool valid = !MASK || s < 3 || s < d;
             const Pt pc = point(valid ? row.v[s] : row.v[0]);
-            const double ta = valid ? __ldg(tau + s * vs) : 0.0;
-            face<MASK>(pp, pc, ta, valid, s);
+#if TM_GRAD_TAU_EARLY
+            const double tas = ta[s];
+#else
+            const double tas = valid ? __ldg(tau + s * vs) : 0.0;
+#endif
+            face<MASK>(pp, pc, tas, valid, s);
             pp = pc;
         }
     }

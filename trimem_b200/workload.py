@@ -1,8 +1,8 @@
 """The synthetic workloads of BASELINE.json / SURVEY.md section 8(d).
 
-The same function parametrises the product module (trimem_b200.core) and the
-oracle (the reference's trimem.core built under oracle/_ref): both expose the
-same API, which is the point of the drop-in boundary.
+The functions take the module to parametrise as an argument (trimem_b200.core, or any module with
+the trimem.core API such as the reference's own build): same API, which is the point of the drop-in
+boundary.
 """
 import numpy as np
 
