@@ -145,7 +145,9 @@ int tm_flush_l2(tm_mesh* m, unsigned long long bytes);
 /* average device time (CUDA events on the mesh's stream) of `iters` launches of ONE sweep set:
  * which = 0 the energy() sweeps (ring properties + pair sweep + reduction), 1 the gradient's own
  * property sweep (+ reduction), 2 the ring gradient sweep (pair force already evaluated), 3 the
- * pair sweep alone; flush_bytes > 0 evicts L2 before every launch (outside the timed span).      */
+ * pair sweep alone, 4 energy + gradient (all sweeps), 5 one gradient evaluation at new positions
+ * (geometry sweep, pair force, ring gradient: what a leapfrog step costs); flush_bytes > 0 evicts
+ * L2 before every launch (outside the timed span).                                              */
 int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int which, int iters,
                    unsigned long long flush_bytes, float* ms_avg);
 

@@ -22,8 +22,9 @@ e, props = cm.energy(nl, p)
 g = cm.gradient(nl, p)
 out = {"list": ns, "lib": os.environ.get("TRIMEM_B200_LIB", "default"), "V": cm.V, "rep": rep, "E": e, "gnorm": float(np.linalg.norm(g)),
        "E_core": estore.energy(mesh), "gnorm_core": float(np.linalg.norm(estore.gradient(mesh)))}
-for name, w in (("props_full", 0), ("props_geo", 1), ("grad", 2), ("pairs", 3)):
+for name, w in (("props_full", 0), ("props_geo", 1), ("grad", 2), ("pairs", 3), ("EG", 4), ("G_newpos", 5)):
     out[name + "_us"] = round(1e3 * cm.time_kernel(nl, p, w, iters, 512 << 20), 2)
+    out[name + "_warmL2_us"] = round(1e3 * cm.time_kernel(nl, p, w, iters, 0), 2)
 cm.sync()
 import time
 ts = []

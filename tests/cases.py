@@ -106,6 +106,15 @@ FLIPSTAT_LARGE = (100, 0.1, [("flip", 1, 2), ("pflip", 8, 3)])
 CASES["ico6_flip"] = ("jittered_icosphere", (6,), dict(kappa=K1R, fracs=(1.0, 1.0, 1.0), repulsion="physical",
                                                        n_search="cell-list", exclusion=2))
 
+# checkpoint hand-off (tests/golden/make_golden.py restart_case): flips, continuation state, displacement
+RESTART_FLIPS = "flip_ico4_verlet"
+RESTART_CONT = (0.25, 0.0)              # continuation delta, initial lambda (two updates -> 0.5)
+RESTART_FRACS = (0.9, 0.8, 0.95)
+
+
+def restart_displacement(x):
+    return x + 0.004 * np.sin(3.0 * x[:, [1, 2, 0]]) * np.linalg.norm(x, axis=1, keepdims=True)
+
 
 def flip_inputs(name):
     case, n, seed = FLIP_CASES[name]

@@ -263,6 +263,41 @@ def hmc_chain_cases():
         save(name, xs=np.array(xs), acc=np.array(accs), temperature=np.array([chain.T]))
 
 
+def restart_case():
+    """Checkpoint hand-off (src/trimem/mc/util.py:153-160): after a flip sweep, two continuation updates and a
+    displacement, the state (x, f, lam, delta) is all that is handed over; the restart builds the EnergyManager on
+    the INITIAL mesh with the checkpoint's continuation parameters, the mesh from (x, f), rebuilds the list on it
+    and evaluates. Golden = the reference's answers on the restarted objects."""
+    case, edges, u = cases.flip_inputs(cases.RESTART_FLIPS)
+    mesh, es = cases.build(ref, case)
+    x_init, f_init = mesh.points().copy(), mesh.fv_indices().copy()
+    refprobe.flip_sweep(mesh, es, edges, u)
+    # (eparams is handed out by reference: nested assignments are live, tests/test_gpu_energy.py)
+    es.eparams.continuation_params.delta, es.eparams.continuation_params.lam = cases.RESTART_CONT
+    es.eparams.area_frac, es.eparams.volume_frac, es.eparams.curvature_frac = cases.RESTART_FRACS
+    es.update_reference_properties()
+    es.update_reference_properties()
+    x = cases.restart_displacement(mesh.points())
+    np.copyto(mesh.points(), x)
+    es.update_repulsion(mesh)
+    e_cont, g_cont = es.energy(mesh), es.gradient(mesh)
+    lam, delta, f = es.eparams.continuation_params.lam, es.eparams.continuation_params.delta, mesh.fv_indices().copy()
+    # restart
+    mesh0 = ref.TriMesh(x_init, f_init)
+    ep2 = workload.energy_params(ref, mesh0, **cases.CASES[case][2])
+    ep2.area_frac, ep2.volume_frac, ep2.curvature_frac = cases.RESTART_FRACS
+    cp2 = ep2.continuation_params
+    cp2.lam, cp2.delta = lam, delta
+    ep2.continuation_params = cp2
+    es2 = ref.EnergyManager(mesh0, ep2)
+    mesh2 = ref.TriMesh(x, f)
+    es2.update_repulsion(mesh2)
+    e2, g2, p2 = es2.energy(mesh2), es2.gradient(mesh2), cases.props6(es2.properties(mesh2))
+    print("restart: continued", e_cont, "restarted", e2, "grad diff", np.abs(g2 - g_cont).max() / np.abs(g_cont).max())
+    save("restart_" + case, x=x, f=f, lam=np.array([lam]), delta=np.array([delta]), energy=np.array([e2]), grad=g2,
+         props=p2, energy_continued=np.array([e_cont]))
+
+
 def open_mesh_cases():
     out = {}
     for name in cases.OPEN_MESHES:
@@ -365,7 +400,7 @@ def flip_statistics():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc", "open"]
+    which = sys.argv[1:] or ["topology", "analytic", "primitives", "neighbours", "flips", "energy", "spread", "trajectory", "hmc", "open", "restart"]
     if "topology" in which: topology_cases()
     if "analytic" in which: analytic_cases()
     if "primitives" in which: primitive_cases()
@@ -376,5 +411,6 @@ if __name__ == "__main__":
     if "trajectory" in which: trajectory_cases()
     if "hmc" in which: hmc_chain_cases()
     if "open" in which: open_mesh_cases()
+    if "restart" in which: restart_case()
     if "flipstats" in which: flip_statistics()
     if "big" in which: big_case()

@@ -1,6 +1,6 @@
 """read_mesh (src/mesh.cpp:7-16 -> OpenMesh::IO::read_mesh): STL binary / ASCII with OpenMesh's
 corner welding (bitwise-equal float32 coordinates, vertices numbered by first appearance, degenerate
-facets dropped), OFF, OBJ. Host-only logic: runs in the CPU suite; the docs' known answer through an
+facets dropped), OFF, OBJ, PLY (ascii and both binary byte orders). Host-only logic: runs in the CPU suite; the docs' known answer through an
 STL file (doc/python-module.rst:60-98) is checked on the GPU."""
 import os
 import struct
@@ -103,6 +103,74 @@ def test_read_off_and_obj(core, tmp_path):
         fh.write("OFF 4 1 0\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n")
     assert np.array_equal(core.read_mesh(quad).fv_indices(), core.TriMesh(
         np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], float), np.array([[0, 1, 2], [0, 2, 3]])).fv_indices())
+
+
+def write_ply(path, v, f, fmt="ascii", ftype="double", extra=False, index_name="vertex_indices"):
+    """PLY with optional extra vertex properties (a uchar colour triple between the coordinates and a trailing
+    float) and an extra face property, so that the reader has to skip by declared type."""
+    end = {"ascii": "", "binary_little_endian": "<", "binary_big_endian": ">"}[fmt]
+    fc = {"float": "f", "double": "d"}[ftype]
+    head = ["ply", "format %s 1.0" % fmt, "comment made by the test", "element vertex %d" % len(v),
+            "property %s x" % ftype]
+    if extra:
+        head += ["property uchar red"]
+    head += ["property %s y" % ftype, "property %s z" % ftype]
+    if extra:
+        head += ["property float quality"]
+    head += ["element face %d" % len(f)]
+    if extra:
+        head += ["property short flag"]
+    head += ["property list uchar int %s" % index_name, "end_header"]
+    with open(path, "wb") as fh:
+        fh.write(("\n".join(head) + "\n").encode())
+        if fmt == "ascii":
+            rep = (lambda t: "%.9g" % np.float32(t)) if ftype == "float" else (lambda t: "%.17g" % t)
+            for p in v:
+                row = [rep(p[0])] + (["7"] if extra else []) + [rep(p[1]), rep(p[2])] + (["0.5"] if extra else [])
+                fh.write((" ".join(row) + "\n").encode())
+            for t in f:
+                fh.write((("-3 " if extra else "") + "3 %d %d %d\n" % tuple(t)).encode())
+        else:
+            for p in v:
+                fh.write(struct.pack(end + fc, p[0]))
+                if extra:
+                    fh.write(struct.pack("B", 7))
+                fh.write(struct.pack(end + 2 * fc, p[1], p[2]))
+                if extra:
+                    fh.write(struct.pack(end + "f", 0.5))
+            for t in f:
+                if extra:
+                    fh.write(struct.pack(end + "h", -3))
+                fh.write(struct.pack(end + "B3i", 3, *[int(k) for k in t]))
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+@pytest.mark.parametrize("ftype,extra", [("double", False), ("float", True)])
+def test_read_ply(core, tmp_path, fmt, ftype, extra):
+    v, f = meshgen.icosphere(2)
+    path = str(tmp_path / "m.ply")
+    write_ply(path, v, f, fmt, ftype, extra, "vertex_index" if extra else "vertex_indices")
+    mesh = core.read_mesh(path)
+    want = v if ftype == "double" else v.astype(np.float32).astype(np.float64)     # float32 widened, like STL
+    assert np.array_equal(mesh.points(), want)
+    ref = core.TriMesh(want, f)
+    for a, b in zip(mesh.halfedge_arrays(), ref.halfedge_arrays()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(mesh.fv_indices(), ref.fv_indices())
+
+
+def test_read_ply_errors(core, tmp_path):
+    v, f = meshgen.icosphere(1)
+    good = tmp_path / "g.ply"
+    write_ply(str(good), v, f, "binary_little_endian")
+    data = good.read_bytes()
+    (tmp_path / "trunc.ply").write_bytes(data[:-7])
+    (tmp_path / "nohead.ply").write_bytes(data.replace(b"end_header\n", b""))
+    bad_index = tmp_path / "idx.ply"
+    write_ply(str(bad_index), v, np.array([[0, 1, len(v)]]), "ascii")
+    for name in ("trunc.ply", "nohead.ply", "idx.ply"):
+        with pytest.raises(RuntimeError, match="read error on file"):
+            core.read_mesh(str(tmp_path / name))
 
 
 def test_read_errors(core, tmp_path):

@@ -380,6 +380,14 @@ PYBIND11_MODULE(core, m) {
           py::arg("mesh"), py::arg("estore"), py::arg("flip_ratio"), py::arg("seed") = -1,
           py::call_guard<py::gil_scoped_release>(),
           "Batch-parallel flip sweep; returns the number of accepted flips.");
+    m.def("flip_with",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, std::vector<int> edges, std::vector<double> u, bool parallel) {
+              py::gil_scoped_release nogil;
+              return flip_with(mesh, estore, edges, u, parallel);
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("edges"), py::arg("u"), py::arg("parallel") = false,
+          "Extension: flip sweep over the caller's proposals `edges` with the caller's acceptance variates `u` "
+          "(serial semantics, or the batch-parallel sweep with parallel=True); returns the number of accepted flips.");
 
     // ---- neighbour lists (src/bindings.cpp:893-985) -------------------------------------------------
     py::class_<Point>(m, "Point", "3D point (opaque).")

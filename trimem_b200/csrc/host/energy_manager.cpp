@@ -186,19 +186,10 @@ std::string EnergyManager::info(HalfedgeMesh& mesh) {
 
 // ----------------------------------------------------------------------- flips --
 namespace {
-int flip_sweep(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed, int mode) {
-    const int nedges = mesh.n_edges();
-    const int nflips = (int)(nedges * flip_ratio);
-    if (nflips <= 0 || nedges <= 0) return 0;
-    unsigned long long s = seed >= 0 ? (unsigned long long)seed
-        : (unsigned long long)std::chrono::high_resolution_clock::now().time_since_epoch().count();
-    std::mt19937 gen((std::mt19937::result_type)s);
-    std::uniform_int_distribution<int> propose(0, nedges - 1);
-    std::uniform_real_distribution<double> accept(0.0, 1.0);
-    std::vector<int> edges(nflips);
-    std::vector<double> u(nflips);
-    for (int i = 0; i < nflips; i++) { edges[i] = propose(gen); u[i] = accept(gen); }
-
+int flip_sweep_with(HalfedgeMesh& mesh, EnergyManager& estore, const std::vector<int>& edges, const std::vector<double>& u,
+                    int mode) {
+    const int nflips = (int)edges.size();
+    if (nflips <= 0) return 0;
     tm_energy_params p = estore.abi_params();
     tm_mesh* dm = mesh.device();
     double props[6];
@@ -217,7 +208,30 @@ int flip_sweep(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, lon
     mesh.mark_device_in_sync();
     return nacc;
 }
+
+int flip_sweep(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed, int mode) {
+    const int nedges = mesh.n_edges();
+    const int nflips = (int)(nedges * flip_ratio);
+    if (nflips <= 0 || nedges <= 0) return 0;
+    unsigned long long s = seed >= 0 ? (unsigned long long)seed
+        : (unsigned long long)std::chrono::high_resolution_clock::now().time_since_epoch().count();
+    std::mt19937 gen((std::mt19937::result_type)s);
+    std::uniform_int_distribution<int> propose(0, nedges - 1);
+    std::uniform_real_distribution<double> accept(0.0, 1.0);
+    std::vector<int> edges(nflips);
+    std::vector<double> u(nflips);
+    for (int i = 0; i < nflips; i++) { edges[i] = propose(gen); u[i] = accept(gen); }
+    return flip_sweep_with(mesh, estore, edges, u, mode);
+}
 }  // namespace
+
+int flip_with(HalfedgeMesh& mesh, EnergyManager& estore, const std::vector<int>& edges, const std::vector<double>& u,
+              bool parallel) {
+    if (edges.size() != u.size()) throw std::invalid_argument("flip_with: one acceptance variate per proposed edge");
+    for (int e : edges)
+        if (e < 0 || e >= mesh.n_edges()) throw std::out_of_range("flip_with: edge id out of range");
+    return flip_sweep_with(mesh, estore, edges, u, parallel ? TM_FLIP_BATCH : TM_FLIP_SERIAL);
+}
 
 int flip_serial(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed) {
     // the reference constructs a runtime_error for flip_ratio > 1 but never throws it

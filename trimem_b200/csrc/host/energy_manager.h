@@ -106,6 +106,10 @@ public:
 // `seed` < 0 seeds from the clock like the reference (flips.cpp:20,105-106).
 int flip_serial(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
 int flip_parallel_batches(HalfedgeMesh& mesh, EnergyManager& estore, double flip_ratio, long long seed = -1);
+// extension: the same sweeps with the caller's proposals and acceptance variates (one per proposal) instead of the
+// internal generator's: reproducible sweeps for tests and restarts
+int flip_with(HalfedgeMesh& mesh, EnergyManager& estore, const std::vector<int>& edges, const std::vector<double>& u,
+              bool parallel);
 
 // ---- velocity-Verlet trajectory (src/trimem/mc/hmc.py:14-26, device resident) ------------
 // n_steps of _vv_integration from the mesh's current points() and the momenta p0 (n_vertices x 3);

@@ -517,18 +517,22 @@ int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int whic
                    unsigned long long flush_bytes, float* ms_avg) {
     if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     TM_CHECK(iters > 0 && ms_avg, "bad arguments");
-    TM_CHECK(which >= 0 && which <= 3, "which must be 0 (energy sweeps: ring properties + pairs + reduction), "
-             "1 (the gradient's property sweep + reduction), 2 (ring gradient sweep) or 3 (pair sweep alone)");
+    TM_CHECK(which >= 0 && which <= 5, "which must be 0 (energy sweeps: ring properties + pairs + reduction), "
+             "1 (the gradient's property sweep + reduction), 2 (ring gradient sweep), 3 (pair sweep alone), "
+             "4 (energy + gradient) or 5 (a gradient evaluation at new positions: geometry sweep, pair force, ring gradient)");
     // the gradient sweep consumes rho, the reduced sums and the pair force of earlier sweeps
     if (tm_launch_props(m, view_of(nl), *p, true, false)) return 1;
     double total = 0.0;
     for (int it = 0; it < iters; it++) {
         if (flush_bytes && tm_flush_l2(m, flush_bytes)) return 1;
         TM_CUDA(cudaEventRecord(m->ev0, m->stream));
+        if (which >= 4) m->frep_epoch = m->pos_epoch - 1;      // the composites re-evaluate the pair force
         int rc = which == 0 ? tm_launch_props(m, view_of(nl), *p, true, false)
                : which == 1 ? tm_launch_props(m, view_of(nl), *p, false, false)
                : which == 2 ? tm_launch_grad(m, view_of(nl), *p)
-                            : tm_launch_pairs(m, view_of(nl), *p);
+               : which == 3 ? tm_launch_pairs(m, view_of(nl), *p)
+               : which == 4 ? (tm_launch_props(m, view_of(nl), *p, true, false) || tm_launch_grad(m, view_of(nl), *p))
+                            : (tm_launch_props(m, view_of(nl), *p, false, false) || tm_launch_grad(m, view_of(nl), *p));
         if (rc) return 1;
         TM_CUDA(cudaEventRecord(m->ev1, m->stream));
         TM_CUDA(cudaEventSynchronize(m->ev1));

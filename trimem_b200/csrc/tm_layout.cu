@@ -12,6 +12,7 @@
 // at the C ABI: ids are converted on the way in and out.
 #include <cfloat>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "tm_common.cuh"
@@ -258,7 +259,10 @@ int tm_ensure_layout(tm_mesh* m) {
         if (build_permutation(m)) return 1;
         m->perm_valid = true;
         m->topo_dev_valid = false;
-        m->layout_epoch++;
+        // unique over all mesh handles of the process: a neighbour list built on another handle (rows in that
+        // handle's vertex order) can then never pass tm_check_nlist by coincidence
+        static std::atomic<unsigned long long> g_layout{0};
+        m->layout_epoch = ++g_layout;
     }
     if (!m->topo_dev_valid) {
         k_map_ids<<<(m->HE + NT - 1) / NT, NT, 0, m->stream>>>(m->HE, m->he_to_h, m->h2d, m->he_to); TM_LAUNCHED();
@@ -310,7 +314,8 @@ int tm_check_nlist(const tm_mesh* m, const tm_nlist* nl) {
     if (!nl) return 0;
     TM_CHECK(nl->V == m->V, "neighbour list was built for %d vertices, mesh has %d", nl->V, m->V);
     TM_CHECK(nl->layout_epoch == m->layout_epoch,
-             "neighbour list is stale: the mesh's vertex order changed after it was built (rebuild it)");
+             "neighbour list is stale: it was built on another mesh object or before the mesh's vertex order "
+             "changed (call update_repulsion(mesh) / rebuild it)");
     if (nl->kind == TM_NLIST_VERLET) {
         const SweepRange R = tm_owned_range(m);
         TM_CHECK(nl->rows_first <= R.first && nl->rows_first + nl->rows_count >= R.first + R.count,
