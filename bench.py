@@ -176,18 +176,23 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     V = chains[0][0].n_vertices()
     stats = [None] * R
 
-    def run(k, n_moves, first_move):
+    lazy_upd = [hmc.LazyRepulsion(c[2]) for c in chains]
+
+    def run(k, n_moves, first_move, lazy=False):
         mesh, estore, ch, gid = chains[k]
         flips = acc0 = 0
         for mv in range(first_move, first_move + n_moves):
             ch.step()
-            estore.update_repulsion(mesh)
+            if lazy:
+                lazy_upd[k]()               # rebuild only when the device-side trigger fires
+            else:
+                estore.update_repulsion(mesh)
             if (mv + 1) % 10 == 0:
-                flips += core.pflip(mesh, estore, 0.1, seed=977 * gid + mv)
+                flips += lazy_upd[k].flips_accepted(core.pflip(mesh, estore, 0.1, seed=977 * gid + mv))
         stats[k] = (ch.acc, ch.i, flips)
 
-    def all_chains(n_moves, first_move):
-        th = [threading.Thread(target=run, args=(k, n_moves, first_move)) for k in range(R)]
+    def all_chains(n_moves, first_move, lazy=False):
+        th = [threading.Thread(target=run, args=(k, n_moves, first_move, lazy)) for k in range(R)]
         [t.start() for t in th]
         [t.join() for t in th]
     all_chains(10, 0)                   # warm-up: trajectory graphs captured, one flip sweep, list pools filled
@@ -198,6 +203,16 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     all_chains(n_moves, 10)
     wall = time.perf_counter() - t0
     launches = core.launch_count() - launches0
+    stats_timed = list(stats)
+    # the same chains with the list rebuilt only when the device-side trigger fires
+    for c in chains:
+        c[1].update_repulsion(c[0]); c[2].displacement = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    all_chains(n_moves, 40, lazy=True)
+    wall_lazy = time.perf_counter() - t0
+    rebuilt = sum(u.rebuilds for u in lazy_upd) / max(1, sum(u.rebuilds + u.skipped for u in lazy_upd))
+    stats[:] = stats_timed
     # one chain alone, for the concurrency gain
     t0 = time.perf_counter()
     run(0, 10, 30)
@@ -207,7 +222,7 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     return {"wall_s": wall, "moves": n_moves, "L": L, "R": R, "V": V, "solo_ms_per_move": 1e3 * solo,
             "hmc_acceptance": float(np.mean([s[0] / max(s[1], 1) for s in stats])),
             "flips_accepted_per_sweep": float(np.mean([s[2] for s in stats])) / max(1, n_moves // 10),
-            "launches": int(launches)}
+            "launches": int(launches), "wall_lazy_s": wall_lazy, "lazy_rebuild_fraction": rebuilt}
 
 
 def hmc_step_run(args, core, workload, rank):
@@ -702,7 +717,12 @@ def main():
                 "ms_per_move_per_chain_concurrent": 1e3 * repl_s / repl["moves"],
                 "ms_per_move_one_chain_alone": repl["solo_ms_per_move"],
                 "hmc_acceptance": repl["hmc_acceptance"], "flips_accepted_per_sweep": repl["flips_accepted_per_sweep"],
-                "gpu_launches": repl["launches"]},
+                "gpu_launches": repl["launches"],
+                "lazy_repulsion": {"what": "the same chains with hmc.LazyRepulsion: the verlet list is rebuilt only when the "
+                                           "displacement measured on the device behind each trajectory exceeds a quarter of "
+                                           "rlist - lc1, or flips were accepted (this rank's wall clock)",
+                                   "moves_per_s": world * repl["R"] * repl["moves"] / repl["wall_lazy_s"],
+                                   "rebuilds_per_move": repl["lazy_rebuild_fraction"]}},
             "hmc_step_config2": hmc2,
             "partitioned": part,
             "gpu_launches": int(launches),

@@ -210,6 +210,15 @@ int tm_vv_stats(tm_mesh* m, const tm_energy_params* p, double stats[4], double p
 int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const double* p0, double mass,
                     double dt, int n_steps, double* x_out, double* p_out, double stats[4]);
 
+/* On-device rebuild trigger (the cadence the reference leaves to its per-move callback,
+ * src/trimem/mc/evaluators.py:181-182). Every tm_vv_integrate over a verlet list also measures, on the device and
+ * behind the trajectory (one more kernel, no extra synchronisation: the value travels with the statistics), how far
+ * the END POINT of the trajectory is from the positions the list was built from. displacement = the largest such
+ * vertex displacement; margin = rlist - rep_lc1: as long as no vertex has moved more than margin / 2 since the build,
+ * the frozen rows cannot miss a pair inside the cut-off and a rebuild would change no energy or gradient.
+ * Returns an error if the last trajectory did not measure it (cell list, no list, asynchronous entry).          */
+int tm_vv_displacement(tm_mesh* m, tm_nlist* nl, double rep_lc1, double* displacement, double* margin);
+
 /* ---- one mesh partitioned across devices  (BASELINE.json config 4) ----
  * No reference counterpart (its sweeps are OpenMP loops in one address space,
  * src/kernel.h:243-262). Every rank holds the whole mesh, owns a contiguous slice of

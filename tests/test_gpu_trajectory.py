@@ -181,3 +181,62 @@ def test_hmc_chain_vs_reference_hmc(gpu_core, name):
         prev = want
     assert abs(chain.T - float(gold["temperature"][0])) <= 1e-15 * chain.T
     assert chain.counter["move"] == nsteps
+
+
+def test_rebuild_trigger_measured_on_device(gpu_core):
+    """the trajectory measures, on the device, how far its end point is from the positions the verlet
+    list was built from; the value equals the host-side computation and tm_nlist_displacement's."""
+    m = gpu_core
+    mesh, es = cases.build(m, "ico4_physical_cell2")
+    es.eparams.repulse_params.n_search = "verlet-list"
+    es.update_repulsion(mesh)
+    x0 = mesh.points().copy()
+    rp = es.eparams.repulse_params
+    p0 = np.random.default_rng(5).normal(size=x0.shape)
+    xn, pn, st = m.vv_integrate(mesh, es, p0, 1.0, 2.0e-5, 6)
+    disp, margin = m.vv_displacement(mesh, es)
+    want = np.sqrt(((xn - x0) ** 2).sum(axis=1)).max()
+    assert abs(disp - want) <= 1e-12 * want and want > 0.0
+    assert margin == rp.rlist - rp.lc1
+    # a second trajectory from the same start, list rebuilt in between: same end point, same displacement
+    es.update_repulsion(mesh)
+    xn2, _, _ = m.vv_integrate(mesh, es, p0, 1.0, 2.0e-5, 6)
+    assert np.array_equal(xn, xn2) and m.vv_displacement(mesh, es)[0] == disp
+    # cell lists keep no build positions: the query says so instead of returning something stale
+    es.eparams.repulse_params.n_search = "cell-list"
+    es.update_repulsion(mesh)
+    m.vv_integrate(mesh, es, p0, 1.0, 2.0e-5, 2)
+    with pytest.raises(RuntimeError, match="did not measure"):
+        m.vv_displacement(mesh, es)
+
+
+def test_lazy_repulsion_chain_equals_rebuild_every_move(gpu_core):
+    """A chain that rebuilds its verlet list only when the device-side trigger fires visits the same states, with the
+    same Hamiltonians, as the chain that rebuilds after every move (the reference's cadence, mc/evaluators.py:181-182):
+    a list inside its skin margin is complete. The trigger does fire once the state has moved far enough."""
+    from trimem_b200 import hmc
+    m = gpu_core
+    opts = {"time_step": 2.0e-5, "num_integration_steps": 6, "initial_temperature": 50.0, "info_step": 0}
+    runs = []
+    for lazy in (False, True):
+        mesh, es = cases.build(m, "ico4_physical_cell2")
+        es.eparams.repulse_params.n_search = "verlet-list"
+        es.update_repulsion(mesh)
+        chain = hmc.MeshHMC(mesh, es, options=dict(opts), verbose=False, rng=np.random.RandomState(31))
+        upd = hmc.LazyRepulsion(chain, fraction=0.5)
+        states, hams = [], []
+        for k in range(24):
+            chain.step()
+            if lazy:
+                upd()
+            else:
+                es.update_repulsion(mesh)
+            states.append(chain.x.copy())
+            hams.append(np.array(chain.last[2]))
+        runs.append((np.array(states), np.array(hams), upd))
+    (xs0, h0, _), (xs1, h1, upd) = runs
+    assert upd.skipped > 0 and upd.rebuilds > 0, (upd.skipped, upd.rebuilds)       # both branches exercised
+    # same lists up to entries outside the cut-off: same energies; the row ORDER differs between a fresh and an older
+    # list, so sums agree to rounding, not bitwise
+    assert np.abs(h1 - h0).max() <= 1e-11 * np.abs(h0).max()
+    assert np.linalg.norm(xs1 - xs0) <= 1e-9 * np.linalg.norm(xs0 - xs0[0] + 1e-300) + 1e-12

@@ -99,6 +99,7 @@ def lib():
     L.tm_mesh_get_momenta.argtypes = [vp, _dp]
     L.tm_vv_integrate_async.argtypes = [vp, vp, pp, C.c_double, C.c_double, C.c_int, C.c_int]
     L.tm_vv_stats.argtypes = [vp, pp, _dp, _dp, _dp]
+    L.tm_vv_displacement.argtypes = [vp, vp, C.c_double, _dp, _dp]
     L.tm_vv_integrate.argtypes = [vp, vp, pp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
     L.tm_part_create.argtypes = [vp, C.c_int, C.c_int]
     L.tm_part_info.argtypes = [vp, _ip, _ip, _ip, _ip, _ip, _ip]

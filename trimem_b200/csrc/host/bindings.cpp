@@ -435,6 +435,12 @@ PYBIND11_MODULE(core, m) {
           "Finite difference gradient of energy.");
 
     // ---- device-resident trajectory (extension; replaces the Python loop of mc/hmc.py:14-26) -----------
+    m.def("vv_displacement",
+          [](HalfedgeMesh& mesh, EnergyManager& estore) { return vv_displacement(mesh, estore); },
+          py::arg("mesh"), py::arg("estore"),
+          "Extension: (displacement, margin) of the last vv_integrate over a verlet list -- the largest distance of a\n"
+          "vertex of the trajectory's end point from where it was when the list was built, and rlist - lc1. While\n"
+          "displacement <= margin / 2 the frozen rows miss no pair inside the cut-off.");
     m.def("vv_integrate",
           [](HalfedgeMesh& mesh, EnergyManager& estore, py::array_t<double, py::array::c_style | py::array::forcecast> p0,
              double mass, double dt, int n_steps) {

@@ -252,6 +252,12 @@ void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, d
         fail();
 }
 
+std::tuple<double, double> vv_displacement(HalfedgeMesh& mesh, EnergyManager& estore) {
+    double disp = 0, margin = 0;
+    if (tm_vv_displacement(mesh.device(), estore.nlist_handle(), estore.params.repulse_params.lc1, &disp, &margin)) fail();
+    return {disp, margin};
+}
+
 // --------------------------------------------------------------- setup reductions --
 double area(HalfedgeMesh& mesh) {
     double a = 0, l = 0;

@@ -119,6 +119,10 @@ int flip_with(HalfedgeMesh& mesh, EnergyManager& estore, const std::vector<int>&
 void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, double mass, double dt,
                   int n_steps, double* x_out, double* p_out, double* stats);
 
+// extension (rebuild trigger): (largest vertex displacement of the last trajectory's end point from the
+// positions the verlet list was built from, margin = rlist - lc1), measured on the device behind the trajectory
+std::tuple<double, double> vv_displacement(HalfedgeMesh& mesh, EnergyManager& estore);
+
 // ---- setup-time reductions (src/util.h) ------------------------------------------------
 double area(HalfedgeMesh& mesh);
 double edges_length(HalfedgeMesh& mesh);

@@ -129,7 +129,7 @@ int fetch_sums(tm_mesh* m, double out[6]) {
 extern "C" {
 
 const char* tm_last_error(void) { return g_err; }
-int tm_abi_version(void) { return 2; }
+int tm_abi_version(void) { return 3; }
 
 int tm_device_count(void) {
     int n = 0;
@@ -487,6 +487,9 @@ int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const d
     TM_CHECK(mass > 0.0, "mass must be positive");
     if (tm_import_momenta(m, p0)) return 1;
     if (tm_vv_run(m, view_of(nl), *p, mass, dt, n_steps, stats != nullptr)) return 1;
+    // the rebuild trigger: displacement of the end point from the list's build positions (d_stats[14], squared)
+    m->vv_disp_list = 0;
+    if (stats && nl && !m->part && tm_nlist_measure_displacement(nl, m, m->d_stats + 14) == 0) m->vv_disp_list = nl->serial;
     if (p_out && tm_export_vec3_owned(m, m->mom, p_out)) return 1;
     if (x_out) {
         if (tm_part_make_current(m)) return 1;
@@ -496,6 +499,16 @@ int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const d
     }
     if (stats) return tm_vv_stats(m, p, stats, nullptr, nullptr);
     TM_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int tm_vv_displacement(tm_mesh* m, tm_nlist* nl, double rep_lc1, double* displacement, double* margin) {
+    TM_CHECK(m != nullptr && nl != nullptr, "null argument");
+    TM_CHECK(m->h_stats != nullptr && m->vv_disp_list != 0 && m->vv_disp_list == nl->serial,
+             "the last trajectory on this mesh did not measure the displacement against this list "
+             "(needs tm_vv_integrate with statistics over a verlet list)");
+    if (displacement) *displacement = sqrt(m->h_stats[14]);
+    if (margin) *margin = nl->rlist - rep_lc1;
     return 0;
 }
 

@@ -138,6 +138,7 @@ struct tm_mesh {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool pairs_inflight = false;
+    unsigned long long vv_disp_list = 0;   // serial of the list the last trajectory measured its end point's displacement against
     cudaEvent_t ev_pre_upload = nullptr;   // recorded on `stream` just before a position upload is enqueued
     int V = 0, HE = 0;
     int *he_to = nullptr, *he_next = nullptr, *he_face = nullptr, *v_he = nullptr;
@@ -288,6 +289,7 @@ int tm_launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p); //
 // m->xout3 and copied to `grad_host`; no layout / staging work (speculative path of tm_gradient)
 int tm_launch_grad_speculative(tm_mesh* m, const NlView& nl, const tm_energy_params& p, cudaStream_t st, double* grad_host);
 bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_params& p);
+int tm_nlist_measure_displacement(tm_nlist* nl, tm_mesh* m, double* out);   // tm_nlist.cu (asynchronous)
 int tm_join_pairs(tm_mesh* m);   // tm_energy.cu: the mesh's stream waits for a pair sweep still running beside it
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
 double tm_energy_from_props(const tm_energy_params& p, const double s[6]);    // tm_api.cu (kernel.h:110-122)

@@ -568,6 +568,20 @@ int tm_nlist_destroy(tm_nlist* nl) {
 // mc/evaluators.py:181-182): the frozen rows stay complete for a cut-off dmax as long as no vertex has moved
 // further than (rlist - dmax) / 2 since the build. Returns the largest displacement on the mesh's
 // current device positions; needs_rebuild = 2 * displacement > rlist - dmax.
+}  // extern "C"
+
+// asynchronous: out (device, 8 bytes) <- largest squared displacement of the mesh's current device positions from
+// the list's build positions; 1 if the list keeps none (cell lists)
+int tm_nlist_measure_displacement(tm_nlist* nl, tm_mesh* m, double* out) {
+    if (!nl || nl->kind != TM_NLIST_VERLET || !nl->x_build || nl->layout_epoch != m->layout_epoch) return 1;
+    if (cudaMemsetAsync(out, 0, 8, m->stream) != cudaSuccess) return 1;
+    k_max_displacement2<<<296, NT, 0, m->stream>>>(m->V, m->pos, nl->x_build, reinterpret_cast<unsigned long long*>(out));
+    TM_LAUNCHED();
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+extern "C" {
+
 int tm_nlist_displacement(tm_nlist* nl, tm_mesh* m, double dmax, double* displacement, int* needs_rebuild) {
     TM_CHECK(nl != nullptr && m != nullptr, "null argument");
     TM_CHECK(nl->kind == TM_NLIST_VERLET && nl->x_build, "the skin criterion applies to verlet lists");

@@ -76,6 +76,11 @@ class MeshHMC:
         self.T = self.Tinit
         self.x = self.trimesh.points().copy()
         self.last = None            # (dh, accepted, [U0, K0, U1, K1]) of the last step
+        # rebuild trigger (extension): largest vertex displacement of the CURRENT state from the
+        # positions the verlet list was built from, as measured on the device behind each trajectory (None: not
+        # measured -- cell list or no repulsion), and rlist - lc1. See LazyRepulsion.
+        self.displacement = 0.0
+        self.margin = None
         # source of the momenta and the Metropolis variate: numpy's global state like the reference, or the chain's
         # own numpy.random.RandomState (independent chains driven from several threads, ranks of a partitioned mesh)
         self.rng = np.random if rng is None else rng
@@ -94,9 +99,14 @@ class MeshHMC:
         a = 1.0 if dh <= 0 else np.exp(-dh)
         u = self.rng.uniform()
         acc = u <= a
+        try:
+            d_end, self.margin = m.vv_displacement(self.trimesh, self.estore)
+        except RuntimeError:
+            d_end, self.margin = None, None
         if acc:
             self.x = xn
             self.acc += 1
+            self.displacement = d_end       # a rejected move returns to a state whose displacement is known
         self.i += 1
         self.last = (dh, bool(acc), st)
 
@@ -124,3 +134,48 @@ class MeshHMC:
             self.step()
             self.info()
             self.cb(self.x, self.counter)
+
+
+class LazyRepulsion:
+    """Per-move callback that rebuilds the verlet list only when the device-side trigger says so.
+
+    The reference rebuilds the list in its per-move callback every ``refresh`` moves whatever has happened
+    (mc/evaluators.py:181-182). A verlet list built with ``rlist > lc1`` stays COMPLETE -- no pair inside the
+    repulsion cut-off is missing, so energies and gradients are those of a fresh list -- until some vertex has moved
+    more than ``(rlist - lc1) / 2`` from where it was at the build. ``MeshHMC`` tracks that displacement for the
+    chain's current state (measured on the device behind every trajectory, no extra synchronisation); this callback
+    rebuilds when it exceeds ``fraction`` of the bound (default one half: the other half is left to the motion inside
+    the next trajectory), after accepted flips (a verlet list freezes its exclusions), and always
+    for lists that keep no build positions (cell lists: those are cheap to rebuild).
+
+        hmc = MeshHMC(mesh, estore, ...)
+        upd = LazyRepulsion(hmc)
+        hmc.cb = upd                              # or call upd(x, counter) from an existing callback
+        ...; upd.flips_accepted(core.pflip(...))  # after a flip sweep
+    """
+
+    def __init__(self, hmc, fraction=0.5):
+        self.hmc = hmc
+        self.fraction = fraction
+        self.force = False
+        self.rebuilds = 0
+        self.skipped = 0
+
+    def flips_accepted(self, n):
+        self.force = self.force or n > 0
+        return n
+
+    def needed(self):
+        h = self.hmc
+        if self.force or h.margin is None or h.displacement is None:
+            return True
+        return h.displacement > self.fraction * 0.5 * h.margin
+
+    def __call__(self, x=None, counter=None):
+        if self.needed():
+            self.hmc.estore.update_repulsion(self.hmc.trimesh)
+            self.hmc.displacement = 0.0
+            self.force = False
+            self.rebuilds += 1
+        else:
+            self.skipped += 1
