@@ -420,26 +420,33 @@ k_props_generic(MeshView mv, DevParams P, P4* pos_rw, double* __restrict__ vprop
 // per neighbour.
 struct PairConst {
     double lc1, lc1sq, rd;      // cut-off, its square, (double) r
-    const double* tab;          // 2^(j/64), in shared memory (tm_math::exp_tab)
+    unsigned dl_hi_floor;       // high word of -(lc1 * 2^-20): |l - lc1| is kept above that (see pair_eval)
 };
 
 // phi = exp(l/(l-lc1)) / l^r and slope = -(lc1/(l-lc1)^2 + r/l) / l^(r+1) * exp(l/(l-lc1)) for l2 < lc1^2,
 // both 0 for inactive entries. R2: r == 2 (the default exponent) without the power loop.
+// `tab` = the 2^(j/64) table in shared memory (tm_math::exp_tab_clamped). Guards, all outside the fp64 pipe:
+//  * l - lc1 is negative for an active entry except in the rounding corner l2 < lc1^2 <= l^2, and arbitrarily
+//    small; its high word is raised (unsigned max: negative doubles order like their bit patterns) to that of
+//    -(lc1 2^-20), which keeps t = l / (l - lc1) above ~ -2^20 -- inside the range of the exponential's
+//    integer arithmetic -- and changes no entry whose exp(t) is not far below the smallest double anyway;
+//  * the exponential clamps its power of two at 2^-1021 (integer max) instead of comparing t with -708:
+//    such an entry contributes ~1e-308 where the reference's exp underflows to 0.
 template <bool R2>
-__device__ __forceinline__ void pair_eval(const PairConst& C, int rr, double l2, bool active, double& phi, double& sl) {
+__device__ __forceinline__ void pair_eval(const PairConst& C, const double* tab, int rr, double l2, bool active,
+                                          double& phi, double& sl) {
     const double l2s = active ? l2 : C.lc1sq * 0.25;          // any harmless in-range value
     const double il = rsqrt_pos(l2s);
     const double l = l2s * il;
-    double dl = l - C.lc1;                                    // < 0; guard the rounding corner l2 < lc1^2 <= l^2
-    dl = dl < -1.0e-300 ? dl : -1.0e-300;
+    double dl = l - C.lc1;
+    dl = __hiloint2double((int)max((unsigned)__double2hiint(dl), C.dl_hi_floor), __double2loint(dl));
     const double w = rcp_pos(dl);
     // exp(l * w), argument <= 0
-    const double t = l * w;
-    double ex = tm_math::exp_tab(t, C.tab);
-    ex = (active && t >= -708.0) ? ex : 0.0;
+    double ex = tm_math::exp_tab_clamped(l * w, tab);
+    ex = active ? ex : 0.0;
     const double ilr = R2 ? il * il : powi(il, rr);
     phi = ex * ilr;
-    sl = -fma(C.lc1 * w, w, C.rd * il) * (phi * il);
+    sl = -fma(C.lc1 * w, w, R2 ? il + il : C.rd * il) * (phi * il);
 }
 
 // cell-ordered copy of the position records for the cell-list scan: rec[k] = (x, y, z of cell_items[k], id)
@@ -467,6 +474,9 @@ constexpr int PAIR_THREADS = TM_PAIR_NT;
 constexpr int PAIR_QCAP = 56;                   // queued candidates per thread before an early flush (cell lists)
 constexpr int PAIR_XCAP = 32;                   // exclusion-row entries per thread kept in shared memory
 constexpr int PB = TM_PAIR_BATCH;
+#ifndef TM_PAIR_INTERLEAVE
+#define TM_PAIR_INTERLEAVE 0
+#endif
 #ifndef TM_PAIR_CELL_MINB
 #define TM_PAIR_CELL_MINB 3
 #endif
@@ -484,7 +494,8 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
     double rep = 0.0;
     if (t < R.count) {
         PairConst C;
-        C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr; C.tab = s_exp2;
+        C.lc1 = lc1; C.lc1sq = lc1 * lc1; C.rd = (double)rr;
+        C.dl_hi_floor = (unsigned)__double2hiint(-lc1) - (20u << 20);
         const P4 ri = ldrec(mv.pos, i);
         const d3 xi = mk3(ri.x, ri.y, ri.z);
         d3 gr = mk3(0, 0, 0);
@@ -505,6 +516,22 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
 #pragma unroll
             for (int u = 0; u < PB; u++) jn[u] = (PB + u < e) ? idx(PB + u) : i;
             for (int k = 0; k < e; k += PB) {
+#if TM_PAIR_INTERLEAVE
+                // Entry u's record is consumed (difference vector, squared distance) and its registers are reloaded
+                // with the record of entry u of the NEXT stage at once: 71 instead of 80 instructions per entry, and
+                // slower (68.7 against 6x us, profiles/r02r): the loads of a stage no longer go out together.
+#pragma unroll
+                for (int u = 0; u < PB; u++) {
+                    const d3 dv = xi - mk3(xn[u].x, xn[u].y, xn[u].z);
+                    const double l2 = dot3(dv, dv);
+                    xn[u] = ldrec(mv.pos, jn[u]);
+                    jn[u] = (k + 2 * PB + u < e) ? idx(k + 2 * PB + u) : i;
+                    double phi, sl;
+                    pair_eval<R2>(C, s_exp2, rr, l2, (k + u < e) && (l2 < C.lc1sq), phi, sl);
+                    if (WITH_E) rep += phi;
+                    if (WITH_F) axpy3(gr, sl, dv);
+                }
+#else
                 P4 x[PB];
 #pragma unroll
                 for (int u = 0; u < PB; u++) x[u] = xn[u];
@@ -519,10 +546,11 @@ k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, 
                     const d3 dv = xi - mk3(x[u].x, x[u].y, x[u].z);
                     const double l2 = dot3(dv, dv);
                     double phi, sl;
-                    pair_eval<R2>(C, rr, l2, (k + u < e) && (l2 < C.lc1sq), phi, sl);
+                    pair_eval<R2>(C, s_exp2, rr, l2, (k + u < e) && (l2 < C.lc1sq), phi, sl);
                     if (WITH_E) rep += phi;
                     if (WITH_F) axpy3(gr, sl, dv);
                 }
+#endif
             }
         };
         if (!CELL) {

@@ -68,6 +68,25 @@ __device__ __forceinline__ double exp_tab(double t, const double* tab) {
     return __hiloint2double(__double2hiint(p) + ((k >> 6) << 20), __double2loint(p));
 }
 
+// The same with the power of two clamped at 2^-1021 (one integer max) instead of a comparison of t with -708 by
+// the caller: for t < ~-708 the result is ~1e-308 (normal) where exp() underflows to 0. Valid for
+// -2^24 < t <= 0 (the integer k must fit 32 bits). Used by the pair sweep (pair_eval).
+__device__ __forceinline__ double exp_tab_clamped(double t, const double* tab) {
+    const double MAGIC = 6755399441055744.0;
+    double kd = fma(t, 92.33248261689366, MAGIC);
+    const int k = __double2loint(kd);
+    kd -= MAGIC;
+    double r = fma(kd, -0.010830424609594047, t);
+    r = fma(kd, -8.66550983900947e-11, r);
+    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= tab[k & 63];
+    return __hiloint2double(__double2hiint(p) + (max(k >> 6, -1021) << 20), __double2loint(p));
+}
+
 // exp(t) for t <= 0 (t = l/(l - lc1) of the flat-bottom potentials). Returns 0 below -708
 // (the true value is < 3.4e-308 there).
 __device__ __forceinline__ double exp_nonpos(double t) {
