@@ -1119,6 +1119,18 @@ bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_par
     return nl.kind >= 0 && pair_force_valid(m, nl, p);
 }
 
+// cell lists: the candidates' records (position, id) at the current positions, in cell order
+static int ensure_cellrec(tm_mesh* m, const NlView& nl, cudaStream_t st) {
+    if (nl.kind == TM_NLIST_CELL && !(m->cellrec_epoch == m->pos_epoch && m->cellrec_list == nl.serial)) {
+        k_cell_gather<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, nl.cell_items, m->pos, const_cast<P4*>(nl.cell_rec));
+        TM_LAUNCHED();
+        TM_CUDA(cudaGetLastError());
+        m->cellrec_epoch = m->pos_epoch; m->cellrec_list = nl.serial;
+    }
+    return 0;
+}
+int tm_ensure_cellrec(tm_mesh* m, const NlView& nl) { return tm_join_pairs(m) || ensure_cellrec(m, nl, m->stream); }
+
 // pair sweep: energy partials (quantity 5) and/or per-vertex force
 // beside = on the mesh's second stream, concurrently with whatever the caller launches next on the
 // main stream (the ring property sweep); tm_join_pairs before the first consumer
@@ -1138,12 +1150,7 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
         st = m->stream2;
     }
     const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * (PAIR_QCAP + PAIR_XCAP) * PAIR_THREADS : 0;
-    if (nl.kind == TM_NLIST_CELL && !(m->cellrec_epoch == m->pos_epoch && m->cellrec_list == nl.serial)) {
-        // the candidates' records at the current positions, in cell order
-        k_cell_gather<<<(m->V + 255) / 256, 256, 0, st>>>(m->V, nl.cell_items, m->pos, const_cast<P4*>(nl.cell_rec));
-        TM_LAUNCHED();
-        m->cellrec_epoch = m->pos_epoch; m->cellrec_list = nl.serial;
-    }
+    if (ensure_cellrec(m, nl, st)) return 1;
 #define TM_PAIRS2(E, F, W, R2, CL) k_pairs<E, F, W, R2, CL><<<nb, PAIR_THREADS, qbytes, st>>>( \
         mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
 #define TM_PAIRS(E, F, W, R2) do { if (nb <= 0) break; if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)

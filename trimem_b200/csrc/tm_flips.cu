@@ -43,6 +43,7 @@ struct FlipWS {
     int cap = 0, E = 0;
     int *edges = nullptr, *owner = nullptr, *rem_a = nullptr, *rem_b = nullptr, *sel = nullptr;
     int *flips = nullptr, *counters = nullptr;   // counters: [0] n_rem_next [1] n_flips [2] n_acc [3] err
+    int *patch = nullptr;                        // [PATCH_CAP + 1][cap]: the patch edges k_batch_mark visited, for k_batch_select
     double *u = nullptr, *before = nullptr, *after = nullptr, *state = nullptr;   // state: props[6], e0
 };
 
@@ -192,23 +193,37 @@ __device__ __forceinline__ void for_each_patch_edge(const Topo& t, int e, F f) {
     }
 }
 
+// The edges visited are kept (slot-major, so the stores of a warp coalesce) for k_batch_select, which then reads a
+// list instead of repeating the walk's chain of dependent loads; a patch of more than PATCH_CAP visits is walked again.
+constexpr int PATCH_CAP = 64;
 __global__ void k_batch_mark(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
-                             int* __restrict__ owner) {
+                             int* __restrict__ owner, int* __restrict__ patch, int cap) {
     const int r = blockIdx.x * NT + threadIdx.x;
     if (r >= nrem) return;
     const int p = rem[r];
-    for_each_patch_edge(t, edges[p], [&](int ed) { atomicMin(owner + ed, p); });
+    int n = 0;
+    for_each_patch_edge(t, edges[p], [&](int ed) {
+        atomicMin(owner + ed, p);
+        if (n < PATCH_CAP) patch[(size_t)(n + 1) * cap + r] = ed;
+        ++n;
+    });
+    patch[r] = n;
 }
 
 // sel[p]: 0 = not selected this round, 1 = selected and flippable, 2 = selected, not flippable
 __global__ void k_batch_select(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
-                               const int* __restrict__ owner, int* __restrict__ sel) {
+                               const int* __restrict__ owner, int* __restrict__ sel, const int* __restrict__ patch, int cap) {
     const int r = blockIdx.x * NT + threadIdx.x;
     if (r >= nrem) return;
     const int p = rem[r];
     const int e = edges[p];
     bool mine = true;
-    for_each_patch_edge(t, e, [&](int ed) { if (owner[ed] != p) mine = false; });
+    const int n = patch[r];
+    if (n <= PATCH_CAP) {
+        for (int k = 0; k < n; k++) mine &= (owner[patch[(size_t)(k + 1) * cap + r]] == p);
+    } else {
+        for_each_patch_edge(t, e, [&](int ed) { if (owner[ed] != p) mine = false; });
+    }
     sel[p] = !mine ? 0 : (d_is_flip_ok(t, e) ? 1 : 2);
 }
 
@@ -257,75 +272,105 @@ __device__ __forceinline__ double energy_mul(const DevParams& P, const double* s
     return fma(P.kappa_b, s[3], e);
 }
 
-// ordered Metropolis scan over the round (the decisions are sequential, ~50 flops per
-// proposal; the warp fetches 32 proposals' data at a time); also compacts the not-yet-processed proposals for the next round and appends
-// the applied / reverted flips to the replay list.
-__global__ void k_batch_metropolis(DevParams P, int nrem, const int* __restrict__ rem, int* __restrict__ rem_next,
-                                   const double* __restrict__ u, const int* __restrict__ edges,
-                                   int* __restrict__ sel, const double* __restrict__ before,
-                                   const double* __restrict__ after, double* __restrict__ state,
-                                   int* __restrict__ flips, int* __restrict__ counters) {
-    // One warp. The decisions are inherently sequential (every acceptance changes the global sums the
-    // next energy difference is taken against), but the DATA of 32 proposals are fetched by the 32
-    // lanes at once and handed round by shuffles, so the scan costs ~100 cycles per proposal instead
-    // of a chain of dependent global loads. Every lane carries the same running state.
-    if (blockIdx.x != 0) return;
+// Ordered Metropolis scan over the round; also compacts the not-yet-processed proposals for the next round and
+// appends the applied / reverted flips to the replay list.
+//
+// One block. The decisions are inherently sequential (every acceptance changes the global sums the next energy
+// difference is taken against) but everything around them is not: per tile of MT remaining proposals all threads
+// fetch their proposal's data at once, the carried-over proposals are compacted into rem_next and the selected ones
+// -- a few percent of a round -- into shared memory, both in proposal order (ballot scans); thread 0 then walks the
+// compacted tile: ~25 dependent fp64 operations and no global load per decision. (Round 2 measured the earlier
+// one-warp version, which paid a chain of dependent global loads per 32 proposals whether selected or not, at
+// 0.8 ms for 12,288 remaining proposals: 8 of the sweep's 18 ms. profiles/r02t_pflip_launches.csv)
+constexpr int MT = 512;
+
+// exclusive prefix count of `flag` over the block in thread order; total returned to every thread
+__device__ __forceinline__ int block_rank(bool flag, int* s_warp /* MT/32 + 1 */, int& total) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    double props[6];
-    for (int q = 0; q < 6; q++) props[q] = state[q];
-    double e0 = state[6];
-    int nflips = counters[1], nacc = counters[2], nnext = 0;
-    // replay list of this round: first every applied flip, in proposal order ...
-    for (int r0 = 0; r0 < nrem; r0 += 32) {
-        const int r = r0 + lane;
-        const int p = r < nrem ? rem[r] : -1;
-        const int s = p >= 0 ? sel[p] : -1;
-        const unsigned applied = __ballot_sync(FULL, s == 1);
-        if (s == 1) flips[nflips + __popc(applied & ((1u << lane) - 1))] = edges[p];
-        nflips += __popc(applied);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(FULL, flag);
+    __syncthreads();                                   // s_warp may still be read from the previous call
+    if (lane == 0) s_warp[w] = __popc(b);
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int k = 0; k < MT / 32; k++) {
+        const int c = s_warp[k];
+        base += k < w ? c : 0;
+        tot += c;
     }
-    for (int r0 = 0; r0 < nrem; r0 += 32) {
-        const int r = r0 + lane;
+    total = tot;
+    return base + __popc(b & ((1u << lane) - 1));
+}
+
+__global__ void __launch_bounds__(MT)
+k_batch_metropolis(DevParams P, int nrem, const int* __restrict__ rem, int* __restrict__ rem_next,
+                   const double* __restrict__ u, const int* __restrict__ edges,
+                   int* __restrict__ sel, const double* __restrict__ before,
+                   const double* __restrict__ after, double* __restrict__ state,
+                   int* __restrict__ flips, int* __restrict__ counters) {
+    if (blockIdx.x != 0) return;
+    __shared__ double s_d[6][MT];
+    __shared__ double s_lu[MT];
+    __shared__ int s_ed[MT], s_p[MT];
+    __shared__ int s_warp[MT / 32 + 1];
+    const int tid = threadIdx.x;
+    int nflips = counters[1], nnext = 0;
+    // replay list of this round: first every applied flip, in proposal order ...
+    for (int r0 = 0; r0 < nrem; r0 += MT) {
+        const int r = r0 + tid;
+        const int p = r < nrem ? rem[r] : -1;
+        const bool applied = p >= 0 && sel[p] == 1;
+        int tot;
+        const int pos = block_rank(applied, s_warp, tot);
+        if (applied) flips[nflips + pos] = edges[p];
+        nflips += tot;
+    }
+    // ... then the decisions (thread 0 carries the running state)
+    double props[6] = {0, 0, 0, 0, 0, 0};
+    double e0 = 0.0;
+    int nacc = 0;
+    if (tid == 0) {
+        for (int q = 0; q < 6; q++) props[q] = state[q];
+        e0 = state[6];
+        nacc = counters[2];
+    }
+    for (int r0 = 0; r0 < nrem; r0 += MT) {
+        const int r = r0 + tid;
         const int p = r < nrem ? rem[r] : -1;
         const int s = p >= 0 ? sel[p] : -1;
         // not selected this round: carried over, order kept
-        const unsigned carry = __ballot_sync(FULL, s == 0);
-        if (s == 0) rem_next[nnext + __popc(carry & ((1u << lane) - 1))] = p;
-        nnext += __popc(carry);
-        double d[6] = {0, 0, 0, 0, 0, 0};
-        double up = 0.0;
-        int ed = 0;
+        int tot0, tot1;
+        const int pos0 = block_rank(s == 0, s_warp, tot0);
+        if (s == 0) rem_next[nnext + pos0] = p;
+        nnext += tot0;
+        const int pos1 = block_rank(s == 1, s_warp, tot1);
         if (s == 1) {
-            for (int q = 0; q < 6; q++) d[q] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q];
-            up = log(u[p]);                              // accept iff log(u) <= -dE: no exponential in the chain
-            ed = edges[p];
+            // flips.cpp:133-160: dprops = before - after
+            for (int q = 0; q < 6; q++) s_d[q][pos1] = before[6 * (size_t)p + q] - after[6 * (size_t)p + q];
+            s_lu[pos1] = log(u[p]);                      // accept iff log(u) <= -dE: no exponential in the chain
+            s_ed[pos1] = edges[p];
+            s_p[pos1] = p;
         }
-        unsigned todo = __ballot_sync(FULL, s == 1);
-        bool rejected = false;
-        while (todo) {
-            const int k = __ffs(todo) - 1;
-            todo &= todo - 1;
-            // flips.cpp:133-160: dprops = before - after; props -= dprops
-            double dk[6];
-            for (int q = 0; q < 6; q++) { dk[q] = __shfl_sync(FULL, d[q], k); props[q] -= dk[q]; }
-            const double uk = __shfl_sync(FULL, up, k);
-            const int ek = __shfl_sync(FULL, ed, k);
-            const double en = energy_mul(P, props);
-            const double de = en - e0;
-            if (de < 0.0 || uk <= -de) {
-                e0 = en;
-                ++nacc;
-            } else {
-                for (int q = 0; q < 6; q++) props[q] += dk[q];
-                if (lane == k) rejected = true;
-                if (lane == 0) flips[nflips] = ek;       // ... then every reverted flip
-                ++nflips;
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 0; k < tot1; k++) {
+                double dk[6];
+                for (int q = 0; q < 6; q++) { dk[q] = s_d[q][k]; props[q] -= dk[q]; }    // props -= dprops
+                const double en = energy_mul(P, props);
+                const double de = en - e0;
+                if (de < 0.0 || s_lu[k] <= -de) {
+                    e0 = en;
+                    ++nacc;
+                } else {
+                    for (int q = 0; q < 6; q++) props[q] += dk[q];
+                    sel[s_p[k]] = 3;                     // rejected: flip back
+                    flips[nflips++] = s_ed[k];           // ... then every reverted flip
+                }
             }
         }
-        if (rejected) sel[p] = 3;                        // rejected: flip back
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         for (int q = 0; q < 6; q++) state[q] = props[q];
         state[6] = e0;
         counters[0] = nnext; counters[1] = nflips; counters[2] = nacc;
@@ -372,7 +417,7 @@ int ensure_ws(tm_mesh* m, int n) {
     }
     if (ws->cap < n) {
         cudaFree(ws->edges); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel); cudaFree(ws->flips);
-        cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after);
+        cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after); cudaFree(ws->patch);
         ws->cap = 0;
         size_t c = (size_t)n;
         TM_CUDA(cudaMalloc(&ws->edges, sizeof(int) * c));
@@ -383,6 +428,7 @@ int ensure_ws(tm_mesh* m, int n) {
         TM_CUDA(cudaMalloc(&ws->u, sizeof(double) * c));
         TM_CUDA(cudaMalloc(&ws->before, sizeof(double) * 6 * c));
         TM_CUDA(cudaMalloc(&ws->after, sizeof(double) * 6 * c));
+        TM_CUDA(cudaMalloc(&ws->patch, sizeof(int) * (PATCH_CAP + 1) * c));
         ws->cap = n;
     }
     if (!ws->counters) TM_CUDA(cudaMalloc(&ws->counters, sizeof(int) * 8));
@@ -406,7 +452,7 @@ int tm_flips_release(tm_mesh* m) {
     if (!ws) return 0;
     cudaFree(ws->edges); cudaFree(ws->owner); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel);
     cudaFree(ws->flips); cudaFree(ws->counters); cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after);
-    cudaFree(ws->state);
+    cudaFree(ws->state); cudaFree(ws->patch);
     delete ws;
     m->flipws = nullptr;
     return 0;
@@ -436,6 +482,7 @@ static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, 
     // partitioned mesh: the sweep runs replicated on every rank over the whole mesh (same proposals, same
     // decisions, same connectivity everywhere), so every rank first needs every position (collective)
     if (tm_part_make_current(m)) return 1;
+    if (nl && tm_ensure_cellrec(m, nl->view())) return 1;      // the live evaluations scan the cell-ordered records
     FlipWS* ws = (FlipWS*)m->flipws;
     cudaStream_t st = m->stream;
     const DevParams P = tm_to_dev(*p);
@@ -461,12 +508,12 @@ static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, 
         while (nrem > 0) {
             const int nb = (nrem + NT - 1) / NT, nb4 = (4 * nrem + NT - 1) / NT;
             TM_CUDA(cudaMemsetAsync(ws->owner, 0x7f, sizeof(int) * (size_t)ws->E, st));
-            k_batch_mark<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner); TM_LAUNCHED();
-            k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel); TM_LAUNCHED();
+            k_batch_mark<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->patch, ws->cap); TM_LAUNCHED();
+            k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel, ws->patch, ws->cap); TM_LAUNCHED();
             k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->before, ws->counters); TM_LAUNCHED();
             k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 1); TM_LAUNCHED();
             k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->after, ws->counters); TM_LAUNCHED();
-            k_batch_metropolis<<<1, 32, 0, st>>>(P, nrem, rem, rem_next, ws->u, ws->edges, ws->sel, ws->before,
+            k_batch_metropolis<<<1, MT, 0, st>>>(P, nrem, rem, rem_next, ws->u, ws->edges, ws->sel, ws->before,
                                                  ws->after, ws->state, ws->flips, ws->counters); TM_LAUNCHED();
             k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 3); TM_LAUNCHED();
             TM_CUDA(cudaMemcpyAsync(hc, ws->counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
@@ -513,6 +560,7 @@ int tm_edge_vertex_properties(tm_mesh* m, tm_nlist* nl, const tm_energy_params* 
     TM_CHECK(!nl || nl->kind != TM_NLIST_VERLET || nl->rows_count == m->V,
              "this verlet list holds a partition's slice only");
     FlipWS* ws = (FlipWS*)m->flipws;
+    if (nl && tm_ensure_cellrec(m, nl->view())) return 1;
     TM_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(int) * 8, m->stream));
     k_evp<<<1, 32, 0, m->stream>>>(m->view(), topo_of(m), nl ? nl->view() : tm_no_nlist(), tm_to_dev(*p), edge,
                                    ws->state, ws->counters + 3);

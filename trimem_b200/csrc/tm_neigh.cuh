@@ -140,6 +140,40 @@ __device__ __forceinline__ void for_each_pair_fast(const MeshView& mv, const NlV
             const double l2 = dot3(d, d);
             if (l2 < dmax2) f(j, d, l2);
         }
+    } else if (nl.kind == TM_NLIST_CELL && LIVE) {
+        // Flip kernels (one thread evaluates one vertex, latency is everything): the candidates of a cell are
+        // contiguous records in cell_rec (position and id, gathered at the current positions: tm_ensure_cellrec)
+        // and x is the fastest cell index, so the 27 cells are 9 runs read four records per trip -- independent
+        // loads -- instead of 150 times cell_items -> pos, two dependent loads per candidate. Same candidate set
+        // and semantics as below; the order of the sum is that of the cell-list pair sweep (k_pairs).
+        int c[3];
+        c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
+        c[1] = (int)((xi.y - nl.box_min[1]) / nl.cell[1]);
+        c[2] = (int)((xi.z - nl.box_min[2]) / nl.cell[2]);
+        const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, nl.shape[0] - 1);
+        if (x0 > x1) return;
+        for (int b = -1; b < 2; b++) {
+            const int jj = c[1] + b;
+            if (jj < 0 || jj >= nl.shape[1]) continue;
+            for (int g = -1; g < 2; g++) {
+                const int kk = c[2] + g;
+                if (kk < 0 || kk >= nl.shape[2]) continue;
+                const int base = jj * nl.strides[1] + kk * nl.strides[2];          // strides[0] == 1
+                const int kb = __ldg(nl.cell_start + base + x0), ke = __ldg(nl.cell_start + base + x1 + 1);
+                for (int k = kb; k < ke; k += 4) {
+                    P4 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) x[u] = ldrec(nl.cell_rec, min(k + u, ke - 1));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int j = __double2loint(x[u].w);
+                        const d3 d = xi - mk3(x[u].x, x[u].y, x[u].z);
+                        const double l2 = dot3(d, d);
+                        if (k + u < ke && j != i && l2 < dmax2 && !excluded_live(mv, i, j, nl.excl)) f(j, d, l2);
+                    }
+                }
+            }
+        }
     } else if (nl.kind == TM_NLIST_CELL) {
         int c[3];
         c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
