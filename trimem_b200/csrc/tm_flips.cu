@@ -43,6 +43,7 @@ struct FlipWS {
     int cap = 0, E = 0;
     int *edges = nullptr, *owner = nullptr, *rem_a = nullptr, *rem_b = nullptr, *sel = nullptr;
     int *flips = nullptr, *counters = nullptr;   // counters: [0] n_rem_next [1] n_flips [2] n_acc [3] err
+    int *selidx = nullptr;                       // proposals selected and flippable this round (counters[5] of them)
     int *patch = nullptr;                        // [PATCH_CAP + 1][cap]: the patch edges k_batch_mark visited, for k_batch_select
     double *u = nullptr, *before = nullptr, *after = nullptr, *state = nullptr;   // state: props[6], e0
 };
@@ -115,64 +116,187 @@ __device__ bool live_vertex_props(const MeshView& mv, const Topo& t, const NlVie
     return true;
 }
 
+// The same evaluation by a whole warp (all 32 lanes call it with the same v; every lane receives the six values).
+// One thread per patch vertex is pure latency -- ring walk, ring records, ~150 cell-list candidates, each a chain of
+// dependent loads: ~150 us per evaluation at 40,962 vertices, profiles/r02u -- so the lanes split the work: the ring
+// is walked once (every lane follows the same chain; lane s keeps the word of slot s), lane s evaluates slot s with
+// its neighbours' spokes taken by shuffle, the list candidates are dealt out lane by lane, and the sums are fixed
+// butterflies. Per-slot and per-pair arithmetic is that of vertex_props / for_each_pair_fast<LIVE>; only the order
+// of the sums differs (tree instead of ring order). Valence > 32: lane 0 evaluates serially.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ bool warp_live_vertex_props(const MeshView& mv, const Topo& t, const NlView& nl, const DevParams& P,
+                                       int v, double out[6]) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // ring of v: every lane walks (same addresses: one transaction per step), lane s keeps slot s
+    int d = 0, word = 0;
+    bool big = false;
+    {
+        const int h0 = vld(t.v_he + v);
+        if (h0 >= 0) {
+            int h = h0;
+            do {
+                if (d >= 32) { big = true; break; }
+                int w = vld(t.he_to + h);
+                if (vld(t.he_face + h) >= 0) w |= TM_RING_FACE;
+                if (vld(t.he_face + (h ^ 1)) >= 0) w |= TM_RING_OFACE;
+                if (lane == d) word = w;
+                ++d;
+                h = vld(t.he_next + (h ^ 1));
+            } while (h != h0);
+        }
+    }
+    if (big) {
+        int ok = 1;
+        if (lane == 0) ok = live_vertex_props(mv, t, nl, P, v, out) ? 1 : 0;
+        for (int q = 0; q < 6; q++) out[q] = __shfl_sync(FULL, out[q], 0);
+        return __shfl_sync(FULL, ok, 0) != 0;
+    }
+    const d3 xi = ldpos(mv.pos, v);
+    double area = 0, vol = 0, curv = 0, teth = 0;
+    if (d > 0) {
+        const bool on = lane < d;
+        const d3 e = on ? ldpos(mv.pos, word & TM_RING_MASK) - xi : mk3(0, 0, 0);
+        const int prv = lane == 0 ? d - 1 : lane - 1, nxt = lane + 1 >= d ? 0 : lane + 1;
+        const d3 e_p = mk3(__shfl_sync(FULL, e.x, prv), __shfl_sync(FULL, e.y, prv), __shfl_sync(FULL, e.z, prv));
+        const d3 e_n = mk3(__shfl_sync(FULL, e.x, nxt), __shfl_sync(FULL, e.y, nxt), __shfl_sync(FULL, e.z, nxt));
+        if (on && (word & TM_RING_FACE)) {                     // slot `lane`, as vertex_props::step
+            const d3 n = cross3(e, e_p), n_n = cross3(e_n, e);
+            const double l = sqrt_nn(dot3(e, e));
+            const double a_f = 0.5 * sqrt_nn(dot3(n, n));
+            area = a_f;
+            vol = dot3(xi, n);
+            if (word & TM_RING_OFACE) curv = l * tm_math::atan2_fast(-l * dot3(e_n, n), dot3(n, n_n));
+            if (P.bond_type == TM_BOND_EDGE) { if (l > P.lc0 || l < P.lc1) teth = tether_edge(l, P); }
+            else { const double q = a_f / P.a0 - 1.0; teth = q * q; }
+        }
+        area = warp_sum(area); vol = warp_sum(vol); curv = warp_sum(curv); teth = warp_sum(teth);
+    }
+    area = area / 3.0;
+    vol = vol / 18.0;
+    curv = curv / 4.0;
+    teth = teth / (P.bond_type == TM_BOND_EDGE ? 2.0 : 3.0);
+    double rep = 0.0;
+    if (nl.kind >= 0 && P.rep_lc1 > 0.0) {
+        const double lc1 = P.rep_lc1, dmax2 = lc1 * lc1;
+        const int rr = P.rep_r;
+        double sl;
+        if (nl.kind == TM_NLIST_VERLET) {
+            const int n = nl.row_cnt[v];
+            const int* col = nl.row_j + tm_row_base(v, nl.row_cap);
+            for (int k = lane; k < n; k += 32) {
+                const d3 dv = xi - ldpos(mv.pos, __ldg(col + k * 32));
+                const double l2 = dot3(dv, dv);
+                if (l2 < dmax2) rep += repulsion_pair<false>(l2, lc1, rr, sl);
+            }
+        } else {
+            // cell list: build-time occupancy, live position of v, live exclusions (cell_list.h:131-219); the 27
+            // cells are 9 runs of contiguous records (tm_ensure_cellrec), dealt out to the lanes
+            int c[3];
+            c[0] = (int)((xi.x - nl.box_min[0]) / nl.cell[0]);
+            c[1] = (int)((xi.y - nl.box_min[1]) / nl.cell[1]);
+            c[2] = (int)((xi.z - nl.box_min[2]) / nl.cell[2]);
+            const int x0 = max(c[0] - 1, 0), x1 = min(c[0] + 1, nl.shape[0] - 1);
+            // lane r < 9 fetches the bounds of run r; every lane then walks all runs with its own stride
+            int kb = 0, ke = 0;
+            if (lane < 9 && x0 <= x1) {
+                const int jj = c[1] + lane / 3 - 1, kk = c[2] + lane % 3 - 1;
+                if (jj >= 0 && jj < nl.shape[1] && kk >= 0 && kk < nl.shape[2]) {
+                    const int base = jj * nl.strides[1] + kk * nl.strides[2];          // strides[0] == 1
+                    kb = __ldg(nl.cell_start + base + x0);
+                    ke = __ldg(nl.cell_start + base + x1 + 1);
+                }
+            }
+            for (int r = 0; r < 9; r++) {
+                const int b = __shfl_sync(FULL, kb, r), e = __shfl_sync(FULL, ke, r);
+                for (int k = b + lane; k < e; k += 32) {
+                    const P4 x = ldrec(nl.cell_rec, k);
+                    const int j = __double2loint(x.w);
+                    const d3 dv = xi - mk3(x.x, x.y, x.z);
+                    const double l2 = dot3(dv, dv);
+                    if (j != v && l2 < dmax2 && !excluded_live(mv, v, j, nl.excl)) rep += repulsion_pair<false>(l2, lc1, rr, sl);
+                }
+            }
+        }
+        rep = warp_sum(rep);
+    }
+    out[0] = area; out[1] = vol; out[2] = curv;
+    out[3] = 2.0 * curv * curv / area;
+    out[4] = teth; out[5] = rep;
+    return true;
+}
+
 // ---- TM_FLIP_SERIAL ------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_flip_serial(MeshView mv, Topo t, NlView nl, DevParams P, int n, const int* __restrict__ edges,
               const double* __restrict__ u, double* __restrict__ state, int* __restrict__ flips,
               int* __restrict__ counters) {
-    const int lane = threadIdx.x;
-    double props[6];
-    for (int q = 0; q < 6; q++) props[q] = state[q];
-    double e0 = energy_of(P, props);
-    int nflips = 0, nacc = 0, err = 0;
-
+    // four warps, one per patch vertex (warp_live_vertex_props); thread 0 keeps the running state and takes the
+    // decisions, in the reference's order of operations (flips.cpp:22-80)
+    __shared__ double s_vp[4][6];
+    __shared__ int s_ok, s_err;
+    const int tid = threadIdx.x, wq = tid >> 5, lane = tid & 31;
+    double props[6] = {0, 0, 0, 0, 0, 0};
+    double e0 = 0.0;
+    int nflips = 0, nacc = 0;
+    if (tid == 0) {
+        for (int q = 0; q < 6; q++) props[q] = state[q];
+        e0 = energy_of(P, props);
+        s_err = 0;
+    }
+    __syncthreads();
+    auto evaluate = [&](int e, double (&sum)[6]) {
+        double vp[6];
+        const bool fine = warp_live_vertex_props(mv, t, nl, P, patch_vertex(t, e, wq), vp);
+        if (lane == 0) {
+            for (int q = 0; q < 6; q++) s_vp[wq][q] = vp[q];
+            if (!fine) s_err = 1;
+        }
+        __syncthreads();
+        if (tid == 0)                       // props{0} += vp(v0) += vp(v1) ... in the reference's order
+            for (int q = 0; q < 6; q++) sum[q] = ((s_vp[0][q] + s_vp[1][q]) + s_vp[2][q]) + s_vp[3][q];
+        __syncthreads();
+    };
     for (int p = 0; p < n; p++) {
         const int e = edges[p];
-        int ok = 0;
-        if (lane == 0) ok = d_is_flip_ok(t, e) ? 1 : 0;     // also false on boundary edges
-        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (tid == 0) s_ok = d_is_flip_ok(t, e) ? 1 : 0;     // also false on boundary edges
+        __syncthreads();
+        const int ok = s_ok;
+        __syncthreads();
         if (!ok) continue;
-
-        double vp[6] = {0, 0, 0, 0, 0, 0}, oprops[6], nprops[6];
-        if (lane < 4 && !live_vertex_props(mv, t, nl, P, patch_vertex(t, e, lane), vp)) err = 1;
-        for (int q = 0; q < 6; q++) {   // props{0} += vp(v0) += vp(v1) ... in the reference's order
-            double s = 0.0;
-            for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[q], l);
-            oprops[q] = s;
+        double oprops[6] = {0, 0, 0, 0, 0, 0}, nprops[6] = {0, 0, 0, 0, 0, 0};
+        evaluate(e, oprops);
+        if (tid == 0) { d_flip(t, e); __threadfence_block(); }
+        __syncthreads();
+        evaluate(e, nprops);
+        if (tid == 0) {
+            // flips.cpp:49-76
+            for (int q = 0; q < 6; q++) { props[q] -= oprops[q]; props[q] += nprops[q]; }
+            const double en = energy_of(P, props);
+            const double de = en - e0;
+            const double alpha = de < 0.0 ? 1.0 : exp(-de);
+            flips[nflips++] = e;
+            if (u[p] <= alpha) {
+                e0 = en;
+                ++nacc;
+            } else {
+                d_flip(t, e);
+                flips[nflips++] = e;
+                for (int q = 0; q < 6; q++) { props[q] -= nprops[q]; props[q] += oprops[q]; }
+                __threadfence_block();
+            }
         }
-        __syncwarp();
-        if (lane == 0) d_flip(t, e);
-        __syncwarp();
-        if (lane < 4 && !live_vertex_props(mv, t, nl, P, patch_vertex(t, e, lane), vp)) err = 1;
-        for (int q = 0; q < 6; q++) {
-            double s = 0.0;
-            for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[q], l);
-            nprops[q] = s;
-        }
-        // flips.cpp:49-76
-        for (int q = 0; q < 6; q++) { props[q] -= oprops[q]; props[q] += nprops[q]; }
-        const double en = energy_of(P, props);
-        const double de = en - e0;
-        const double alpha = de < 0.0 ? 1.0 : exp(-de);
-        const bool accept = u[p] <= alpha;
-        if (lane == 0) flips[nflips] = e;
-        ++nflips;
-        if (accept) {
-            e0 = en;
-            ++nacc;
-        } else {
-            __syncwarp();
-            if (lane == 0) { d_flip(t, e); flips[nflips] = e; }
-            ++nflips;
-            for (int q = 0; q < 6; q++) { props[q] -= nprops[q]; props[q] += oprops[q]; }
-            __syncwarp();
-        }
+        __syncthreads();
     }
-    err = __any_sync(0xffffffffu, err);
-    if (lane == 0) {
+    if (tid == 0) {
         for (int q = 0; q < 6; q++) state[q] = props[q];
         state[6] = e0;
-        counters[1] = nflips; counters[2] = nacc; counters[3] = err;
+        counters[1] = nflips; counters[2] = nacc; counters[3] = s_err;
     }
 }
 
@@ -212,7 +336,8 @@ __global__ void k_batch_mark(Topo t, int nrem, const int* __restrict__ rem, cons
 
 // sel[p]: 0 = not selected this round, 1 = selected and flippable, 2 = selected, not flippable
 __global__ void k_batch_select(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
-                               const int* __restrict__ owner, int* __restrict__ sel, const int* __restrict__ patch, int cap) {
+                               const int* __restrict__ owner, int* __restrict__ sel, const int* __restrict__ patch, int cap,
+                               int* __restrict__ nsel, int* __restrict__ selidx) {
     const int r = blockIdx.x * NT + threadIdx.x;
     if (r >= nrem) return;
     const int p = rem[r];
@@ -224,29 +349,31 @@ __global__ void k_batch_select(Topo t, int nrem, const int* __restrict__ rem, co
     } else {
         for_each_patch_edge(t, e, [&](int ed) { if (owner[ed] != p) mine = false; });
     }
-    sel[p] = !mine ? 0 : (d_is_flip_ok(t, e) ? 1 : 2);
+    const int sv = !mine ? 0 : (d_is_flip_ok(t, e) ? 1 : 2);
+    sel[p] = sv;
+    if (sv == 1) selidx[atomicAdd(nsel, 1)] = p;          // (any order: the evaluations are independent)
 }
 
-// 4 threads per remaining proposal: patch properties on the current connectivity
-__global__ void k_batch_props(MeshView mv, Topo t, NlView nl, DevParams P, int nrem,
-                              const int* __restrict__ rem, const int* __restrict__ edges,
-                              const int* __restrict__ sel, double* __restrict__ out, int* __restrict__ counters) {
-    const int gid = blockIdx.x * NT + threadIdx.x;
-    const int r = gid >> 2, q = gid & 3;
-    const bool active = r < nrem && sel[rem[r]] == 1;
-    double vp[6] = {0, 0, 0, 0, 0, 0};
-    int p = 0;
-    if (active) {
-        p = rem[r];
-        if (!live_vertex_props(mv, t, nl, P, patch_vertex(t, edges[p], q), vp)) counters[3] = 1;
+// One block per selected proposal (compacted by k_batch_select into selidx, *nsel of them; the grid is sized for
+// every remaining proposal and the surplus blocks leave at once), one warp per patch vertex.
+__global__ void __launch_bounds__(128)
+k_batch_props(MeshView mv, Topo t, NlView nl, DevParams P, const int* __restrict__ nsel, const int* __restrict__ selidx,
+              const int* __restrict__ edges, double* __restrict__ out, int* __restrict__ counters) {
+    if ((int)blockIdx.x >= *nsel) return;
+    __shared__ double s_vp[4][6];
+    const int p = selidx[blockIdx.x];
+    const int wq = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double vp[6];
+    const bool fine = warp_live_vertex_props(mv, t, nl, P, patch_vertex(t, edges[p], wq), vp);
+    if (lane == 0) {
+        for (int c = 0; c < 6; c++) s_vp[wq][c] = vp[c];
+        if (!fine) counters[3] = 1;
     }
-    // sum the 4 vertices in the reference's order (all 4 lanes of a group take the same branch)
-    const unsigned base = (threadIdx.x & 31) & ~3u;
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        double s = 0.0;
-        for (int l = 0; l < 4; l++) s += __shfl_sync(0xffffffffu, vp[c], base + l);
-        if (active && q == 0) out[6 * (size_t)p + c] = s;
+    __syncthreads();
+    // the 4 vertices summed in the reference's order
+    if (threadIdx.x < 6) {
+        const int c = threadIdx.x;
+        out[6 * (size_t)p + c] = ((s_vp[0][c] + s_vp[1][c]) + s_vp[2][c]) + s_vp[3][c];
     }
 }
 
@@ -417,7 +544,7 @@ int ensure_ws(tm_mesh* m, int n) {
     }
     if (ws->cap < n) {
         cudaFree(ws->edges); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel); cudaFree(ws->flips);
-        cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after); cudaFree(ws->patch);
+        cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after); cudaFree(ws->patch); cudaFree(ws->selidx);
         ws->cap = 0;
         size_t c = (size_t)n;
         TM_CUDA(cudaMalloc(&ws->edges, sizeof(int) * c));
@@ -429,6 +556,7 @@ int ensure_ws(tm_mesh* m, int n) {
         TM_CUDA(cudaMalloc(&ws->before, sizeof(double) * 6 * c));
         TM_CUDA(cudaMalloc(&ws->after, sizeof(double) * 6 * c));
         TM_CUDA(cudaMalloc(&ws->patch, sizeof(int) * (PATCH_CAP + 1) * c));
+        TM_CUDA(cudaMalloc(&ws->selidx, sizeof(int) * c));
         ws->cap = n;
     }
     if (!ws->counters) TM_CUDA(cudaMalloc(&ws->counters, sizeof(int) * 8));
@@ -452,7 +580,7 @@ int tm_flips_release(tm_mesh* m) {
     if (!ws) return 0;
     cudaFree(ws->edges); cudaFree(ws->owner); cudaFree(ws->rem_a); cudaFree(ws->rem_b); cudaFree(ws->sel);
     cudaFree(ws->flips); cudaFree(ws->counters); cudaFree(ws->u); cudaFree(ws->before); cudaFree(ws->after);
-    cudaFree(ws->state); cudaFree(ws->patch);
+    cudaFree(ws->state); cudaFree(ws->patch); cudaFree(ws->selidx);
     delete ws;
     m->flipws = nullptr;
     return 0;
@@ -498,7 +626,7 @@ static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, 
     *mutated = true;
 
     if (mode == TM_FLIP_SERIAL) {
-        k_flip_serial<<<1, 32, 0, st>>>(mv, t, nv, P, n, ws->edges, ws->u, ws->state, ws->flips, ws->counters);
+        k_flip_serial<<<1, 128, 0, st>>>(mv, t, nv, P, n, ws->edges, ws->u, ws->state, ws->flips, ws->counters);
         TM_LAUNCHED();
     } else {
         k_init_state<<<1, 32, 0, st>>>(P, ws->state); TM_LAUNCHED();
@@ -506,13 +634,15 @@ static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, 
         int nrem = n;
         int *rem = ws->rem_a, *rem_next = ws->rem_b;
         while (nrem > 0) {
-            const int nb = (nrem + NT - 1) / NT, nb4 = (4 * nrem + NT - 1) / NT;
+            const int nb = (nrem + NT - 1) / NT;
             TM_CUDA(cudaMemsetAsync(ws->owner, 0x7f, sizeof(int) * (size_t)ws->E, st));
             k_batch_mark<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->patch, ws->cap); TM_LAUNCHED();
-            k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel, ws->patch, ws->cap); TM_LAUNCHED();
-            k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->before, ws->counters); TM_LAUNCHED();
+            TM_CUDA(cudaMemsetAsync(ws->counters + 5, 0, sizeof(int), st));
+            k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel, ws->patch, ws->cap,
+                                             ws->counters + 5, ws->selidx); TM_LAUNCHED();
+            k_batch_props<<<nrem, 128, 0, st>>>(mv, t, nv, P, ws->counters + 5, ws->selidx, ws->edges, ws->before, ws->counters); TM_LAUNCHED();
             k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 1); TM_LAUNCHED();
-            k_batch_props<<<nb4, NT, 0, st>>>(mv, t, nv, P, nrem, rem, ws->edges, ws->sel, ws->after, ws->counters); TM_LAUNCHED();
+            k_batch_props<<<nrem, 128, 0, st>>>(mv, t, nv, P, ws->counters + 5, ws->selidx, ws->edges, ws->after, ws->counters); TM_LAUNCHED();
             k_batch_metropolis<<<1, MT, 0, st>>>(P, nrem, rem, rem_next, ws->u, ws->edges, ws->sel, ws->before,
                                                  ws->after, ws->state, ws->flips, ws->counters); TM_LAUNCHED();
             k_batch_apply<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->sel, 3); TM_LAUNCHED();
