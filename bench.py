@@ -34,8 +34,47 @@ FLUSH_BYTES = 512 << 20          # > 126 MB L2
 
 # Counters of the three sweeps from the committed `ncu --set full` capture of this build at 655,362 vertices
 # (per launch; profiles/README.md says how they were taken). They explain the live timings of the roofline object.
-NCU_SOURCE = "profiles/r02_ncu_full_sweeps.txt (per launch, 655,362 vertices)"
-NCU = {}
+NCU_SOURCE = "profiles/r02_ncu_full_sweeps.txt, profiles/r02_ncu_full_grad.txt (per launch, 655,362 vertices)"
+# issue bound = 2 * (fp64 warp instructions) + (other warp instructions) cycles per scheduler: an fp64 warp instruction holds a
+# scheduler's issue port for two cycles on B200 (64 fp64 lanes per SM), DESIGN.md section 4
+NCU = {
+    "k_pairs": {
+        "ncu_us_cold_serialised": 63.104,
+        "dram_bytes_per_launch": 81661952.0,
+        "warp_instructions": 36611824.0,
+        "fp64_warp_instructions": 16903951,
+        "fp64_pipe_pct": 53.8,
+        "issue_bound_cycles_per_scheduler": 90398,
+        "active_cycles_per_scheduler": 106085,
+        "issue_bound_fraction": 0.852,
+        "registers": 80,
+        "warps_active_pct": 34.057766
+    },
+    "k_props": {
+        "ncu_us_cold_serialised": 37.216,
+        "dram_bytes_per_launch": 44592639.99999999,
+        "warp_instructions": 18982564.0,
+        "fp64_warp_instructions": 9878346,
+        "fp64_pipe_pct": 54.8,
+        "issue_bound_cycles_per_scheduler": 48752,
+        "active_cycles_per_scheduler": 60866,
+        "issue_bound_fraction": 0.801,
+        "registers": 64,
+        "warps_active_pct": 44.341362
+    },
+    "k_grad": {
+        "ncu_us_cold_serialised": 38.56,
+        "dram_bytes_per_launch": 95247104.0,
+        "warp_instructions": 12132445.0,
+        "fp64_warp_instructions": 7113958,
+        "fp64_pipe_pct": 37.4,
+        "issue_bound_cycles_per_scheduler": 32511,
+        "active_cycles_per_scheduler": 64324,
+        "issue_bound_fraction": 0.505,
+        "registers": 128,
+        "warps_active_pct": 21.139982
+    }
+}
 
 
 def env_int(name, default):
@@ -171,7 +210,7 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
                                               kappa=(10.0 * (1 + gid % 8), 1.0e6, 1.0e6, 0.0, 1.0e5, 1.0e3),
                                               fracs=(1.0, 0.5 + 0.5 * ((gid // 8) % 8) / 7.0, 1.0))
         ch = hmc.MeshHMC(mesh, estore, options={"time_step": 1.0e-6, "num_integration_steps": L, "info_step": 0},
-                         verbose=False, rng=np.random.RandomState(1000 + gid))
+                         verbose=False, rng=np.random.default_rng(1000 + gid))   # (a Generator draws outside the interpreter lock)
         chains.append((mesh, estore, ch, gid))
     V = chains[0][0].n_vertices()
     stats = [None] * R
@@ -726,8 +765,8 @@ def main():
             "hmc_step_config2": hmc2,
             "partitioned": part,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom + " (longest kernel of the step; all three sweeps are bound by instruction issue, "
-                                                     "fp64 at half rate, not by HBM: DESIGN.md section 4)",
+            "roofline": {"bound": "hbm", "kernel": dom + " (longest kernel of the step; the sweeps are bound by fp64 instruction issue and by the "
+                                                     "latency of a warp's dependent loads, not by HBM: DESIGN.md section 4)",
                          "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
                          "traffic": NCU.get(dom, {}).get("dram_bytes_per_launch") if args.subdiv == 8 else None,
                          "traffic_source": NCU_SOURCE, "peak_source": peak_src,

@@ -49,16 +49,17 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 #ifndef TM_GRAD_NT
 #define TM_GRAD_NT 128
 #endif
-// resident blocks per SM the register allocation aims at (measured on B200 at 655,362 vertices, gpurun_out
-// r02f / r02i kernel timings): property sweep 8 blocks of 128 = 64 registers (44 bytes of spills) 42.2 us, 6 blocks
-// / 80 registers 44.6, 5 / 96 47.0, 4 / 120 50.9; ring gradient 6 blocks / 80 registers (84 bytes of spills) 46.3 us,
-// 5 / 96 47.5, 4 / 128 45.2-57 (depending on what the scheduler hoists), 8 / 64 48.7. 64- and 256-thread blocks
-// at the same number of resident warps: within 1 us.
+// resident blocks per SM the register allocation aims at (measured on B200 at 655,362 vertices, profiles/r02*
+// kernel timings): property sweep 8 blocks of 128 = 64 registers (44 bytes of spills) 42.2 us, 6 blocks / 80
+// registers 44.6, 5 / 96 47.0, 4 / 120 50.9. Ring gradient, after the pair force and the sums moved to the head of
+// the kernel: 4 blocks / 128 registers (no spills) 42.5 us, 5 / 96 45.8, 6 / 80 (470 bytes of spills) 44.1, 8 / 64
+// 48.7: the sweep is bound by the round trips of a warp, not by issue, and the larger allocation lets the scheduler
+// keep more of a warp's loads in flight. 64- and 256-thread blocks at the same number of resident warps: within 1 us.
 #ifndef TM_PROPS_MINB
 #define TM_PROPS_MINB 8
 #endif
 #ifndef TM_GRAD_MINB
-#define TM_GRAD_MINB 5
+#define TM_GRAD_MINB 4
 #endif
 constexpr int TM_PROPS_THREADS = TM_PROPS_NT;
 constexpr int TM_GRAD_THREADS  = TM_GRAD_NT;

@@ -53,6 +53,14 @@ __device__ __forceinline__ int row_valence(const R8& r) {
     return d;
 }
 
+// slot s of a row held in registers (select chain: no reload of the row for a rare slot)
+__device__ __forceinline__ int row_slot(const R8& r, int s) {
+    int j = r.v[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) j = s == k ? r.v[k] : j;
+    return j;
+}
+
 __device__ __forceinline__ R8 ldrow(const R8* __restrict__ rows, int i) {
     R8 r;
     const int4 a = __ldg(reinterpret_cast<const int4*>(rows + i));
@@ -966,7 +974,7 @@ __device__ __forceinline__ d3 ring_grad_closed(const MeshView& mv, const DevPara
     while (tmask) {
         const int s = __ffs(tmask) - 1;
         tmask &= tmask - 1;
-        const d3 e = ldpos(mv.pos, mv.ring8[i].v[s]) - xi;
+        const d3 e = ldpos(mv.pos, row_slot(row, s)) - xi;
         const double l2 = dot3(e, e);
         const double il = rsqrt_pos(l2);
         axpy3(g, -K.kt * tether_edge_fac(l2 * il, P) * il, e);
@@ -1001,12 +1009,17 @@ __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevP
 // what follows the ring walk of vertex i: repulsion, the gradient row, and the velocity-Verlet update fused
 // into the sweep (tm_integrate.cu)
 template <int UPD>
+// fpre: the vertex's pair force, already in registers (the closed-fan sweep requests it with the ring records)
 __device__ __forceinline__ void grad_finish(const DevParams& P, int i, const P4& ri, d3 g, const double* __restrict__ force,
-                                            double* __restrict__ grad, const VVFuse& U) {
+                                            double* __restrict__ grad, const VVFuse& U, const d3* fpre = nullptr) {
     // repulsion (mesh_properties.cpp:139-146): 2 kappa_r * pair force of k_pairs
     if (force) {
-        const double* f = force + 3 * (size_t)i;
-        axpy3(g, 2.0 * P.kappa_r, mk3(__ldg(f), __ldg(f + 1), __ldg(f + 2)));
+        if (fpre) {
+            axpy3(g, 2.0 * P.kappa_r, *fpre);
+        } else {
+            const double* f = force + 3 * (size_t)i;
+            axpy3(g, 2.0 * P.kappa_r, mk3(__ldg(f), __ldg(f + 1), __ldg(f + 2)));
+        }
     }
 
     double* o = grad + 3 * (size_t)i;
@@ -1057,23 +1070,26 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     row.v[0] = TM_RING_GENERIC;
     P4 ri;
     ri.x = ri.y = ri.z = ri.w = 0.0;
+    d3 fr = mk3(0, 0, 0);
     if (live) {
         row = ldrow(mv.ring8, i);
         ri = ldrec(mv.pos, i);
+        // the epilogue's operands. The pair force is loaded now (three coalesced doubles: waiting for it behind the
+        // walk was a tenth of a warp's life, profiles/r02x); the update's are requested into L2, no register held.
+        if (force) { const double* f = force + 3 * (size_t)i; fr = mk3(__ldg(f), __ldg(f + 1), __ldg(f + 2)); }
+        if (UPD > 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
+        }
     }
+    // (the three sums are requested with the row, not behind it)
+    double fA, fV, fC;
+    penalty_factors(P, sums, fA, fV, fC);
     const bool closed = row.v[0] != TM_RING_GENERIC;
     const int d = closed ? row_valence(row) : 0;
     const int dmax = __reduce_max_sync(0xffffffffu, d);
     const bool uniform = __all_sync(0xffffffffu, !closed || d == dmax);
     if (!closed) return;
-    // the epilogue's operands: requested now (no register held), L2-resident when the walk is done
-    if (force) asm volatile("prefetch.global.L2 [%0];" ::"l"(force + 3 * (size_t)i));
-    if (UPD > 0) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
-    }
-    double fA, fV, fC;
-    penalty_factors(P, sums, fA, fV, fC);
     GradC K;
     K.kb = P.kappa_b; K.kt = P.kappa_t;
     K.W0 = fma(2.0 * K.kb, ri.w, 0.5 * fC);       // W_s = W0 - kb (rho_i - rho_s)
@@ -1081,7 +1097,7 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     K.U0h = fma(-K.c3, ri.w * ri.w, 0.5 * fA);
     K.fV6 = fV * (1.0 / 6.0);
     const d3 g = ring_grad_closed(mv, P, K, row, d, dmax, uniform, i, mk3(ri.x, ri.y, ri.z), ri.w);
-    grad_finish<UPD>(P, i, ri, g, force, grad, U);
+    grad_finish<UPD>(P, i, ri, g, force, grad, U, &fr);
 }
 
 // The vertices of `list` inside [R.first, R.first + R.count): valence > 8 or < 3, and the boundary vertices

@@ -47,7 +47,9 @@ class MeshHMC:
         callback: ``callback(x, counter)`` after every step (default: no-op).
         counter: step counters shared with a flip proposal (default: fresh counters).
         options: see ``trimem.mc.hmc.HMC``.
-        rng: ``numpy.random.RandomState`` of this chain (default: numpy's global state, as in the reference).
+        rng: ``numpy.random.RandomState`` or ``numpy.random.Generator`` of this chain (default: numpy's global state, as
+            in the reference; a ``Generator`` draws the momenta outside the interpreter lock, which is what lets
+            several chains driven from threads of one process overlap their host work).
     """
 
     def __init__(self, mesh, estore, callback=None, counter=None, options={}, verbose=True, rng=None):
