@@ -1011,7 +1011,8 @@ __device__ __forceinline__ void ring_grad_generic(const MeshView& mv, const DevP
 template <int UPD>
 // fpre: the vertex's pair force, already in registers (the closed-fan sweep requests it with the ring records)
 __device__ __forceinline__ void grad_finish(const DevParams& P, int i, const P4& ri, d3 g, const double* __restrict__ force,
-                                            double* __restrict__ grad, const VVFuse& U, const d3* fpre = nullptr) {
+                                            double* __restrict__ grad, const VVFuse& U, const d3* fpre = nullptr,
+                                            const double* upre = nullptr /* momenta [0..2], previous gradient [3..5] */) {
     // repulsion (mesh_properties.cpp:139-146): 2 kappa_r * pair force of k_pairs
     if (force) {
         if (fpre) {
@@ -1033,8 +1034,8 @@ __device__ __forceinline__ void grad_finish(const DevParams& P, int i, const P4&
         double xn[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            const double a = -U.g_prev[3 * (size_t)i + k];
-            const double pk = __dadd_rn(U.mom[3 * (size_t)i + k], __dmul_rn(__dmul_rn(0.5, __dadd_rn(a, an[k])), U.dt));
+            const double a = -(upre ? upre[3 + k] : U.g_prev[3 * (size_t)i + k]);
+            const double pk = __dadd_rn(upre ? upre[k] : U.mom[3 * (size_t)i + k], __dmul_rn(__dmul_rn(0.5, __dadd_rn(a, an[k])), U.dt));
             U.mom[3 * (size_t)i + k] = pk;
             if (UPD > 1) {
                 const double num = __dadd_rn(__dmul_rn(pk, U.dt), __dmul_rn(__dmul_rn(0.5, an[k]), U.dt2));
@@ -1071,15 +1072,16 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     P4 ri;
     ri.x = ri.y = ri.z = ri.w = 0.0;
     d3 fr = mk3(0, 0, 0);
+    double up[6] = {0, 0, 0, 0, 0, 0};        // the fused update's momenta and previous gradient, requested with the row too
     if (live) {
         row = ldrow(mv.ring8, i);
         ri = ldrec(mv.pos, i);
         // the epilogue's operands. The pair force is loaded now (three coalesced doubles: waiting for it behind the
-        // walk was a tenth of a warp's life, profiles/r02x); the update's are requested into L2, no register held.
+        // walk was a tenth of a warp's life, profiles/r02x), and so are the fused update's.
         if (force) { const double* f = force + 3 * (size_t)i; fr = mk3(__ldg(f), __ldg(f + 1), __ldg(f + 2)); }
         if (UPD > 0) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(U.mom + 3 * (size_t)i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(U.g_prev + 3 * (size_t)i));
+#pragma unroll
+            for (int k = 0; k < 3; k++) { up[k] = U.mom[3 * (size_t)i + k]; up[3 + k] = __ldg(U.g_prev + 3 * (size_t)i + k); }
         }
     }
     // (the three sums are requested with the row, not behind it)
@@ -1097,7 +1099,7 @@ k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* 
     K.U0h = fma(-K.c3, ri.w * ri.w, 0.5 * fA);
     K.fV6 = fV * (1.0 / 6.0);
     const d3 g = ring_grad_closed(mv, P, K, row, d, dmax, uniform, i, mk3(ri.x, ri.y, ri.z), ri.w);
-    grad_finish<UPD>(P, i, ri, g, force, grad, U, &fr);
+    grad_finish<UPD>(P, i, ri, g, force, grad, U, &fr, UPD > 0 ? up : nullptr);
 }
 
 // The vertices of `list` inside [R.first, R.first + R.count): valence > 8 or < 3, and the boundary vertices
