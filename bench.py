@@ -251,6 +251,16 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     all_chains(n_moves, 40, lazy=True)
     wall_lazy = time.perf_counter() - t0
     rebuilt = sum(u.rebuilds for u in lazy_upd) / max(1, sum(u.rebuilds + u.skipped for u in lazy_upd))
+    # ... and with the momenta drawn on the device as well (counter-based generator; the host draw is most of a move)
+    for c in chains:
+        c[2].device_momenta = 5000 + c[3]
+    all_chains(5, 60, lazy=True)
+    barrier()
+    t0 = time.perf_counter()
+    all_chains(n_moves, 65, lazy=True)
+    wall_dev = time.perf_counter() - t0
+    for c in chains:
+        c[2].device_momenta = None
     stats[:] = stats_timed
     # one chain alone, for the concurrency gain
     t0 = time.perf_counter()
@@ -261,7 +271,7 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     return {"wall_s": wall, "moves": n_moves, "L": L, "R": R, "V": V, "solo_ms_per_move": 1e3 * solo,
             "hmc_acceptance": float(np.mean([s[0] / max(s[1], 1) for s in stats])),
             "flips_accepted_per_sweep": float(np.mean([s[2] for s in stats])) / max(1, n_moves // 10),
-            "launches": int(launches), "wall_lazy_s": wall_lazy, "lazy_rebuild_fraction": rebuilt}
+            "launches": int(launches), "wall_lazy_s": wall_lazy, "lazy_rebuild_fraction": rebuilt, "wall_device_momenta_s": wall_dev}
 
 
 def hmc_step_run(args, core, workload, rank):
@@ -761,7 +771,10 @@ def main():
                                            "displacement measured on the device behind each trajectory exceeds a quarter of "
                                            "rlist - lc1, or flips were accepted (this rank's wall clock)",
                                    "moves_per_s": world * repl["R"] * repl["moves"] / repl["wall_lazy_s"],
-                                   "rebuilds_per_move": repl["lazy_rebuild_fraction"]}},
+                                   "rebuilds_per_move": repl["lazy_rebuild_fraction"],
+                                   "moves_per_s_with_device_momenta": world * repl["R"] * repl["moves"] / repl["wall_device_momenta_s"],
+                                   "device_momenta": "MeshHMC(device_momenta=seed): momenta of a move drawn on the device "
+                                                     "(Philox4x32-10 + Box-Muller, tm_mesh_random_momenta) instead of by numpy"}},
             "hmc_step_config2": hmc2,
             "partitioned": part,
             "gpu_launches": int(launches),

@@ -33,7 +33,7 @@ typedef struct tm_nlist tm_nlist;  /* device neighbour list (cell / verlet)     
 const char* tm_last_error(void);
 /* 1: energy / gradient / neighbour lists / flips; 2: + trajectories (tm_vv_*), partitioned meshes
  * (tm_part_*), tm_nlist_displacement; 3: + tm_vv_displacement (rebuild trigger measured behind the
- * trajectory), tm_time_kernel composites 4/5. Additions only: a caller of version 1 keeps working.   */
+ * trajectory), tm_mesh_random_momenta, tm_time_kernel composites 4/5. Additions only: a caller of version 1 keeps working.   */
 int  tm_abi_version(void);
 /* number of visible CUDA devices (0 when there is no driver / device)         */
 int  tm_device_count(void);
@@ -196,6 +196,12 @@ int tm_mesh_flip(tm_mesh* m, int edge);
  * mc/evaluators.py:181-182). Momenta are (V,3) in the caller's vertex numbering.   */
 int tm_mesh_set_momenta(tm_mesh* m, const double* p);
 int tm_mesh_get_momenta(tm_mesh* m, double* p);
+/* Extension: momenta <- scale * N(0, 1) drawn ON THE DEVICE (the reference draws them with numpy on the host,
+ * src/trimem/mc/hmc.py:135-137; with the trajectory on the device that draw is two thirds of a move). Philox4x32-10
+ * keyed by `seed`, counter = (vertex id, half, sequence), two 53-bit uniforms -> Box-Muller: the values depend on
+ * (seed, sequence, vertex) only, so a chain is reproducible from its seed and move numbers. Asynchronous.
+ * tm_vv_integrate(..., p0 = NULL, ...) then integrates from the momenta on the device.                         */
+int tm_mesh_random_momenta(tm_mesh* m, unsigned long long seed, unsigned long long sequence, double scale);
 /* x, p <- n_steps velocity-Verlet steps from the mesh's current device positions and
  * momenta, force = -gradient of the functional `params` describes; asynchronous.
  * with_energies != 0 also evaluates U(x0), U(xN) (the full sweeps replace the

@@ -62,6 +62,18 @@ def build(mod, case):
     return mesh, mod.EnergyManager(mesh, ep)
 
 
+GRAD_TILE = 64
+
+
+def tile_sums(a, tile=None):
+    """(ceil(V / tile), 3): vector sums of consecutive row tiles of a (V, 3) array."""
+    tile = tile or GRAD_TILE
+    V = len(a)
+    pad = (-V) % tile
+    b = np.vstack([a, np.zeros((pad, a.shape[1]))]) if pad else a
+    return b.reshape(-1, tile, a.shape[1]).sum(axis=1)
+
+
 def sample_rows(n_vertices, n=None):
     rng = np.random.default_rng(7)
     return np.sort(rng.choice(n_vertices, size=min(n or N_SAMPLED_ROWS, n_vertices), replace=False))

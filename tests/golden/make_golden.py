@@ -61,6 +61,22 @@ def energy_cases():
         save(name, **out)
 
 
+def gradient_tile_sums():
+    """For the cases too large to store the whole gradient: the vector sum of every tile of cases.GRAD_TILE
+    consecutive rows (host numbering) of the reference's gradient, so that EVERY row of the device's gradient is
+    checked against the reference through exactly one tile, not only the sampled rows. Stored beside the case's
+    other fixtures as <case>_gtiles.npz."""
+    for name in cases.CASES:
+        if name.endswith(("_flip", "_flip_cell", "_flip_verlet")):
+            continue
+        mesh, es = cases.build(ref, name)
+        V = mesh.n_vertices()
+        if V <= cases.FULL_GRADIENT_MAX_V:
+            continue
+        grad = es.gradient(mesh)
+        save(name + "_gtiles", tile_sums=cases.tile_sums(grad), tile_abs=cases.tile_sums(np.abs(grad)))
+
+
 def big_case():
     """BASELINE config 4: the 10,485,762-vertex mesh on the reference (six sums, energy, 4,096 sampled gradient rows,
     gradient sum and norm, pair count). Run with OMP_NUM_THREADS=8; ~5 minutes and ~8 GB."""
@@ -412,5 +428,6 @@ if __name__ == "__main__":
     if "hmc" in which: hmc_chain_cases()
     if "open" in which: open_mesh_cases()
     if "restart" in which: restart_case()
+    if "gtiles" in which: gradient_tile_sums()
     if "flipstats" in which: flip_statistics()
     if "big" in which: big_case()

@@ -41,6 +41,12 @@ def test_pybind_path_vs_golden(gpu_core, case):
         rows = gold["rows"]
         assert np.linalg.norm(g[rows] - gold["grad_rows"]) / np.linalg.norm(gold["grad_rows"]) < TOL
         assert np.linalg.norm(g.sum(axis=0) - gold["grad_sum"]) < TOL * float(gold["grad_norm"])
+        # every row, through the vector sums of tiles of 64 consecutive rows of the reference's gradient: a tile's
+        # sum cancels, so the yardstick is the tile's sum of absolute values (what rounding in a 64-term sum scales with)
+        tiles = cases.load_golden(case + "_gtiles")
+        mine = cases.tile_sums(g)
+        assert mine.shape == tiles["tile_sums"].shape
+        assert np.all(np.abs(mine - tiles["tile_sums"]) <= TOL * tiles["tile_abs"])
 
 
 @pytest.mark.parametrize("case", ["ico4_config1", "ico4_stress_cell2", "ico4_stress_verlet2", "ico4_area_stress", "ico3_area"])

@@ -240,3 +240,86 @@ def test_lazy_repulsion_chain_equals_rebuild_every_move(gpu_core):
     # list, so sums agree to rounding, not bitwise
     assert np.abs(h1 - h0).max() <= 1e-11 * np.abs(h0).max()
     assert np.linalg.norm(xs1 - xs0) <= 1e-9 * np.linalg.norm(xs0 - xs0[0] + 1e-300) + 1e-12
+
+
+def philox4x32_10_numpy(c, k):
+    """Philox4x32-10 (Salmon et al., SC'11) on numpy arrays: c (N, 4) uint32 counters, k (2,) uint32 key."""
+    c = c.astype(np.uint64).copy()
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[:, 0], M1 * c[:, 2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c = np.stack([hi1 ^ c[:, 1] ^ k0, lo1, hi0 ^ c[:, 3] ^ k1, lo0], axis=1)
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & MASK, (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c.astype(np.uint32)
+
+
+def test_device_momenta_are_the_documented_generator(gpu_core):
+    """tm_mesh_random_momenta: Philox4x32-10 keyed by the seed, counter (vertex, half, sequence), 53-bit uniforms,
+    Box-Muller -- restated in numpy and compared value for value; then the moments and a Kolmogorov-Smirnov test."""
+    from scipy import stats
+    from trimem_b200 import cabi
+    import halfedge
+    v, f = cases.mesh_of("ico6_stress_verlet2")
+    V = len(v)
+    he_to, he_next, he_face, v_he, _ = halfedge.build(V, f)
+    cm = cabi.Mesh(he_to, he_next, he_face, v_he, xyz=v)
+    # Philox known-answer (Random123 kat_vectors): counter = key = 0 and all ones
+    kat0 = philox4x32_10_numpy(np.zeros((1, 4), np.uint32), np.zeros(2, np.uint32))[0]
+    assert [int(x) for x in kat0] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    kat1 = philox4x32_10_numpy(np.full((1, 4), 0xffffffff, np.uint32), np.full(2, 0xffffffff, np.uint32))[0]
+    assert [int(x) for x in kat1] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    seed, seq, scale = 0x1234567890ABCDEF, 7, 2.5
+    cm.random_momenta(seed, seq, scale)
+    p = cm.momenta()
+    key = np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32)
+    z = np.empty((V, 4))
+    for half in (0, 1):
+        c = np.stack([np.arange(V, dtype=np.uint32), np.full(V, half, np.uint32), np.full(V, seq, np.uint32),
+                      np.zeros(V, np.uint32)], axis=1)
+        w = philox4x32_10_numpy(c, key).astype(np.float64)
+        u = lambda hi, lo: (np.floor(hi / 32.0) * 67108864.0 + np.floor(lo / 64.0) + 0.5) / 9007199254740992.0
+        r = np.sqrt(-2.0 * np.log(u(w[:, 0], w[:, 1])))
+        ang = 2.0 * np.pi * u(w[:, 2], w[:, 3])
+        z[:, 2 * half], z[:, 2 * half + 1] = r * np.cos(ang), r * np.sin(ang)
+    assert np.abs(p - scale * z[:, :3]).max() <= 1e-12 * scale * np.abs(z).max()
+    # reproducible, and a different stream for another sequence number / seed
+    cm.random_momenta(seed, seq, scale)
+    assert np.array_equal(cm.momenta(), p)
+    cm.random_momenta(seed, seq + 1, scale)
+    q = cm.momenta()
+    assert abs(np.corrcoef(p.ravel(), q.ravel())[0, 1]) < 5.0 / np.sqrt(p.size)
+    n = p.size
+    s = p.ravel() / scale
+    assert abs(s.mean()) < 5.0 / np.sqrt(n) and abs(s.var() - 1.0) < 5.0 * np.sqrt(2.0 / n)
+    assert abs((s ** 4).mean() - 3.0) < 5.0 * np.sqrt(96.0 / n)
+    assert stats.kstest(s, "norm").pvalue > 1e-3
+
+
+def test_hmc_with_device_momenta(gpu_core):
+    """MeshHMC(device_momenta=seed): reproducible from the seed, K(p0) consistent with the drawn momenta, and the same
+    acceptance behaviour as the chain whose momenta numpy draws on the host."""
+    from trimem_b200 import hmc
+    m = gpu_core
+    opts = {"time_step": 1.0e-5, "num_integration_steps": 8, "initial_temperature": 50.0, "info_step": 0}
+    def run(**kw):
+        mesh, es = cases.build(m, "ico4_stress_verlet2")
+        chain = hmc.MeshHMC(mesh, es, options=dict(opts), verbose=False, **kw)
+        hams, acc = [], 0
+        for _ in range(12):
+            chain.step()
+            hams.append(np.array(chain.last[2]))
+            acc += chain.last[1]
+        return chain.x.copy(), np.array(hams), acc
+    x1, h1, a1 = run(device_momenta=11, rng=np.random.RandomState(3))
+    x2, h2, a2 = run(device_momenta=11, rng=np.random.RandomState(3))
+    assert np.array_equal(x1, x2) and np.array_equal(h1, h2)                       # same seed, same chain
+    x3, h3, a3 = run(device_momenta=12, rng=np.random.RandomState(3))
+    assert not np.array_equal(x1, x3)
+    xh, hh, ah = run(rng=np.random.RandomState(3))
+    # kinetic energy of the draw: 3V/2 * T on average (equipartition), both ways of drawing
+    V = len(x1)
+    for h in (h1, h3, hh):
+        assert abs(h[:, 1].mean() / (1.5 * V * 50.0) - 1.0) < 0.05
+    assert abs(a1 - ah) <= 4 and abs(a3 - ah) <= 4

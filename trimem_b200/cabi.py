@@ -100,6 +100,7 @@ def lib():
     L.tm_vv_integrate_async.argtypes = [vp, vp, pp, C.c_double, C.c_double, C.c_int, C.c_int]
     L.tm_vv_stats.argtypes = [vp, pp, _dp, _dp, _dp]
     L.tm_vv_displacement.argtypes = [vp, vp, C.c_double, _dp, _dp]
+    L.tm_mesh_random_momenta.argtypes = [vp, C.c_ulonglong, C.c_ulonglong, C.c_double]
     L.tm_vv_integrate.argtypes = [vp, vp, pp, _dp, C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
     L.tm_part_create.argtypes = [vp, C.c_int, C.c_int]
     L.tm_part_info.argtypes = [vp, _ip, _ip, _ip, _ip, _ip, _ip]
@@ -272,6 +273,9 @@ class Mesh:
         p = np.ascontiguousarray(p, dtype=np.float64)
         assert p.shape == (self.V, 3)
         _chk(lib().tm_mesh_set_momenta(self.h, _d(p)))
+
+    def random_momenta(self, seed, sequence, scale=1.0):
+        _chk(lib().tm_mesh_random_momenta(self.h, seed, sequence, scale))
 
     def momenta(self):
         p = np.zeros((self.V, 3))

@@ -435,6 +435,23 @@ PYBIND11_MODULE(core, m) {
           "Finite difference gradient of energy.");
 
     // ---- device-resident trajectory (extension; replaces the Python loop of mc/hmc.py:14-26) -----------
+    m.def("vv_integrate_random",
+          [](HalfedgeMesh& mesh, EnergyManager& estore, unsigned long long seed, unsigned long long sequence, double scale,
+             double mass, double dt, int n_steps) {
+              const int n = mesh.n_vertices();
+              py::array_t<double> x = pinned_array(n, 3);
+              py::array_t<double> st(4);
+              double *xo = x.mutable_data(), *so = st.mutable_data();
+              {
+                  py::gil_scoped_release nogil;
+                  vv_integrate_random(mesh, estore, seed, sequence, scale, mass, dt, n_steps, xo, so);
+              }
+              return py::make_tuple(x, st);
+          },
+          py::arg("mesh"), py::arg("estore"), py::arg("seed"), py::arg("sequence"), py::arg("scale"), py::arg("mass"),
+          py::arg("time_step"), py::arg("n_steps"),
+          "Extension: vv_integrate with the momenta drawn on the device, scale * N(0, 1) per component from the counter-based\n"
+          "generator keyed by (seed, sequence, vertex). Returns (x_new, [U(x0), K(p0), U(xN), K(pN)]).");
     m.def("vv_displacement",
           [](HalfedgeMesh& mesh, EnergyManager& estore) { return vv_displacement(mesh, estore); },
           py::arg("mesh"), py::arg("estore"),

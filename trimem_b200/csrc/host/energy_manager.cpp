@@ -252,6 +252,14 @@ void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, d
         fail();
 }
 
+void vv_integrate_random(HalfedgeMesh& mesh, EnergyManager& estore, unsigned long long seed, unsigned long long sequence,
+                         double scale, double mass, double dt, int n_steps, double* x_out, double* stats) {
+    tm_energy_params p = estore.abi_params();
+    tm_mesh* dm = mesh.device();
+    if (tm_mesh_random_momenta(dm, seed, sequence, scale)) fail();
+    if (tm_vv_integrate(dm, estore.nlist_handle(), &p, nullptr, mass, dt, n_steps, x_out, nullptr, stats)) fail();
+}
+
 std::tuple<double, double> vv_displacement(HalfedgeMesh& mesh, EnergyManager& estore) {
     double disp = 0, margin = 0;
     if (tm_vv_displacement(mesh.device(), estore.nlist_handle(), estore.params.repulse_params.lc1, &disp, &margin)) fail();

@@ -119,6 +119,10 @@ int flip_with(HalfedgeMesh& mesh, EnergyManager& estore, const std::vector<int>&
 void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, double mass, double dt,
                   int n_steps, double* x_out, double* p_out, double* stats);
 
+// extension: the same with the momenta drawn on the device, scale * N(0, 1) from (seed, sequence) (tm_mesh_random_momenta);
+// the end point's momenta stay on the device (the Metropolis test needs their kinetic energy only: stats[3])
+void vv_integrate_random(HalfedgeMesh& mesh, EnergyManager& estore, unsigned long long seed, unsigned long long sequence,
+                         double scale, double mass, double dt, int n_steps, double* x_out, double* stats);
 // extension (rebuild trigger): (largest vertex displacement of the last trajectory's end point from the
 // positions the verlet list was built from, margin = rlist - lc1), measured on the device behind the trajectory
 std::tuple<double, double> vv_displacement(HalfedgeMesh& mesh, EnergyManager& estore);

@@ -443,6 +443,12 @@ int tm_mesh_set_momenta(tm_mesh* m, const double* p) {
     return 0;
 }
 
+int tm_mesh_random_momenta(tm_mesh* m, unsigned long long seed, unsigned long long sequence, double scale) {
+    if (check_mesh(m)) return 1;
+    TM_CHECK(!m->part, "device-drawn momenta are not available on a partitioned mesh");
+    return tm_random_momenta(m, seed, sequence, scale);
+}
+
 int tm_mesh_get_momenta(tm_mesh* m, double* p) {
     if (check_mesh(m)) return 1;
     TM_CHECK(p != nullptr, "null momenta");
@@ -482,10 +488,11 @@ int tm_vv_stats(tm_mesh* m, const tm_energy_params* p, double stats[4], double p
 int tm_vv_integrate(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, const double* p0, double mass, double dt,
                     int n_steps, double* x_out, double* p_out, double stats[4]) {
     if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
-    TM_CHECK(p0 != nullptr, "null momenta");
     TM_CHECK(n_steps >= 0, "negative number of integration steps");
     TM_CHECK(mass > 0.0, "mass must be positive");
-    if (tm_import_momenta(m, p0)) return 1;
+    // p0 == NULL: the momenta already on the device (tm_mesh_set_momenta / tm_mesh_random_momenta)
+    TM_CHECK(p0 != nullptr || m->mom != nullptr, "null momenta and none on the device");
+    if (p0 && tm_import_momenta(m, p0)) return 1;
     if (tm_vv_run(m, view_of(nl), *p, mass, dt, n_steps, stats != nullptr)) return 1;
     // the rebuild trigger: displacement of the end point from the list's build positions (d_stats[14], squared)
     m->vv_disp_list = 0;

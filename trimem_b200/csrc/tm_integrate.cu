@@ -329,6 +329,53 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
     return 0;
 }
 
+// ---- momenta drawn on the device (extension) ---------------------------------------------------
+// The reference draws an HMC move's momenta with numpy on the host (src/trimem/mc/hmc.py:135-137); at 40,962
+// vertices that draw is two thirds of a move once the trajectory runs on the device (scripts/hmc_breakdown.py).
+// Counter-based generator, so a chain is reproducible from (seed, move number) whatever the launch shape:
+// Philox4x32-10 (Salmon et al., SC'11; constants as published) keyed by the seed, counter = (vertex id in HOST
+// numbering, half, sequence lo, sequence hi); the four words of a block make two 53-bit uniforms in (0, 1) and
+// Box-Muller turns them into two standard normals; a vertex takes three of its two blocks' four.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {          // (0, 1), 53 bits
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+__global__ void k_random_momenta(int V, const int* __restrict__ d2h, unsigned long long seed, unsigned long long seq,
+                                 double scale, double* __restrict__ mom) {
+    const int d = blockIdx.x * NT + threadIdx.x;
+    if (d >= V) return;
+    const unsigned v = (unsigned)d2h[d];               // host numbering: the draw does not depend on the device order
+    double z[4];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        unsigned w[4];
+        philox4x32_10(v, (unsigned)half, (unsigned)seq, (unsigned)(seq >> 32), (unsigned)seed, (unsigned)(seed >> 32), w);
+        const double r = sqrt(-2.0 * log(u53(w[0], w[1])));
+        double sn, cs;
+        sincospi(2.0 * u53(w[2], w[3]), &sn, &cs);
+        z[2 * half] = r * cs; z[2 * half + 1] = r * sn;
+    }
+    mom[3 * (size_t)d] = scale * z[0]; mom[3 * (size_t)d + 1] = scale * z[1]; mom[3 * (size_t)d + 2] = scale * z[2];
+}
+
+int tm_random_momenta(tm_mesh* m, unsigned long long seed, unsigned long long seq, double scale) {
+    if (ensure_state(m)) return 1;
+    k_random_momenta<<<(m->V + NT - 1) / NT, NT, 0, m->stream>>>(m->V, m->d2h, seed, seq, scale, m->mom); TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int tm_import_momenta(tm_mesh* m, const double* p_host) {
     if (ensure_state(m)) return 1;
     // through the host-numbered staging block, on the mesh's stream (positions staged there have

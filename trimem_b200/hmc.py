@@ -47,12 +47,14 @@ class MeshHMC:
         callback: ``callback(x, counter)`` after every step (default: no-op).
         counter: step counters shared with a flip proposal (default: fresh counters).
         options: see ``trimem.mc.hmc.HMC``.
+        device_momenta: ``None`` (default: momenta from ``rng``, like the reference) or an integer seed: momenta drawn on the
+            device (extension, see below).
         rng: ``numpy.random.RandomState`` or ``numpy.random.Generator`` of this chain (default: numpy's global state, as
             in the reference; a ``Generator`` draws the momenta outside the interpreter lock, which is what lets
             several chains driven from threads of one process overlap their host work).
     """
 
-    def __init__(self, mesh, estore, callback=None, counter=None, options={}, verbose=True, rng=None):
+    def __init__(self, mesh, estore, callback=None, counter=None, options={}, verbose=True, rng=None, device_momenta=None):
         self.trimesh = getattr(mesh, "trimesh", mesh)
         self.mesh = mesh
         self.estore = estore
@@ -86,6 +88,11 @@ class MeshHMC:
         # source of the momenta and the Metropolis variate: numpy's global state like the reference, or the chain's
         # own numpy.random.RandomState (independent chains driven from several threads, ranks of a partitioned mesh)
         self.rng = np.random if rng is None else rng
+        # extension: an integer seed -> the momenta of move k are drawn ON THE DEVICE from (seed, k) (counter-based
+        # generator, core.vv_integrate_random) instead of by numpy on the host, where the draw is two thirds of a move at
+        # 40,962 vertices. Such a chain is reproducible from its seed but is not the reference's chain for any numpy seed.
+        self.device_momenta = device_momenta
+        self.n_draws = 0
 
     def _set_mesh(self, x):
         np.copyto(self.trimesh.points(), x)
@@ -93,9 +100,14 @@ class MeshHMC:
     def _step(self):
         """Metropolis step (hmc.py:133-155)."""
         p_var = self.m * self.T
-        p = self.rng.normal(size=self.x.shape) * np.sqrt(p_var)
         self._set_mesh(self.x)
-        xn, pn, st = m.vv_integrate(self.trimesh, self.estore, p, self.m, self.dt, self.L)
+        if self.device_momenta is None:
+            p = self.rng.normal(size=self.x.shape) * np.sqrt(p_var)
+            xn, pn, st = m.vv_integrate(self.trimesh, self.estore, p, self.m, self.dt, self.L)
+        else:
+            xn, st = m.vv_integrate_random(self.trimesh, self.estore, int(self.device_momenta), self.n_draws,
+                                           float(np.sqrt(p_var)), self.m, self.dt, self.L)
+            self.n_draws += 1
         # (nlog_prob(xn) + K(pn)) - (nlog_prob(x) + K(p)), in the reference's order of operations
         dh = ((st[2] + st[3]) - (st[0] + st[1])) / self.T
         a = 1.0 if dh <= 0 else np.exp(-dh)
