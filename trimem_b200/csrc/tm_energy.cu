@@ -485,6 +485,7 @@ constexpr int PB = TM_PAIR_BATCH;
 #ifndef TM_PAIR_INTERLEAVE
 #define TM_PAIR_INTERLEAVE 0
 #endif
+
 #ifndef TM_PAIR_CELL_MINB
 #define TM_PAIR_CELL_MINB 3
 #endif
