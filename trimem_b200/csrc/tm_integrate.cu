@@ -279,7 +279,8 @@ int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double ma
         slot = &C->g[0];
         for (auto& g : C->g) if (g.stamp < slot->stamp) slot = &g;
         if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-        slot->key = key; slot->uses = 1; slot->stamp = ++C->clock;
+        memcpy(&slot->key, &key, sizeof(VVKey));          // (bytewise: same_key compares the padding too)
+        slot->uses = 1; slot->stamp = ++C->clock;
         return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
     }
     slot->stamp = ++C->clock;
