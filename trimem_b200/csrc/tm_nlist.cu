@@ -55,6 +55,7 @@ __global__ void k_cell_fill(int V, const int* __restrict__ cell_of, const int* _
     int i = blockIdx.x * NT + threadIdx.x;
     if (i >= V) return;
     int c = cell_of[i];
+    if (c < 0) return;                              // outside a clipped grid
     int slot = atomicAdd(cursor + c, 1);
     items[cell_start[c] + slot] = i;
 }
@@ -102,6 +103,9 @@ __device__ __forceinline__ void for_each_cell_pair(const MeshView& mv, const NlV
 struct VGrid {
     double lo[3], inv[3];
     int n[3];
+    // clip: only the vertices inside [lo, hi] are binned (a partitioned mesh bins what its owned rows can reach)
+    double hi[3];
+    int clip;
 };
 __device__ __forceinline__ void vcell(const VGrid& g, d3 p, int c[3]) {
     c[0] = min(g.n[0] - 1, max(0, (int)((p.x - g.lo[0]) * g.inv[0])));
@@ -113,16 +117,22 @@ __global__ void k_vcell_count(VGrid g, const P4* __restrict__ pos, int V, int* _
     int i = blockIdx.x * NT + threadIdx.x;
     if (i >= V) return;
     int c[3];
-    vcell(g, ldpos(pos, i), c);
+    const d3 p = ldpos(pos, i);
+    if (g.clip && (p.x < g.lo[0] || p.x > g.hi[0] || p.y < g.lo[1] || p.y > g.hi[1] || p.z < g.lo[2] || p.z > g.hi[2])) {
+        cell_of[i] = -1;
+        return;
+    }
+    vcell(g, p, c);
     const int id = (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
     cell_of[i] = id;
     atomicAdd(count + id, 1);
 }
 
 // cell-ordered copy of the positions for the search: rec[k] = (x, y, z of items[k], id)
-__global__ void k_vgather(int V, const int* __restrict__ items, const P4* __restrict__ pos, P4* __restrict__ rec) {
+__global__ void k_vgather(int V, const int* __restrict__ n_items, const int* __restrict__ items, const P4* __restrict__ pos,
+                          P4* __restrict__ rec) {
     const int k = blockIdx.x * NT + threadIdx.x;
-    if (k >= V) return;
+    if (k >= V || k >= *n_items) return;           // (n_items: the binned vertices, = V unless the grid is clipped)
     const int j = items[k];
     const d3 p = ldpos(pos, j);
     P4 r;
@@ -432,13 +442,30 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
     if (nl->excl == 2 && tm_ensure_ring2(m)) return 1;
     double hb[6];
     if (tm_bbox(m, reinterpret_cast<const double*>(m->pos), 4, V, hb)) return 1;
+    // The search grid. A partitioned mesh builds the rows of the vertices it owns, so its grid covers their bounding
+    // box widened by rlist -- everything a row can list lies inside -- and the rest of the mesh is not binned: at
+    // 10,485,762 vertices on 8 ranks that is an eighth of the 134 M cells to scan and a quarter of the vertices to
+    // sort and gather, which is what kept the rebuild from scaling (round 1: 9.5 ms on one GPU, 2.8 ms on eight).
+    const SweepRange Rg = tm_owned_range(m);
+    double gb[6] = {hb[0], hb[1], hb[2], hb[3], hb[4], hb[5]};
+    const bool clip = Rg.count > 0 && Rg.count < V;
+    if (clip) {
+        double ob[6];
+        if (tm_bbox(m, reinterpret_cast<const double*>(m->pos + Rg.first), 4, Rg.count, ob)) return 1;
+        for (int k = 0; k < 3; k++) {
+            gb[k] = ob[k] - nl->rlist > hb[k] ? ob[k] - nl->rlist : hb[k];
+            gb[3 + k] = ob[3 + k] + nl->rlist < hb[3 + k] ? ob[3 + k] + nl->rlist : hb[3 + k];
+        }
+    }
     VGrid g;
+    g.clip = clip ? 1 : 0;
     long long ncell = 1;
     for (int k = 0; k < 3; k++) {
-        const double dim = hb[3 + k] - hb[k];
+        const double dim = gb[3 + k] - gb[k];
         int nk = (int)(dim / nl->rlist);
         if (nk < 1) nk = 1;
-        g.lo[k] = hb[k];
+        g.lo[k] = gb[k];
+        g.hi[k] = gb[3 + k];
         g.n[k] = nk;
         g.inv[k] = dim > 0.0 ? nk / dim : 0.0;      // cell edge dim/nk >= rlist
         ncell *= nk;
@@ -477,7 +504,7 @@ int build_verlet(tm_mesh* m, tm_nlist* nl) {
     while (std::sqrt(std::nextafter(s2max, HUGE_VAL)) <= nl->rlist) s2max = std::nextafter(s2max, HUGE_VAL);
     PoolBuf<P4> rec(dev);
     TM_CHECK(!rec.alloc(V), "out of device memory for the search records");
-    k_vgather<<<vb, NT, 0, m->stream>>>(V, items.p, m->pos, rec.p); TM_LAUNCHED();
+    k_vgather<<<vb, NT, 0, m->stream>>>(V, start.p + ncell, items.p, m->pos, rec.p); TM_LAUNCHED();
 
     nl->row_cnt = (int*)tm_pool_alloc(dev, sizeof(int) * (size_t)V);
     TM_CHECK(nl->row_cnt, "out of device memory for verlet rows");
