@@ -44,7 +44,7 @@ struct FlipWS {
     int *edges = nullptr, *owner = nullptr, *rem_a = nullptr, *rem_b = nullptr, *sel = nullptr;
     int *flips = nullptr, *counters = nullptr;   // counters: [0] n_rem_next [1] n_flips [2] n_acc [3] err
     int *selidx = nullptr;                       // proposals selected and flippable this round (counters[5] of them)
-    int *patch = nullptr;                        // [PATCH_CAP + 1][cap]: the patch edges k_batch_mark visited, for k_batch_select
+    int *patch = nullptr;                        // [PATCH_ROWS][cap]: the patch edges k_batch_mark visited, for k_batch_select
     double *u = nullptr, *before = nullptr, *after = nullptr, *state = nullptr;   // state: props[6], e0
 };
 
@@ -317,21 +317,37 @@ __device__ __forceinline__ void for_each_patch_edge(const Topo& t, int e, F f) {
     }
 }
 
-// The edges visited are kept (slot-major, so the stores of a warp coalesce) for k_batch_select, which then reads a
-// list instead of repeating the walk's chain of dependent loads; a patch of more than PATCH_CAP visits is walked again.
-constexpr int PATCH_CAP = 64;
+// Four threads per remaining proposal, one per patch vertex (the four ring walks are chains of dependent half-edge
+// loads: side by side they take a quarter of the time). The edges visited are kept -- rows 0..3 of `patch` hold the
+// four vertices' visit counts, rows 4 + 16 q + n the edges, slot-major so that a warp's stores coalesce -- for
+// k_batch_select, which then reads a list instead of repeating the walks; a vertex with more than PATCH_Q visits
+// (valence > 8) is walked again there.
+constexpr int PATCH_Q = 16;
+constexpr int PATCH_ROWS = 4 + 4 * PATCH_Q;
 __global__ void k_batch_mark(Topo t, int nrem, const int* __restrict__ rem, const int* __restrict__ edges,
                              int* __restrict__ owner, int* __restrict__ patch, int cap) {
-    const int r = blockIdx.x * NT + threadIdx.x;
+    const int gid = blockIdx.x * NT + threadIdx.x;
+    const int r = gid >> 2, q = gid & 3;
     if (r >= nrem) return;
     const int p = rem[r];
+    const int v = patch_vertex(t, edges[p], q);
     int n = 0;
-    for_each_patch_edge(t, edges[p], [&](int ed) {
-        atomicMin(owner + ed, p);
-        if (n < PATCH_CAP) patch[(size_t)(n + 1) * cap + r] = ed;
-        ++n;
-    });
-    patch[r] = n;
+    const int h0 = vld(t.v_he + v);
+    if (h0 >= 0) {
+        int h = h0, guard = 0;
+        do {
+            const int e1 = h >> 1, e2 = vld(t.he_next + h) >> 1;
+            atomicMin(owner + e1, p);
+            atomicMin(owner + e2, p);
+            if (n + 1 < PATCH_Q) {
+                patch[(size_t)(4 + PATCH_Q * q + n) * cap + r] = e1;
+                patch[(size_t)(4 + PATCH_Q * q + n + 1) * cap + r] = e2;
+            }
+            n += 2;
+            h = vld(t.he_next + (h ^ 1));
+        } while (h != h0 && ++guard < 4096);
+    }
+    patch[(size_t)q * cap + r] = n;
 }
 
 // sel[p]: 0 = not selected this round, 1 = selected and flippable, 2 = selected, not flippable
@@ -342,11 +358,14 @@ __global__ void k_batch_select(Topo t, int nrem, const int* __restrict__ rem, co
     if (r >= nrem) return;
     const int p = rem[r];
     const int e = edges[p];
-    bool mine = true;
-    const int n = patch[r];
-    if (n <= PATCH_CAP) {
-        for (int k = 0; k < n; k++) mine &= (owner[patch[(size_t)(k + 1) * cap + r]] == p);
-    } else {
+    bool mine = true, listed = true;
+    for (int q = 0; q < 4; q++) {
+        const int n = patch[(size_t)q * cap + r];
+        if (n > PATCH_Q) { listed = false; break; }
+        for (int k = 0; k < n; k++) mine &= (owner[patch[(size_t)(4 + PATCH_Q * q + k) * cap + r]] == p);
+    }
+    if (!listed) {
+        mine = true;
         for_each_patch_edge(t, e, [&](int ed) { if (owner[ed] != p) mine = false; });
     }
     const int sv = !mine ? 0 : (d_is_flip_ok(t, e) ? 1 : 2);
@@ -555,7 +574,7 @@ int ensure_ws(tm_mesh* m, int n) {
         TM_CUDA(cudaMalloc(&ws->u, sizeof(double) * c));
         TM_CUDA(cudaMalloc(&ws->before, sizeof(double) * 6 * c));
         TM_CUDA(cudaMalloc(&ws->after, sizeof(double) * 6 * c));
-        TM_CUDA(cudaMalloc(&ws->patch, sizeof(int) * (PATCH_CAP + 1) * c));
+        TM_CUDA(cudaMalloc(&ws->patch, sizeof(int) * PATCH_ROWS * c));
         TM_CUDA(cudaMalloc(&ws->selidx, sizeof(int) * c));
         ws->cap = n;
     }
@@ -636,7 +655,7 @@ static int flip_sweep_body(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, 
         while (nrem > 0) {
             const int nb = (nrem + NT - 1) / NT;
             TM_CUDA(cudaMemsetAsync(ws->owner, 0x7f, sizeof(int) * (size_t)ws->E, st));
-            k_batch_mark<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->patch, ws->cap); TM_LAUNCHED();
+            k_batch_mark<<<(4 * nrem + NT - 1) / NT, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->patch, ws->cap); TM_LAUNCHED();
             TM_CUDA(cudaMemsetAsync(ws->counters + 5, 0, sizeof(int), st));
             k_batch_select<<<nb, NT, 0, st>>>(t, nrem, rem, ws->edges, ws->owner, ws->sel, ws->patch, ws->cap,
                                              ws->counters + 5, ws->selidx); TM_LAUNCHED();
