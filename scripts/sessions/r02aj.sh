@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, GPU session AJ: grid of the property reduction
+mkdir -p gpurun_out
+: > gpurun_out/r02aj_kernels.jsonl
+timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02aj_kernels.jsonl 2>gpurun_out/r02aj_kb.err
+for v in red1 red2; do
+  TRIMEM_B200_LIB=trimem_b200/lib/variants/$v.so timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02aj_kernels.jsonl 2>>gpurun_out/r02aj_kb.err
+done
+cat gpurun_out/r02aj_kernels.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['lib'][-12:], {k: d[k] for k in d if k.endswith('_us') and 'warm' not in k}, d['E'], d['gnorm'])
+"

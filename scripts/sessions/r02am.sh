@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU session AM: pair sweep and ring gradient finishing each other's tiles (DEC): tests + timings with / without
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_pair_dec.py -m gpu -q -x > gpurun_out/r02am_tests.log 2>&1; echo "dec tests rc=$?" >> gpurun_out/r02am_tests.log
+tail -25 gpurun_out/r02am_tests.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r02am_tests_all.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02am_tests_all.log
+tail -8 gpurun_out/r02am_tests_all.log
+: > gpurun_out/r02am_kernels.jsonl
+timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02am_kernels.jsonl 2>gpurun_out/r02am_kb.err
+TM_STREAM_PRIO=0 timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02am_kernels.jsonl 2>>gpurun_out/r02am_kb.err
+TM_PAIR_DEC=0 timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02am_kernels.jsonl 2>>gpurun_out/r02am_kb.err
+TM_PAIR_DEC=0 TM_STREAM_PRIO=0 timeout 300 python scripts/kernel_bench.py 8 stress verlet-list >> gpurun_out/r02am_kernels.jsonl 2>>gpurun_out/r02am_kb.err
+cat gpurun_out/r02am_kernels.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print({k: d[k] for k in d if k.endswith('_us') and 'warm' not in k}, d['E'], d['gnorm'])
+"
+tail -3 gpurun_out/r02am_kb.err
