@@ -99,11 +99,11 @@ double energy_from_props(const tm_energy_params& p, const double s[6]) { return 
 
 // every compute entry: device selected, vertex order / device connectivity / staged positions
 // / one-ring table brought up to date (tm_layout.cu)
-int check_mesh(tm_mesh* m, bool need_layout = true) {
+int check_mesh(tm_mesh* m, bool need_layout = true, bool join = true) {
     TM_CHECK(m != nullptr, "null mesh handle");
     TM_CHECK(m->V > 0 && m->he_to_h != nullptr, "mesh has no topology (call tm_mesh_set_topology first)");
     TM_CUDA(cudaSetDevice(m->device));
-    if (tm_join_pairs(m)) return 1;
+    if (join && tm_join_pairs(m)) return 1;
     if (need_layout && tm_ensure_layout(m)) return 1;
     return 0;
 }
@@ -117,7 +117,7 @@ int check_params(const tm_energy_params* p) {
 NlView view_of(tm_nlist* nl) { return nl ? nl->view() : tm_no_nlist(); }
 
 int fetch_sums(tm_mesh* m, double out[6]) {
-    if (tm_part_quiesce(m)) return 1;
+    if (tm_join_pairs(m) || tm_part_quiesce(m)) return 1;      // (a split pair sweep stores sums[5] itself)
     TM_CUDA(cudaMemcpyAsync(m->h_sums, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
     TM_CUDA(cudaStreamSynchronize(m->stream));
     for (int q = 0; q < 6; q++) out[q] = m->h_sums[q];
@@ -173,10 +173,21 @@ int tm_mesh_create(int device, tm_mesh** out) {
     tm_mesh* m = new tm_mesh();
     m->device = device;
     TM_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
-    TM_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    {
+        // the main stream carries the dependent chain of an evaluation (property sweep -> reduction -> ...), the side
+        // streams the pair sweep and what follows it, which have slack: blocks of the chain are placed first
+        int lo = 0, hi = 0;
+        TM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        TM_CUDA(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, hi));
+        TM_CUDA(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, lo));
+        for (int k = 0; k < TM_PAIR_STREAMS; k++) {
+            TM_CUDA(cudaStreamCreateWithPriority(&m->sp_stream[k], cudaStreamNonBlocking, lo));
+            TM_CUDA(cudaEventCreateWithFlags(&m->sp_ev[k], cudaEventDisableTiming));
+        }
+        TM_CUDA(cudaEventCreateWithFlags(&m->ev_sums, cudaEventDisableTiming));
+    }
     TM_CUDA(cudaEventCreate(&m->ev0));
     TM_CUDA(cudaEventCreate(&m->ev1));
-    TM_CUDA(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
     TM_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     TM_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
     TM_CUDA(cudaEventCreateWithFlags(&m->ev_pre_upload, cudaEventDisableTiming));
@@ -194,6 +205,7 @@ int tm_mesh_destroy(tm_mesh* m) {
     if (!m) return 0;
     cudaSetDevice(m->device);
     cudaStreamSynchronize(m->stream2);
+    for (int k = 0; k < TM_PAIR_STREAMS; k++) cudaStreamSynchronize(m->sp_stream[k]);
     cudaStreamSynchronize(m->stream);
     tm_flips_release(m);
     cudaFree(m->he_to); cudaFree(m->he_next); cudaFree(m->he_face); cudaFree(m->v_he);
@@ -211,6 +223,8 @@ int tm_mesh_destroy(tm_mesh* m) {
     cudaEventDestroy(m->ev0); cudaEventDestroy(m->ev1);
     cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); cudaEventDestroy(m->ev_pre_upload);
     cudaStreamDestroy(m->stream2);
+    for (int k = 0; k < TM_PAIR_STREAMS; k++) { cudaStreamDestroy(m->sp_stream[k]); cudaEventDestroy(m->sp_ev[k]); }
+    cudaEventDestroy(m->ev_sums);
     cudaStreamDestroy(m->stream);
     delete m;
     return 0;
@@ -333,7 +347,10 @@ int tm_energy_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
 }
 
 int tm_gradient_async(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p) {
-    if (check_mesh(m) || check_params(p) || tm_check_nlist(m, nl)) return 1;
+    // (a pair sweep tm_energy_async left running on the side streams stays there when nothing is about to touch the
+    // positions: the ring gradient of each range follows it on the range's stream, tm_launch_grad)
+    const bool settled = m && !m->stage_pending && m->perm_valid && m->topo_dev_valid && m->rings_valid;
+    if (check_mesh(m, true, !settled) || check_params(p) || tm_check_nlist(m, nl)) return 1;
     // Sweep 1: area, volume, curvature sums and rho = c/a per vertex (all the gradient needs from
     // the properties; no tether, no repulsion). They depend on positions and connectivity only,
     // so a property sweep already evaluated for the current positions (energy() immediately
@@ -553,7 +570,7 @@ int tm_time_kernel(tm_mesh* m, tm_nlist* nl, const tm_energy_params* p, int whic
                : which == 3 ? tm_launch_pairs(m, view_of(nl), *p)
                : which == 4 ? (tm_launch_props(m, view_of(nl), *p, true, false) || tm_launch_grad(m, view_of(nl), *p))
                             : (tm_launch_props(m, view_of(nl), *p, false, false) || tm_launch_grad(m, view_of(nl), *p));
-        if (rc) return 1;
+        if (rc || tm_join_pairs(m)) return 1;
         TM_CUDA(cudaEventRecord(m->ev1, m->stream));
         TM_CUDA(cudaEventSynchronize(m->ev1));
         float ms = 0.f;

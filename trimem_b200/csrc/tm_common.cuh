@@ -63,6 +63,7 @@ constexpr int TM_RING_GENERIC = TM_RING_MASK - 1;
 #endif
 constexpr int TM_PROPS_THREADS = TM_PROPS_NT;
 constexpr int TM_GRAD_THREADS  = TM_GRAD_NT;
+constexpr int TM_PAIR_STREAMS = 4;             // side streams a pair sweep can be cut across
 constexpr int TM_REDUCE_BLOCKS = 128;           // second-stage blocks of the property reduction (upper bound)
 
 // ------------------------------------------------------------ device views --
@@ -139,6 +140,13 @@ struct tm_mesh {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool pairs_inflight = false;
+    // the pair sweep cut into ranges of tiles, one side stream each; the ring gradient of a range follows that range's
+    // pair sweep on its stream (launch_pairs / launch_grad_kernels in tm_energy.cu)
+    cudaStream_t sp_stream[TM_PAIR_STREAMS] = {};
+    cudaEvent_t sp_ev[TM_PAIR_STREAMS] = {};    // end of range k's last kernel
+    cudaEvent_t ev_sums = nullptr;              // the reduced sums of the property sweep are in place (main stream)
+    int split = 0;                              // ranges of the pair sweep in flight (0: one sweep on stream2)
+    int rep_cols = 0;                           // > 0: columns of warp partials whose repulsion column awaits its reduction
     unsigned long long vv_disp_list = 0;   // serial of the list the last trajectory measured its end point's displacement against
     cudaEvent_t ev_pre_upload = nullptr;   // recorded on `stream` just before a position upload is enqueued
     int V = 0, HE = 0;

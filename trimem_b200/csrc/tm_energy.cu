@@ -494,11 +494,11 @@ constexpr int PB = TM_PAIR_BATCH;
 template <bool WITH_E, bool WITH_F, bool WRITE_VPROPS, bool R2, bool CELL>
 __global__ void __launch_bounds__(PAIR_THREADS, CELL ? TM_PAIR_CELL_MINB : TM_PAIR_MINB)
 k_pairs(MeshView mv, NlView nl, double lc1, int rr, double* __restrict__ force, double* __restrict__ vprops,
-        double* __restrict__ partials, int nwarps, SweepRange R) {
+        double* __restrict__ partials, int nwarps, SweepRange R, int blk0) {
     __shared__ double s_exp2[64];
     if (threadIdx.x < 64) s_exp2[threadIdx.x] = tm_math::EXP2_64[threadIdx.x];
     __syncthreads();
-    const int t = blockIdx.x * PAIR_THREADS + threadIdx.x;
+    const int t = (blockIdx.x + blk0) * PAIR_THREADS + threadIdx.x;
     const int i = R.first + t;
     double rep = 0.0;
     if (t < R.count) {
@@ -704,8 +704,9 @@ __device__ __forceinline__ void block_sum6(double (&v)[6], double* out /* 6, val
 }
 
 __global__ void __launch_bounds__(RT)
-k_reduce_props(const double* __restrict__ partials, int nwarps, int per, int nq, double* __restrict__ block_sums,
-               unsigned* __restrict__ ticket, double* __restrict__ sums) {
+k_reduce_props(const double* __restrict__ partials, int nwarps, int per, int qlo, int qhi, int slo, int shi,
+               double* __restrict__ block_sums, unsigned* __restrict__ ticket, double* __restrict__ sums) {
+    // quantities [qlo, qhi) are added up (the others count as 0), sums[slo, shi) are stored
     const int lo = blockIdx.x * per, hi = min(lo + per, nwarps);
     double tot[6] = {0, 0, 0, 0, 0, 0};
     // up to 4 independent rows of loads in flight per thread, accumulated in index order
@@ -715,7 +716,7 @@ k_reduce_props(const double* __restrict__ partials, int nwarps, int per, int nq,
         for (int u = 0; u < 4; u++) {
             const int w = w0 + u * RT;
 #pragma unroll
-            for (int q = 0; q < 6; q++) v[u][q] = (w < hi && q < nq) ? __ldcg(partials + (size_t)q * nwarps + w) : 0.0;
+            for (int q = 0; q < 6; q++) v[u][q] = (w < hi && q >= qlo && q < qhi) ? __ldcg(partials + (size_t)q * nwarps + w) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
@@ -740,7 +741,7 @@ k_reduce_props(const double* __restrict__ partials, int nwarps, int per, int nq,
         for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(block_sums + q * TM_REDUCE_BLOCKS + b);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) sums[q] = t;
+        if (lane == 0 && q >= slo && q < shi) sums[q] = t;
         if (threadIdx.x == 0) *ticket = 0;
     }
 }
@@ -1064,8 +1065,8 @@ __device__ __forceinline__ void penalty_factors(const DevParams& P, const double
 template <int UPD>
 __global__ void __launch_bounds__(TM_GRAD_THREADS, TM_GRAD_MINB)
 k_grad(MeshView mv, DevParams P, const double* __restrict__ sums, const double* __restrict__ force,
-       double* __restrict__ grad, SweepRange R, VVFuse U) {
-    const int t = blockIdx.x * TM_GRAD_THREADS + threadIdx.x;
+       double* __restrict__ grad, SweepRange R, VVFuse U, int blk0) {
+    const int t = (blockIdx.x + blk0) * TM_GRAD_THREADS + threadIdx.x;
     const bool live = t < R.count;
     const int i = R.first + t;
     R8 row;
@@ -1151,8 +1152,26 @@ static int ensure_cellrec(tm_mesh* m, const NlView& nl, cudaStream_t st) {
 int tm_ensure_cellrec(tm_mesh* m, const NlView& nl) { return tm_join_pairs(m) || ensure_cellrec(m, nl, m->stream); }
 
 // pair sweep: energy partials (quantity 5) and/or per-vertex force
-// beside = on the mesh's second stream, concurrently with whatever the caller launches next on the
-// main stream (the ring property sweep); tm_join_pairs before the first consumer
+// beside = on the mesh's side streams, concurrently with whatever the caller launches next on the
+// main stream (the ring property sweep); tm_join_pairs before the first consumer.
+//
+// A sweep beside the main stream over a verlet list is cut into K ranges of tiles, one launch and one side stream
+// each, and adds up its own repulsion sum (own_sum). The ring gradient of a range then follows that range's pair
+// sweep on the range's stream (launch_grad_kernels), so the gradient needs neither the whole pair sweep nor a
+// device-side protocol: the kernel boundary is the fence, and while one range's sweep drains, the blocks of the
+// other streams fill the multiprocessors. Measured at 655,362 vertices (profiles/r02ao): E+G 138.0 -> 122.9 us,
+// a gradient at new positions 127.0 -> 118.1 us with K = 2 (K = 4: 124.3 / 118.7, K = 8: 123.9 / 120.3).
+// TM_PAIR_SPLIT=K overrides (0 or 1: one sweep on one side stream, the reduction waits for it).
+static int pair_split(const tm_mesh* m, const NlView& nl, int nb) {
+    static const int K = [] {
+        const char* e = getenv("TM_PAIR_SPLIT");
+        const int k = e ? atoi(e) : 2;
+        return k < 2 ? 0 : (k > TM_PAIR_STREAMS ? TM_PAIR_STREAMS : k);
+    }();
+    // (small meshes: a kernel of a few microseconds gains nothing from being cut in two)
+    return (nl.kind == TM_NLIST_VERLET && !m->part && nb >= 1024 && PAIR_THREADS == TM_GRAD_THREADS) ? K : 0;
+}
+
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
                         int nwarps, bool beside = false) {
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));
@@ -1162,37 +1181,78 @@ static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p,
     const int nb = (R.count + PAIR_THREADS - 1) / PAIR_THREADS;
     MeshView mv = m->view();
     cudaStream_t st = m->stream;
+    const int K = (beside && !write_vprops) ? pair_split(m, nl, nb) : 0;
     if (beside) {
         if (tm_join_pairs(m)) return 1;
         TM_CUDA(cudaEventRecord(m->ev_fork, m->stream));
-        TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
+        if (K <= 0) TM_CUDA(cudaStreamWaitEvent(m->stream2, m->ev_fork, 0));
         st = m->stream2;
     }
     const size_t qbytes = nl.kind == TM_NLIST_CELL ? sizeof(int) * (PAIR_QCAP + PAIR_XCAP) * PAIR_THREADS : 0;
     if (ensure_cellrec(m, nl, st)) return 1;
-#define TM_PAIRS2(E, F, W, R2, CL) k_pairs<E, F, W, R2, CL><<<nb, PAIR_THREADS, qbytes, st>>>( \
-        mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R)
-#define TM_PAIRS(E, F, W, R2) do { if (nb <= 0) break; if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)
+    int gnb = nb, blk0 = 0;
+#define TM_PAIRS2(E, F, W, R2, CL) k_pairs<E, F, W, R2, CL><<<gnb, PAIR_THREADS, qbytes, st>>>( \
+        mv, nl, p.rep_lc1, p.rep_r, m->frep, m->vprops, m->partials, nwarps, R, blk0)
+#define TM_PAIRS1(E, F, W, R2) do { if (nl.kind == TM_NLIST_CELL) TM_PAIRS2(E, F, W, R2, true); else TM_PAIRS2(E, F, W, R2, false); } while (0)
+#define TM_PAIRS(E, F, W, R2) do { if (nb <= 0) break; if (K <= 0) { TM_PAIRS1(E, F, W, R2); break; } \
+        const int per = (nb + K - 1) / K; \
+        for (int k = 0; k < K; k++) { \
+            blk0 = k * per; gnb = nb - blk0 < per ? nb - blk0 : per; \
+            if (gnb <= 0) break; \
+            st = m->sp_stream[k]; \
+            TM_CUDA(cudaStreamWaitEvent(st, m->ev_fork, 0)); \
+            TM_PAIRS1(E, F, W, R2); \
+            TM_CUDA(cudaEventRecord(m->sp_ev[k], st)); \
+            TM_LAUNCHED(); \
+        } } while (0)
     const bool r2 = p.rep_r == 2;
     if (write_vprops) { if (r2) TM_PAIRS(true, true, true, true); else TM_PAIRS(true, true, true, false); }
     else if (with_e)  { if (r2) TM_PAIRS(true, true, false, true); else TM_PAIRS(true, true, false, false); }
     else              { if (r2) TM_PAIRS(false, true, false, true); else TM_PAIRS(false, true, false, false); }
 #undef TM_PAIRS
+#undef TM_PAIRS1
 #undef TM_PAIRS2
-    TM_LAUNCHED();
+    if (K <= 0) TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     if (beside) {
-        TM_CUDA(cudaEventRecord(m->ev_join, m->stream2));
+        if (K <= 0) TM_CUDA(cudaEventRecord(m->ev_join, m->stream2));
         m->pairs_inflight = true;
+        m->split = K;
     }
     m->frep_epoch = m->pos_epoch; m->frep_lc1 = p.rep_lc1; m->frep_r = p.rep_r;
     m->frep_list = nl.serial;
     return 0;
 }
 
+// fixed-order sum of the warp partials of quantities [qlo, qhi) -> sums[slo, shi) on the main stream
+static int launch_reduce(tm_mesh* m, int ncols, int qlo, int qhi, int slo, int shi) {
+    int rb = (ncols + 4 * RT - 1) / (4 * RT);
+    rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
+    const int per = (ncols + rb - 1) / rb;
+    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, ncols, per, qlo, qhi, slo, shi, m->partials + 6 * (size_t)ncols,
+                                            m->ticket, tm_part_local_sums(m));
+    TM_LAUNCHED();
+    TM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The main stream waits for what the side streams carry. A split pair sweep that evaluated the energy left the
+// repulsion column of the warp partials to be added up: that reduction goes behind the wait (rep_cols > 0).
+static int join_side_streams(tm_mesh* m) {
+    if (m->split > 0) { for (int k = 0; k < m->split; k++) TM_CUDA(cudaStreamWaitEvent(m->stream, m->sp_ev[k], 0)); }
+    else TM_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    if (m->rep_cols > 0) {
+        const int ncols = m->rep_cols;
+        m->rep_cols = 0;
+        if (launch_reduce(m, ncols, 5, 6, 5, 6)) return 1;
+    }
+    return 0;
+}
+
 int tm_join_pairs(tm_mesh* m) {
     if (!m->pairs_inflight) return 0;
-    TM_CUDA(cudaStreamWaitEvent(m->stream, m->ev_join, 0));
+    if (join_side_streams(m)) return 1;
+    m->split = 0;
     m->pairs_inflight = false;
     return 0;
 }
@@ -1221,7 +1281,6 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     const int ngen = m->n_generic, gen_warps = (ngen + 31) / 32;
     const int ncols = nwarps + gen_warps;
     if (tm_props_workspace(m)) return 1;
-    double* block_sums = m->partials + 6 * (size_t)ncols;
     DevParams P = tm_to_dev(p);
     MeshView mv = m->view();
     // the repulsion sum is wanted whenever lc1 > 0, whatever kappa_r is (mesh_properties.cpp:46)
@@ -1237,6 +1296,10 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
         TM_CUDA(cudaMemsetAsync(m->vprops, 0, sizeof(double) * 6 * (size_t)m->V, m->stream));
     }
     if (pairs && launch_pairs(m, nl, p, true, write_vprops, ncols, true)) return 1;
+    // Nothing on the main stream waits for a split pair sweep here: the reduction below leaves its column (the
+    // repulsion sum) out, and the first consumer of sums[5] or of the pair force joins and adds it up (tm_launch_grad,
+    // fetch_sums, the trajectory's statistics). Otherwise the reduction adds the pair sweep's warp partials too.
+    const bool own = pairs && m->split > 0;
     if (pairs_for_grad && launch_pairs(m, nl, p, false, false, 0, true)) return 1;
     if (nb <= 0) {
         // a rank of a tiny partitioned mesh may own nothing: it still takes part in the reduction / exchange
@@ -1264,14 +1327,10 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
             mv, P, m->pos, nullptr, nullptr, 0, 0, G);
         TM_LAUNCHED();
     }
-    if (pairs && tm_join_pairs(m)) return 1;            // the reduction adds the pair sweep's partials
-    int rb = (ncols + 4 * RT - 1) / (4 * RT);
-    rb = rb < 1 ? 1 : (rb > TM_REDUCE_BLOCKS ? TM_REDUCE_BLOCKS : rb);
-    const int per = (ncols + rb - 1) / rb;
-    k_reduce_props<<<rb, RT, 0, m->stream>>>(m->partials, ncols, per, full ? 6 : 4, block_sums, m->ticket,
-                                            tm_part_local_sums(m));
-    TM_LAUNCHED();
-    TM_CUDA(cudaGetLastError());
+    if (pairs && !own && tm_join_pairs(m)) return 1;
+    // own: sums[0..4] now, sums[5] from the pair sweep's column behind the join (join_side_streams)
+    if (launch_reduce(m, ncols, 0, full ? (own ? 5 : 6) : 4, 0, own ? 5 : 6)) return 1;
+    if (own) m->rep_cols = ncols;
     if (tm_part_exchange_sums(m, full ? 6 : 4)) return 1;
     m->geo_epoch = m->pos_epoch;        // sums[0..2], rho and the slot quantities now belong to the current positions
     m->sums_full = full;                // a geometry-only sweep leaves sums[4..5] = 0
@@ -1289,9 +1348,29 @@ static int launch_grad_kernels(tm_mesh* m, const DevParams& P, const double* frc
                                cudaStream_t st) {
     const int nb = (R.count + TM_GRAD_THREADS - 1) / TM_GRAD_THREADS;
     const MeshView mv = m->view();
-    if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
-    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
-    else k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U);
+    if (m->pairs_inflight && m->split > 0 && st == m->stream) {
+        // every range's ring gradient behind that range's pair sweep, on the range's stream
+        const int K = m->split, per = (nb + K - 1) / K;
+        TM_CUDA(cudaEventRecord(m->ev_sums, m->stream));
+        // (the main stream meanwhile waits for the pair sweeps -- the events as recorded so far -- and adds up the
+        // repulsion column: a kernel of a few microseconds beside the ring gradients, which do not wait for it)
+        if (join_side_streams(m)) return 1;
+        for (int k = 0; k < K; k++) {
+            const int blk0 = k * per, gnb = nb - blk0 < per ? nb - blk0 : per;
+            if (gnb <= 0) break;
+            cudaStream_t sk = m->sp_stream[k];
+            TM_CUDA(cudaStreamWaitEvent(sk, m->ev_sums, 0));
+            if (U.mode == 2) k_grad<2><<<gnb, TM_GRAD_THREADS, 0, sk>>>(mv, P, m->sums, frc, m->grad, R, U, blk0);
+            else if (U.mode == 1) k_grad<1><<<gnb, TM_GRAD_THREADS, 0, sk>>>(mv, P, m->sums, frc, m->grad, R, U, blk0);
+            else k_grad<0><<<gnb, TM_GRAD_THREADS, 0, sk>>>(mv, P, m->sums, frc, m->grad, R, U, blk0);
+            TM_CUDA(cudaEventRecord(m->sp_ev[k], sk));
+            if (k > 0) TM_LAUNCHED();
+        }
+        if (tm_join_pairs(m)) return 1;     // what follows on the main stream sees the finished gradient
+    }
+    else if (U.mode == 2) k_grad<2><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U, 0);
+    else if (U.mode == 1) k_grad<1><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U, 0);
+    else k_grad<0><<<nb, TM_GRAD_THREADS, 0, st>>>(mv, P, m->sums, frc, m->grad, R, U, 0);
     TM_LAUNCHED();
     if (m->n_generic > 0) {
         const int gb = (m->n_generic + 127) / 128;
@@ -1307,8 +1386,9 @@ static int launch_grad_kernels(tm_mesh* m, const DevParams& P, const double* frc
 int tm_launch_grad(tm_mesh* m, const NlView& nl, const tm_energy_params& p, const VVFuse* fuse) {
     if (tm_ensure_layout(m) || tm_part_refresh(m, nl)) return 1;
     const bool pairs = nl.kind >= 0 && p.rep_lc1 > 0.0 && p.kappa_r != 0.0;
-    if (pairs && !pair_force_valid(m, nl, p) && launch_pairs(m, nl, p, false, false, 0)) return 1;
-    if (tm_join_pairs(m)) return 1;
+    if (pairs && !pair_force_valid(m, nl, p) && (tm_join_pairs(m) || launch_pairs(m, nl, p, false, false, 0))) return 1;
+    // a split pair sweep still in flight: every range's ring gradient follows on that range's stream, joined behind it
+    if (!(pairs && m->split > 0) && tm_join_pairs(m)) return 1;
     const SweepRange R = tm_owned_range(m);
     VVFuse U;
     memset(&U, 0, sizeof(U));

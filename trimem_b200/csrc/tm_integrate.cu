@@ -156,7 +156,7 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
     const double dt2 = dt * dt;
     if (with_energies) {
         // U(x0): full sweeps; their sums, rho and pair force feed the first gradient
-        if (tm_launch_props(m, nl, p, true, false)) return 1;
+        if (tm_launch_props(m, nl, p, true, false) || tm_join_pairs(m)) return 1;      // (a split pair sweep stores sums[5])
         k_store<<<1, 32, 0, m->stream>>>(m->d_stats, m->sums, 6); TM_LAUNCHED();
         if (kinetic(m, mass, m->d_stats + 12)) return 1;
     }
@@ -204,6 +204,7 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
     TM_CUDA(cudaGetLastError());
     if (with_energies) {
         if (n_steps == 0 && tm_launch_props(m, nl, p, true, false)) return 1;
+        if (tm_join_pairs(m)) return 1;
         k_store<<<1, 32, 0, m->stream>>>(m->d_stats + 6, m->sums, 6); TM_LAUNCHED();
         if (kinetic(m, mass, m->d_stats + 13)) return 1;
         TM_CUDA(cudaGetLastError());
