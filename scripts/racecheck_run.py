@@ -16,3 +16,18 @@ for ns in ("verlet-list", "cell-list"):
     p0 = np.random.default_rng(0).normal(size=x0.shape)
     xn, pn, st = core.vv_integrate(mesh, es, p0, 1.0, 1.0e-6, 3)
     print(ns, "E", e, "|g|", float(np.linalg.norm(g)), "pflip", a, "flip", b, "H", st[0] + st[1], st[2] + st[3])
+if "split" in sys.argv:
+    # the pair sweep cut across the side streams, each range's ring gradient behind it (>= 131,072 vertices)
+    from trimem_b200 import cabi
+    mesh, es, x0 = workload.make_case(core, 7, repulsion="stress", n_search="verlet-list")
+    he = mesh.halfedge_arrays()
+    cm = cabi.Mesh(he[0], he[1], he[2], he[3], xyz=x0)
+    rp = es.eparams.repulse_params
+    nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    p = workload.abi_params(es)
+    cm.energy_async(nl, p); cm.gradient_async(nl, p)
+    e, _ = cm.fetch_energy(p)
+    g = cm.fetch_gradient()
+    p0 = np.random.default_rng(0).normal(size=x0.shape)
+    xn, pn, st = cm.vv_integrate(nl, p, p0, 1.0, 5.0e-8, 3)
+    print("split", "E", e, "|g|", float(np.linalg.norm(g)), "H", st[0] + st[1], st[2] + st[3])

@@ -301,6 +301,7 @@ bool tm_pair_force_valid(const tm_mesh* m, const NlView& nl, const tm_energy_par
 int tm_nlist_measure_displacement(tm_nlist* nl, tm_mesh* m, double* out);   // tm_nlist.cu (asynchronous)
 int tm_ensure_cellrec(tm_mesh* m, const NlView& nl);   // tm_energy.cu: cell_rec of a cell list at the current positions
 int tm_random_momenta(tm_mesh* m, unsigned long long seed, unsigned long long seq, double scale);   // tm_integrate.cu
+bool tm_pair_split_active(const tm_mesh* m, const NlView& nl);   // tm_energy.cu: pair sweeps of this mesh / list are cut across the side streams
 int tm_join_pairs(tm_mesh* m);   // tm_energy.cu: the mesh's stream waits for a pair sweep still running beside it
 int tm_flips_release(tm_mesh* m);                               // tm_flips.cu
 double tm_energy_from_props(const tm_energy_params& p, const double s[6]);    // tm_api.cu (kernel.h:110-122)

@@ -1172,6 +1172,10 @@ static int pair_split(const tm_mesh* m, const NlView& nl, int nb) {
     return (nl.kind == TM_NLIST_VERLET && !m->part && nb >= 1024 && PAIR_THREADS == TM_GRAD_THREADS) ? K : 0;
 }
 
+bool tm_pair_split_active(const tm_mesh* m, const NlView& nl) {
+    return nl.kind >= 0 && pair_split(m, nl, (m->V + PAIR_THREADS - 1) / PAIR_THREADS) > 0;
+}
+
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
                         int nwarps, bool beside = false) {
     if (!m->frep) TM_CUDA(cudaMalloc(&m->frep, sizeof(double) * 3 * (size_t)m->V));

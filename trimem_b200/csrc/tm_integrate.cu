@@ -220,7 +220,8 @@ static int vv_run_direct(tm_mesh* m, const NlView& nl, const tm_energy_params& p
 // parity) the launch sequence is captured into a graph -- including the pair sweep's side stream --
 // and from then on replayed with one cudaGraphLaunch; the host-side bookkeeping the launch functions
 // do (epochs, buffer ping-pong) is replayed beside it. Partitioned meshes launch directly: their
-// exchange kernels carry sequence numbers as arguments. TM_VV_GRAPH=0 disables.
+// exchange kernels carry sequence numbers as arguments, and so do meshes whose pair sweep is cut across the side
+// streams (>= 131,072 vertices with a verlet list: tm_vv_run). TM_VV_GRAPH=0 disables.
 struct VVKey {
     int n_steps, with_e, geo_valid, frep_valid, V;
     double mass, dt;
@@ -256,7 +257,11 @@ void tm_vv_release(tm_mesh* m) {
 int tm_vv_run(tm_mesh* m, const NlView& nl, const tm_energy_params& p, double mass, double dt, int n_steps,
               bool with_energies) {
     static const bool enabled = [] { const char* e = getenv("TM_VV_GRAPH"); return !(e && e[0] == '0'); }();
-    if (!enabled || m->part || n_steps < 1) return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
+    // Large meshes launch directly too: their kernels run for tens of microseconds, so the host stays ahead of the
+    // device anyway, and a replayed graph loses what cutting the pair sweep across prioritised side streams gains
+    // (10 steps at 655,362 vertices: 1.40 ms direct, 1.48 ms replayed; profiles/r02as).
+    if (!enabled || m->part || n_steps < 1 || tm_pair_split_active(m, nl))
+        return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
     if (!m->vvcache) m->vvcache = new tm_vvcache();
     tm_vvcache* C = m->vvcache;
     if (C->disabled) return vv_run_direct(m, nl, p, mass, dt, n_steps, with_energies);
