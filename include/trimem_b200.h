@@ -66,6 +66,11 @@ int tm_mesh_get_rings(tm_mesh* m, int* ring_off, int* ring_v, int* ring_flags);
  * Python mutates behind our back, so every evaluation re-uploads.              */
 int tm_mesh_set_positions(tm_mesh* m, const double* xyz);
 int tm_mesh_get_positions(tm_mesh* m, double* xyz);
+/* Extension (ABI 4): the same upload in pieces, so that a caller who is still filling its (pinned) array can hand
+ * over the rows that are ready: rows [first, first + count) of the (V,3) array `xyz` (the pointer is the array's
+ * base). Pieces in any number, `last` != 0 on the final one -- only then do the new positions count as uploaded;
+ * no compute entry in between. (TriMesh.set_points of the host layer: copy and upload overlapped.)              */
+int tm_mesh_set_positions_rows(tm_mesh* m, const double* xyz, int first, int count, int last);
 /* Extension (no reference counterpart): the device stores vertices sorted by the Morton code
  * of a coarse grid cell so that warps work on compact surface patches; the order is built from
  * the first positions a mesh receives. All ids at this boundary stay in the caller's numbering.

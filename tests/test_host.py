@@ -16,7 +16,7 @@ def test_cabi_library_exports_every_declared_symbol():
     L = ctypes.CDLL(cabi.lib_path())
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert cabi.lib().tm_abi_version() == 3
+    assert cabi.lib().tm_abi_version() == 4
 
 
 def test_cabi_param_struct_layout():

@@ -63,6 +63,7 @@ def lib():
     L.tm_mesh_get_topology.argtypes = [vp, _ip, _ip, _ip, _ip]
     L.tm_mesh_get_rings.argtypes = [vp, _ip, _ip, _ip]
     L.tm_mesh_set_positions.argtypes = [vp, _dp]
+    L.tm_mesh_set_positions_rows.argtypes = [vp, _dp, C.c_int, C.c_int, C.c_int]
     L.tm_mesh_get_positions.argtypes = [vp, _dp]
     L.tm_mesh_reorder.argtypes = [vp]
     L.tm_mesh_get_vertex_order.argtypes = [vp, _ip]

@@ -163,6 +163,7 @@ PYBIND11_MODULE(core, m) {
                  // writable view aliasing the mesh's memory, base = the mesh (src/mesh_py.cpp:96-106)
                  HalfedgeMesh& mesh = self.cast<HalfedgeMesh&>();
                  if (mesh.n_vertices() == 0) throw std::runtime_error("TriMesh has no vertices");
+                 mesh.points_exposed();       // (whoever holds the view may write: the compute entries upload and compare again)
                  std::vector<py::ssize_t> shape = {mesh.n_vertices(), 3};
                  std::vector<py::ssize_t> strides = {3 * (py::ssize_t)sizeof(double), (py::ssize_t)sizeof(double)};
                  return py::array_t<double>(shape, strides, mesh.points(), self);
@@ -179,6 +180,19 @@ PYBIND11_MODULE(core, m) {
         .def("next_halfedge_handle",
              [](HalfedgeMesh& mesh, const HalfedgeHandle& he) { check_he(mesh, he); return HalfedgeHandle{mesh.next(he.idx)}; },
              py::arg("edge"), "Returns handle to the halfedge next to halfedge he.")
+        // ---- extension: positions handed over once (not part of the reference surface) ---------------------
+        .def("set_points",
+             [](HalfedgeMesh& mesh, const darray& x) {
+                 if (x.ndim() != 2 || x.shape(0) != mesh.n_vertices() || x.shape(1) != 3)
+                     throw std::runtime_error("Array 'points' must have shape (n_vertices,3)");
+                 const double* src = x.data();
+                 py::gil_scoped_release nogil;
+                 mesh.update_points(src);
+             },
+             py::arg("points"),
+             "Opt-in replacement of np.copyto(mesh.points(), x): copies x into the mesh memory and uploads it in one call; "
+             "energy()/gradient() then skip their own re-upload until points() hands out a writable view again. Views "
+             "obtained BEFORE this call must not be written to afterwards.")
         // extensions used by the parity tests (not part of the reference surface)
         .def("halfedge_arrays",
              [](HalfedgeMesh& mesh) {

@@ -248,7 +248,9 @@ int flip_parallel_batches(HalfedgeMesh& mesh, EnergyManager& estore, double flip
 void vv_integrate(HalfedgeMesh& mesh, EnergyManager& estore, const double* p0, double mass, double dt,
                   int n_steps, double* x_out, double* p_out, double* stats) {
     tm_energy_params p = estore.abi_params();
-    if (tm_vv_integrate(mesh.device(), estore.nlist_handle(), &p, p0, mass, dt, n_steps, x_out, p_out, stats))
+    tm_mesh* dm = mesh.device();
+    mesh.points_exposed();          // the trajectory moves the device positions away from the mesh's own
+    if (tm_vv_integrate(dm, estore.nlist_handle(), &p, p0, mass, dt, n_steps, x_out, p_out, stats))
         fail();
 }
 
@@ -256,6 +258,7 @@ void vv_integrate_random(HalfedgeMesh& mesh, EnergyManager& estore, unsigned lon
                          double scale, double mass, double dt, int n_steps, double* x_out, double* stats) {
     tm_energy_params p = estore.abi_params();
     tm_mesh* dm = mesh.device();
+    mesh.points_exposed();
     if (tm_mesh_random_momenta(dm, seed, sequence, scale)) fail();
     if (tm_vv_integrate(dm, estore.nlist_handle(), &p, nullptr, mass, dt, n_steps, x_out, nullptr, stats)) fail();
 }

@@ -1,5 +1,15 @@
 #include "halfedge_mesh.h"
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <utility>
@@ -26,6 +36,64 @@ void HalfedgeMesh::set_points(const double* xyz, int n) {
     v_he_.assign(n, -1);
     he_to_.clear(); he_next_.clear(); he_prev_.clear(); he_face_.clear(); f_he_.clear();
     ++topo_version_;
+    resident_ = false;
+}
+
+void HalfedgeMesh::update_points(const double* xyz) {
+    if (nv_ <= 0) throw std::runtime_error("TriMesh is empty");
+    tm_mesh* dm = device(false);
+    if (tm_sync(dm)) throw std::runtime_error(tm_last_error());      // (an upload from xyz_ may still be in flight)
+    // A 16 MB copy takes one core ~1 ms, more than the upload and the sweeps behind it together: up to four threads,
+    // and streaming stores -- lines left dirty in several cores' caches make the upload's DMA three times slower
+    // (0.45 -> 1.03 ms for the energy() behind a plain four-thread memcpy, scripts/set_points_timing.py).
+    int cores = 4;
+#if defined(__linux__)
+    { cpu_set_t set; if (sched_getaffinity(0, sizeof(set), &set) == 0) cores = CPU_COUNT(&set); }
+#endif
+    static const int nt_env = [] { const char* e = getenv("TM_SET_POINTS_THREADS"); return e ? atoi(e) : 0; }();
+    int nt = nt_env > 0 ? nt_env : (cores >= 6 ? 4 : (cores >= 3 ? 2 : 1));
+    if (nt > 16) nt = 16;
+    // pieces of whole rows, a multiple of 8 rows each (streaming stores want 16-byte aligned destinations); piece p is
+    // copied by thread p % nt, and uploaded by this thread as soon as it is in place: the upload runs beside the copy
+    const int rows_per = std::max(8, ((nv_ + 4 * nt - 1) / (4 * nt) + 7) & ~7);
+    const int pieces = nv_ < (1 << 15) ? 1 : (nv_ + rows_per - 1) / rows_per;
+    auto copy = [this, xyz](size_t a, size_t b) {           // doubles [a, b), a even (xyz_ is page-aligned)
+        double* d = xyz_;
+        size_t k = a;
+#if defined(__SSE2__)
+        for (; k + 2 <= b; k += 2) _mm_stream_pd(d + k, _mm_loadu_pd(xyz + k));
+        _mm_sfence();
+#endif
+        for (; k < b; k++) d[k] = xyz[k];
+    };
+    if (pieces <= 1) {
+        copy(0, 3 * (size_t)nv_);
+        if (tm_mesh_set_positions(dm, xyz_)) throw std::runtime_error(tm_last_error());
+    } else {
+        std::vector<std::atomic<int>> done(pieces);
+        for (auto& f : done) f.store(0, std::memory_order_relaxed);
+        auto rows = [&](int p, int& first, int& count) { first = p * rows_per; count = std::min(rows_per, nv_ - first); };
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                for (int p = t; p < pieces; p += nt) {
+                    int first, count;
+                    rows(p, first, count);
+                    copy(3 * (size_t)first, 3 * (size_t)(first + count));
+                    done[p].store(1, std::memory_order_release);
+                }
+            });
+        int rc = 0;
+        for (int p = 0; p < pieces; p++) {
+            while (!done[p].load(std::memory_order_acquire)) std::this_thread::yield();
+            int first, count;
+            rows(p, first, count);
+            if (!rc) rc = tm_mesh_set_positions_rows(dm, xyz_, first, count, p == pieces - 1);
+        }
+        for (auto& t : th) t.join();
+        if (rc) throw std::runtime_error(tm_last_error());
+    }
+    resident_ = true;
 }
 
 int HalfedgeMesh::find_halfedge(int a, int b) const {
@@ -187,7 +255,7 @@ tm_mesh* HalfedgeMesh::device(bool upload_positions) {
             throw std::runtime_error(tm_last_error());
         dev_topo_version_ = topo_version_;
     }
-    if (upload_positions && tm_mesh_set_positions(dev_, xyz_))
+    if (upload_positions && !resident_ && tm_mesh_set_positions(dev_, xyz_))
         throw std::runtime_error(tm_last_error());
     return dev_;
 }

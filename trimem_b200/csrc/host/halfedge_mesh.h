@@ -43,7 +43,7 @@ public:
     int n_edges() const { return (int)he_to_.size() / 2; }
     int n_faces() const { return (int)f_he_.size(); }
 
-    double* points() { return xyz_; }
+    double* points() { resident_ = false; return xyz_; }      // (writable: the compute entries upload and compare again)
     const double* points() const { return xyz_; }
 
     // connectivity queries
@@ -73,6 +73,12 @@ public:
     // device mirror: created lazily, connectivity re-uploaded when it changed on the host,
     // positions re-uploaded on every call (Python writes through points() behind our back).
     tm_mesh* device(bool upload_positions = true);
+    // Opt-in extension (TriMesh.set_points): copy `xyz` (n_vertices x 3) into the mesh's memory AND upload it, once.
+    // From then on the compute entries skip their own re-upload -- until a writable view is handed out again
+    // (the non-const points()) or the device positions move on their own (a trajectory: points_exposed()).
+    void update_points(const double* xyz);
+    void points_exposed() { resident_ = false; }
+    bool points_resident() const { return resident_; }
     uint64_t topology_version() const { return topo_version_; }
     // the device connectivity was mutated by a flip sweep and the host replayed the same
     // flips: mark both sides as in sync without a re-upload
@@ -89,6 +95,7 @@ private:
     uint64_t topo_version_ = 1;
     tm_mesh* dev_ = nullptr;
     uint64_t dev_topo_version_ = 0;
+    bool resident_ = false;       // the device holds exactly xyz_ and nobody can have written to xyz_ since
 };
 
 // OpenMesh::IO::read_mesh for the formats trimem's drivers use (STL, OFF, OBJ); mesh_io.cpp

@@ -129,7 +129,7 @@ int fetch_sums(tm_mesh* m, double out[6]) {
 extern "C" {
 
 const char* tm_last_error(void) { return g_err; }
-int tm_abi_version(void) { return 3; }
+int tm_abi_version(void) { return 4; }
 
 int tm_device_count(void) {
     int n = 0;
@@ -324,6 +324,27 @@ int tm_mesh_set_positions(tm_mesh* m, const double* xyz) {
     m->stage_pending = true;
     m->have_positions = true;
     tm_part_positions_uploaded(m);
+    return 0;
+}
+
+int tm_mesh_set_positions_rows(tm_mesh* m, const double* xyz, int first, int count, int last) {
+    if (first == 0) {
+        if (check_mesh(m, false)) return 1;
+        TM_CUDA(cudaEventRecord(m->ev_pre_upload, m->stream));
+    } else {
+        TM_CHECK(m != nullptr && m->V > 0, "null mesh handle");
+        TM_CUDA(cudaSetDevice(m->device));
+    }
+    TM_CHECK(xyz != nullptr, "null positions");
+    TM_CHECK(first >= 0 && count >= 0 && first + count <= m->V, "rows [%d, %d) outside the mesh's %d vertices", first, first + count, m->V);
+    if (count > 0)
+        TM_CUDA(cudaMemcpyAsync(m->xio3 + 3 * (size_t)first, xyz + 3 * (size_t)first, sizeof(double) * 3 * (size_t)count,
+                                cudaMemcpyHostToDevice, m->stream));
+    if (last) {
+        m->stage_pending = true;
+        m->have_positions = true;
+        tm_part_positions_uploaded(m);
+    }
     return 0;
 }
 
