@@ -236,19 +236,25 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
         [t.join() for t in th]
     all_chains(10, 0)                   # warm-up: trajectory graphs captured, one flip sweep, list pools filled
     n_moves = 20
-    launches0 = core.launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    all_chains(n_moves, 10)
-    wall = time.perf_counter() - t0
-    launches = core.launch_count() - launches0
-    stats_timed = list(stats)
+    # Host wall clock of R Python threads sharing one interpreter and one GPU: single runs of 20 moves spread from 0.15
+    # to 2 s on the same box (scripts/chains_timing.py, profiles/r02be_chains_spread.txt: the build before and after this
+    # round's stream changes alike, whatever the interpreter's switch interval), so every figure of this section is the
+    # shortest of three runs, like timeit.
+    REPS = 3
+    wall = float("inf")
+    for rep in range(REPS):
+        launches0 = core.launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        all_chains(n_moves, 10 + 1000 * rep)
+        w = time.perf_counter() - t0
+        if w < wall:
+            wall, launches, stats_timed = w, core.launch_count() - launches0, list(stats)
     # the same chains with the list rebuilt only when the device-side trigger fires
     for c in chains:
         c[1].update_repulsion(c[0]); c[2].displacement = 0.0
-    # (host wall clock of eight Python threads: the shorter of two runs of n_moves, like timeit)
     wall_lazy = float("inf")
-    for rep in range(2):
+    for rep in range(REPS):
         barrier()
         t0 = time.perf_counter()
         all_chains(n_moves, 40 + 100 * rep, lazy=True)
@@ -258,10 +264,12 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
     for c in chains:
         c[2].device_momenta = 5000 + c[3]
     all_chains(5, 60, lazy=True)
-    barrier()
-    t0 = time.perf_counter()
-    all_chains(n_moves, 65, lazy=True)
-    wall_dev = time.perf_counter() - t0
+    wall_dev = float("inf")
+    for rep in range(REPS):
+        barrier()
+        t0 = time.perf_counter()
+        all_chains(n_moves, 70 + 100 * rep, lazy=True)
+        wall_dev = min(wall_dev, time.perf_counter() - t0)
     for c in chains:
         c[2].device_momenta = None
     stats[:] = stats_timed
@@ -297,6 +305,15 @@ def hmc_step_run(args, core, workload, rank):
         chain.step()
     out["hmc_move_ms"] = 1e3 * (time.perf_counter() - t0) / n
     out["hmc_acceptance"] = chain.acc / max(chain.i, 1)
+    # the same move with the momenta drawn on the device (opt-in; the host draw of 3 V normal variates is most of a move)
+    chain.device_momenta = 4242
+    for _ in range(3):
+        chain.step()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        chain.step()
+    out["hmc_move_ms_device_momenta"] = 1e3 * (time.perf_counter() - t0) / n
+    chain.device_momenta = None
     estore.update_repulsion(mesh)
     t0 = time.perf_counter()
     for _ in range(5):
@@ -668,18 +685,6 @@ def main():
     for k in range(6):
         np.copyto(mesh.points(), xs[k % 2])
     host_copy_gbs = 6 * V3 / (time.perf_counter() - t0) / 1e9
-    hp = torch.empty(x0.size, dtype=torch.float64).pin_memory()
-    dp = torch.zeros(x0.size, dtype=torch.float64, device="cuda")
-    pcie = {}
-    # (download first: the DMA leaves no dirty lines of the pinned buffer in the CPU caches, which would slow the upload)
-    for name, src, dst in (("d2h", dp, hp), ("h2d", hp, dp)):
-        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(6):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
-        pcie[name] = 6 * V3 / (time.perf_counter() - t0) / 1e9
-    del hp, dp
 
     # ---- device-resident velocity-Verlet trajectory (tm_vv_integrate_async; hmc.py:14-26): L steps per
     # timed trajectory = L+1 gradient evaluations + L fused update kernels, state never leaves HBM
@@ -734,6 +739,21 @@ def main():
     part = None
     if not args.no_partition:
         part = partitioned_run(args, core, cabi, workload, rank, world, local, barrier, dist if world > 1 else None, torch)
+
+    # PCIe rates of this box (torch copies of a pinned buffer of the positions' size); measured here, after the
+    # host-thread-heavy sections
+    hp = torch.empty(x0.size, dtype=torch.float64).pin_memory()
+    dp = torch.zeros(x0.size, dtype=torch.float64, device="cuda")
+    pcie = {}
+    # (download first: the DMA leaves no dirty lines of the pinned buffer in the CPU caches, which would slow the upload)
+    for name, src, dst in (("d2h", dp, hp), ("h2d", hp, dp)):
+        dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(6):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        pcie[name] = 6 * V3 / (time.perf_counter() - t0) / 1e9
+    del hp, dp
 
     # parity spot check of the timed configuration against itself through both boundaries
     e_dev, _ = cm.energy(nl, p)
@@ -821,7 +841,7 @@ def main():
                 "what": f"{repl['R']} independent HMC + flip chains per GPU (BASELINE config 5: {repl['V']}-vertex membranes of the kappa_b x "
                         f"volume_frac sweep, physical repulsion, verlet-list) through trimem_b200.hmc.MeshHMC / core.pflip / "
                         f"update_repulsion, one host thread per chain; per move {repl['L']} leapfrog steps, every 10th move a "
-                        "pflip(0.1); host wall clock, max over ranks",
+                        "pflip(0.1); host wall clock of the shortest of three runs of 20 moves per chain (single runs spread widely: profiles/r02be_chains_spread.txt), max over ranks",
                 "chains_total": world * repl["R"], "moves_per_chain": repl["moves"],
                 "moves_per_s": world * repl["R"] * repl["moves"] / repl_s,
                 "mvertex_steps_per_s": world * repl["R"] * repl["moves"] * repl["L"] / repl_s * repl["V"] / 1e6,

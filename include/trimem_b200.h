@@ -33,7 +33,8 @@ typedef struct tm_nlist tm_nlist;  /* device neighbour list (cell / verlet)     
 const char* tm_last_error(void);
 /* 1: energy / gradient / neighbour lists / flips; 2: + trajectories (tm_vv_*), partitioned meshes
  * (tm_part_*), tm_nlist_displacement; 3: + tm_vv_displacement (rebuild trigger measured behind the
- * trajectory), tm_mesh_random_momenta, tm_time_kernel composites 4/5. Additions only: a caller of version 1 keeps working.   */
+ * trajectory), tm_mesh_random_momenta, tm_time_kernel composites 4/5; 4: + tm_mesh_set_positions_rows (upload in
+ * pieces). Additions only: a caller of version 1 keeps working.                                                    */
 int  tm_abi_version(void);
 /* number of visible CUDA devices (0 when there is no driver / device)         */
 int  tm_device_count(void);

@@ -109,3 +109,35 @@ def test_split_and_joined_builds_of_a_trajectory_agree(gpu_core, tmp_path):
             assert np.array_equal(a["arr_%d" % j], b["arr_%d" % j]), (other, j)
         for j in (2, 5, 8, 9, 10):             # energies and sums: the repulsion sum is added in another fixed order
             assert np.allclose(a["arr_%d" % j], b["arr_%d" % j], rtol=1e-14, atol=0.0), (other, j)
+
+
+def test_split_path_with_generic_vertices(gpu_core):
+    """After flip sweeps the mesh has vertices of valence > 8 (no fixed-width ring row: k_props_generic / k_grad_generic,
+    launched on the main stream behind the join): asynchronous evaluations still equal the synchronous ones."""
+    mesh, estore, x0 = workload.make_case(gpu_core, SUBDIV, repulsion="physical", n_search="verlet-list",
+                                          kappa=(1.0, 1.0, 1.0, 1.0, 1.0, 1.0), fracs=(1.0, 1.0, 1.0))
+    for k in range(4):
+        gpu_core.pflip(mesh, estore, 0.3, seed=20 + k)
+        estore.update_repulsion(mesh)
+    he = mesh.halfedge_arrays()
+    valence = np.bincount(he[0], minlength=mesh.n_vertices())
+    assert valence.max() > 8, "the sweeps were meant to produce generic vertices"
+    cm = cabi.Mesh(he[0], he[1], he[2], he[3], xyz=x0)
+    rp = estore.eparams.repulse_params
+    nl = cabi.NList(cm, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    p = workload.abi_params(estore)
+    rng = np.random.default_rng(11)
+    amp = 1e-3 * np.linalg.norm(x0[0] - x0[1])
+    for it in range(3):
+        cm.set_positions(x0 + amp * rng.standard_normal(x0.shape))
+        cm.energy_async(nl, p)
+        cm.gradient_async(nl, p)
+        e1, props1 = cm.fetch_energy(p)
+        g1 = cm.fetch_gradient()
+        g2 = cm.gradient(nl, p)
+        e2, props2 = cm.energy(nl, p)
+        assert np.array_equal(g1, g2) and e1 == e2 and np.array_equal(props1, props2), it
+    # and against the pybind path (synchronous calls on its own mesh object)
+    np.copyto(mesh.points(), cm.positions())
+    assert estore.energy(mesh) == e2
+    assert np.array_equal(estore.gradient(mesh), g2)

@@ -178,6 +178,7 @@ int tm_mesh_create(int device, tm_mesh** out) {
         // streams the pair sweep and what follows it, which have slack: blocks of the chain are placed first
         int lo = 0, hi = 0;
         TM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        { const char* e = getenv("TM_STREAM_PRIO"); if (e && e[0] == '0') hi = lo; }
         TM_CUDA(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, hi));
         TM_CUDA(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, lo));
         for (int k = 0; k < TM_PAIR_STREAMS; k++) {
