@@ -236,10 +236,10 @@ def replica_run(args, core, cabi, workload, rank, world, local, barrier):
         [t.join() for t in th]
     all_chains(10, 0)                   # warm-up: trajectory graphs captured, one flip sweep, list pools filled
     n_moves = 20
-    # Host wall clock of R Python threads sharing one interpreter and one GPU: single runs of 20 moves spread from 0.15
-    # to 2 s on the same box (scripts/chains_timing.py, profiles/r02be_chains_spread.txt: the build before and after this
-    # round's stream changes alike, whatever the interpreter's switch interval), so every figure of this section is the
-    # shortest of three runs, like timeit.
+    # Host wall clock of R Python threads sharing one interpreter and one GPU; every figure of this section is the
+    # shortest of three runs, like timeit. (Until the pinned result blocks of the bindings were kept up to a byte budget
+    # instead of four per size, single runs spread from 0.15 to 2 s: eight chains' arrays of one size overflowed the
+    # pool, and every cudaFreeHost / cudaHostAlloc stalled all of them; profiles/r02be_chains_spread.txt.)
     REPS = 3
     wall = float("inf")
     for rep in range(REPS):
@@ -841,7 +841,7 @@ def main():
                 "what": f"{repl['R']} independent HMC + flip chains per GPU (BASELINE config 5: {repl['V']}-vertex membranes of the kappa_b x "
                         f"volume_frac sweep, physical repulsion, verlet-list) through trimem_b200.hmc.MeshHMC / core.pflip / "
                         f"update_repulsion, one host thread per chain; per move {repl['L']} leapfrog steps, every 10th move a "
-                        "pflip(0.1); host wall clock of the shortest of three runs of 20 moves per chain (single runs spread widely: profiles/r02be_chains_spread.txt), max over ranks",
+                        "pflip(0.1); host wall clock of the shortest of three runs of 20 moves per chain, max over ranks",
                 "chains_total": world * repl["R"], "moves_per_chain": repl["moves"],
                 "moves_per_s": world * repl["R"] * repl["moves"] / repl_s,
                 "mvertex_steps_per_s": world * repl["R"] * repl["moves"] * repl["L"] / repl_s * repl["V"] / 1e6,

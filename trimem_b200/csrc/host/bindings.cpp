@@ -75,36 +75,43 @@ class PinnedPool {
 public:
     static PinnedPool& get() { static PinnedPool p; return p; }
     void* take(size_t bytes) {
+        bool first = false;
         {
             std::lock_guard<std::mutex> lk(mu_);
             auto it = free_.find(bytes);
             if (it != free_.end() && !it->second.empty()) {
                 void* p = it->second.back();
                 it->second.pop_back();
+                cached_ -= bytes;
                 return p;
             }
+            first = seen_.insert(bytes).second;
         }
         // first block of this size: the usual caller keeps the previous result alive while it asks
         // for the next one (g = estore.gradient(mesh) in a loop), so two blocks circulate; pinning a
         // 16 MB block costs ~15 ms, which belongs here and not into the caller's second step
-        if (!seen_.count(bytes)) {
-            seen_.insert(bytes);
+        if (first) {
             if (void* spare = tm_host_alloc(bytes)) {
                 std::lock_guard<std::mutex> lk(mu_);
                 free_[bytes].push_back(spare);
+                cached_ += bytes;
             }
         }
         return tm_host_alloc(bytes);
     }
+    // Blocks are kept up to a byte budget, not a count: several chains on host threads of one process (bench.py:
+    // replica_run) circulate two or three result arrays of ONE size each, and every block that is unpinned and pinned
+    // again instead (cudaFreeHost / cudaHostAlloc synchronise the device and serialise in the driver) stalls all of them.
     void give(void* p, size_t bytes) {
         {
             std::lock_guard<std::mutex> lk(mu_);
-            auto& v = free_[bytes];
-            if (v.size() < 4) { v.push_back(p); return; }
+            if (cached_ + bytes <= kBudget) { free_[bytes].push_back(p); cached_ += bytes; return; }
         }
         tm_host_free(p);
     }
 private:
+    static constexpr size_t kBudget = (size_t)1 << 30;
+    size_t cached_ = 0;
     std::mutex mu_;
     std::map<size_t, std::vector<void*>> free_;
     std::set<size_t> seen_;
