@@ -32,7 +32,14 @@ constexpr size_t POOL_MAX_CACHED = (size_t)8 << 30;
 
 void* tm_pool_alloc(int device, size_t bytes) {
     if (bytes == 0) bytes = 16;
-    bytes = (bytes + 255) & ~(size_t)255;
+    // size classes of 1/8 octave (at most 12.5 % over): the cell arrays of a neighbour list change their size a little
+    // from rebuild to rebuild with the membrane's bounding box, and an exact-size cache would miss -- a cudaMalloc per
+    // rebuild and chain, and a cache that only grows
+    {
+        size_t step = 256;
+        while (step * 16 <= bytes) step <<= 1;
+        bytes = (bytes + step - 1) / step * step;
+    }
     const int d = device & 15;
     {
         std::lock_guard<std::mutex> lk(g_pool.mu);
