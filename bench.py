@@ -732,6 +732,14 @@ def main():
         chain.step()
     barrier()
     hmc_api_ms = 1e3 * (time.perf_counter() - t0) / n_moves_api
+    # ... and with the momenta drawn on the device (opt-in): the host's draw of 3 V normal variates is most of the move above
+    chain.device_momenta = 99 + rank
+    chain.step(); chain.step()
+    t0 = time.perf_counter()
+    for _ in range(n_moves_api):
+        chain.step()
+    hmc_api_dev_ms = 1e3 * (time.perf_counter() - t0) / n_moves_api
+    chain.device_momenta = None
     np.copyto(mesh.points(), x0)
 
     repl = replica_run(args, core, cabi, workload, rank, world, local, barrier) if args.replicas > 0 else None
@@ -830,7 +838,7 @@ def main():
                     "host": {"copy_into_pinned_GBps_one_core": host_copy_gbs, "h2d_GBps": pcie["h2d"], "d2h_GBps": pcie["d2h"]},
                     "hmc_move": {"what": f"MeshHMC.step() through trimem_b200.core / trimem_b200.hmc: {L} leapfrog steps on the device, "
                                          "both Hamiltonian evaluations, Metropolis; momenta and positions in, end point and momenta out",
-                                 "ms_per_move": hmc_api_ms, "h2d_bytes_per_move": 2 * V * 24, "d2h_bytes_per_move": 2 * V * 24 + 32,
+                                 "ms_per_move": hmc_api_ms, "ms_per_move_device_momenta_this_rank": hmc_api_dev_ms, "h2d_bytes_per_move": 2 * V * 24, "d2h_bytes_per_move": 2 * V * 24 + 32,
                                  "mvertex_steps_per_s": world * L * V / (hmc_api_ms * 1e-3) / 1e6}},
             "leapfrog": {"what": f"device-resident velocity-Verlet trajectory of {L} steps (tm_vv_integrate_async): "
                                  f"{L + 1} gradient evaluations + {L} fused update kernels, L2 flushed before each trajectory",

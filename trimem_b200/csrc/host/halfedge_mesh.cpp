@@ -56,7 +56,7 @@ void HalfedgeMesh::update_points(const double* xyz) {
     // pieces of whole rows, a multiple of 8 rows each (streaming stores want 16-byte aligned destinations); piece p is
     // copied by thread p % nt, and uploaded by this thread as soon as it is in place: the upload runs beside the copy
     const int rows_per = std::max(8, ((nv_ + 4 * nt - 1) / (4 * nt) + 7) & ~7);
-    const int pieces = nv_ < (1 << 15) ? 1 : (nv_ + rows_per - 1) / rows_per;
+    const int pieces = nv_ < (1 << 18) ? 1 : (nv_ + rows_per - 1) / rows_per;     // (below ~6 MB the threads cost more than they copy)
     auto copy = [this, xyz](size_t a, size_t b) {           // doubles [a, b), a even (xyz_ is page-aligned)
         double* d = xyz_;
         size_t k = a;

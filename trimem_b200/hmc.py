@@ -95,7 +95,8 @@ class MeshHMC:
         self.n_draws = 0
 
     def _set_mesh(self, x):
-        np.copyto(self.trimesh.points(), x)
+        # (np.copyto(self.trimesh.points(), x) in the reference, mesh.py:39-42; set_points copies AND uploads once)
+        self.trimesh.set_points(x)
 
     def _step(self):
         """Metropolis step (hmc.py:133-155)."""
