@@ -1,0 +1,16 @@
+#!/bin/bash
+# round 2, GPU session BK (2 GPUs): split pair sweep on partitioned meshes: partition tests, bench line at 2 ranks
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_partition.py -m gpu -q -x 2>&1 | tail -4
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 --replicas 0 --no-hmc-step > gpurun_out/r02bk_bench_n2.json 2> gpurun_out/r02bk_bench_n2.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+line = [l for l in open('gpurun_out/r02bk_bench_n2.json') if l.startswith('{')][-1]
+d = json.loads(line)
+print({k: d[k] for k in ('value', 'ms_per_step', 'n_gpus')}, d['e2e']['value'])
+p = d['partitioned']; print({k: p.get(k) for k in ('ranks', 'ms_per_eg', 'leapfrog_ms_per_step', 'verlet_rebuild_ms', 'energy_rel_diff_vs_whole_mesh_on_one_device', 'reference_golden')})
+PY
+tail -3 gpurun_out/r02bk_bench_n2.err
+timeout 900 python bench.py --steps 10 --replicas 0 --no-hmc-step --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); p=d['partitioned']; print('1 rank:', {k: p.get(k) for k in ('ranks','ms_per_eg','leapfrog_ms_per_step','reference_golden')})"

@@ -120,6 +120,31 @@ def test_trajectory_partitioned(gpu_core, name, nranks):
     assert abs(st[0, 2] - want[2]) <= 10 * TOL * abs(want[2]) and abs(k1 - want[3]) <= 10 * TOL * abs(want[3])
 
 
+def test_trajectory_partitioned_with_split_pair_sweep(gpu_core):
+    """655,362 vertices on 2 ranks: every rank's pair sweep is cut across its side streams, its ring gradient follows range
+    by range, and the repulsion sum is reduced and exchanged in a second step (tm_energy.cu: join_side_streams). Against
+    the same trajectory of the whole mesh on one handle: the ranks add their sums in rank order, so equal to rounding."""
+    case = "ico8_stress_verlet2"
+    R = Ranks(gpu_core, case, 2)
+    p0 = np.random.default_rng(4).standard_normal(R.v.shape)
+    mass, dt, n = 1.0, 2.0e-8, 3
+    R.each(lambda m, nl: m.set_momenta(p0))
+    R.each(lambda m, nl: m.vv_integrate_async(nl, R.par, mass, dt, n, with_energies=True))
+    stats = np.array(R.each(lambda m, nl: m.vv_stats(R.par)[0]))
+    ps = np.sum(R.each(lambda m, nl: m.momenta()), axis=0)
+    xs = R.each(lambda m, nl: m.positions())
+    assert np.array_equal(xs[0], xs[1])
+    arrs = R.mesh.halfedge_arrays()[:4]
+    rp = R.es.eparams.repulse_params
+    whole = cabi.Mesh(*arrs, xyz=R.v)
+    nl = cabi.NList(whole, cabi.NLIST_VERLET, rp.rlist, rp.exclusion_level)
+    x1, p1, st1 = whole.vv_integrate(nl, R.par, p0, mass, dt, n)
+    assert nrm(xs[0] - R.v, x1 - R.v) < 1e-11 and nrm(ps, p1) < 1e-11
+    assert np.all(stats[:, 0] == stats[0, 0]) and np.all(stats[:, 2] == stats[0, 2])      # identical bits on every rank
+    assert abs(stats[0, 0] - st1[0]) <= 1e-13 * abs(st1[0]) and abs(stats[0, 2] - st1[2]) <= 1e-13 * abs(st1[2])
+    assert abs(stats[:, 1].sum() - st1[1]) <= 1e-12 * abs(st1[1]) and abs(stats[:, 3].sum() - st1[3]) <= 1e-12 * abs(st1[3])
+
+
 def test_rebuild_after_trajectory_and_allsum(gpu_core):
     """A neighbour list rebuilt after a partitioned trajectory sees every rank's current positions
     (tm_nlist_create pulls the far field first), and equals the list a single device builds."""

@@ -316,7 +316,8 @@ SweepRange tm_owned_range(const tm_mesh* m);
 // of the locally reduced sums; no-ops returning 0 on an unpartitioned mesh                tm_part.cu
 SweepRange tm_ghost_range(const tm_mesh* m);
 double* tm_part_local_sums(tm_mesh* m);          // where k_reduce_props writes (m->sums if unpartitioned)
-int tm_part_exchange_sums(tm_mesh* m, int nq);   // publish local sums, add all ranks' in rank order -> m->sums
+int tm_part_exchange_sums(tm_mesh* m, int qlo, int qhi);   // publish local sums, add all ranks' sums [qlo, qhi) in rank order -> m->sums
+int tm_part_nranks(const tm_mesh* m);            // 1 if unpartitioned
 int tm_part_positions_updated(tm_mesh* m);       // after a device-side update of the owned positions: halo pull
 int tm_part_before_update(tm_mesh* m);           // peers must have pulled the previous positions
 int tm_part_release(tm_mesh* m);

@@ -1168,12 +1168,15 @@ static int pair_split(const tm_mesh* m, const NlView& nl, int nb) {
         const int k = e ? atoi(e) : 2;
         return k < 2 ? 0 : (k > TM_PAIR_STREAMS ? TM_PAIR_STREAMS : k);
     }();
-    // (small meshes: a kernel of a few microseconds gains nothing from being cut in two)
-    return (nl.kind == TM_NLIST_VERLET && !m->part && nb >= 1024 && PAIR_THREADS == TM_GRAD_THREADS) ? K : 0;
+    // (small meshes: a kernel of a few microseconds gains nothing from being cut in two.) The ranks of a partitioned
+    // mesh must decide alike -- a split sweep exchanges its sums in two steps -- so they go by the mesh, not by what
+    // each of them owns.
+    const long long tiles = m->part ? (long long)((m->V + PAIR_THREADS - 1) / PAIR_THREADS) / tm_part_nranks(m) : nb;
+    return (nl.kind == TM_NLIST_VERLET && tiles >= 1024 && PAIR_THREADS == TM_GRAD_THREADS) ? K : 0;
 }
 
 bool tm_pair_split_active(const tm_mesh* m, const NlView& nl) {
-    return nl.kind >= 0 && pair_split(m, nl, (m->V + PAIR_THREADS - 1) / PAIR_THREADS) > 0;
+    return nl.kind >= 0 && pair_split(m, nl, (tm_owned_range(m).count + PAIR_THREADS - 1) / PAIR_THREADS) > 0;
 }
 
 static int launch_pairs(tm_mesh* m, const NlView& nl, const tm_energy_params& p, bool with_e, bool write_vprops,
@@ -1248,7 +1251,7 @@ static int join_side_streams(tm_mesh* m) {
     if (m->rep_cols > 0) {
         const int ncols = m->rep_cols;
         m->rep_cols = 0;
-        if (launch_reduce(m, ncols, 5, 6, 5, 6)) return 1;
+        if (launch_reduce(m, ncols, 5, 6, 5, 6) || tm_part_exchange_sums(m, 5, 6)) return 1;
     }
     return 0;
 }
@@ -1335,7 +1338,7 @@ int tm_launch_props(tm_mesh* m, const NlView& nl, const tm_energy_params& p, boo
     // own: sums[0..4] now, sums[5] from the pair sweep's column behind the join (join_side_streams)
     if (launch_reduce(m, ncols, 0, full ? (own ? 5 : 6) : 4, 0, own ? 5 : 6)) return 1;
     if (own) m->rep_cols = ncols;
-    if (tm_part_exchange_sums(m, full ? 6 : 4)) return 1;
+    if (tm_part_exchange_sums(m, 0, full ? (own ? 5 : 6) : 4)) return 1;
     m->geo_epoch = m->pos_epoch;        // sums[0..2], rho and the slot quantities now belong to the current positions
     m->sums_full = full;                // a geometry-only sweep leaves sums[4..5] = 0
     return 0;

@@ -139,7 +139,7 @@ k_pull(PeerTable T, const int* __restrict__ list, int n, P4* pos) {
 }
 
 // publish the local sums of sweep `seq`, wait for every peer's, add in rank order
-__global__ void k_exchange_sums(PeerTable T, PartComm* own, unsigned long long seq, int nq, double* __restrict__ out,
+__global__ void k_exchange_sums(PeerTable T, PartComm* own, unsigned long long seq, int qlo, int qhi, double* __restrict__ out,
                                 unsigned long long timeout_ns) {
     if (threadIdx.x == 0) {
         __threadfence_system();
@@ -151,7 +151,7 @@ __global__ void k_exchange_sums(PeerTable T, PartComm* own, unsigned long long s
     __syncwarp();
     __threadfence_system();
     const int q = threadIdx.x;
-    if (q < nq) {
+    if (q >= qlo && q < qhi) {
         double s = 0.0;
         for (int k = 0; k < T.nranks; k++) s += __ldcv(&T.comm[k]->sums[seq & 1][q]);
         out[q] = s;
@@ -245,12 +245,14 @@ double* tm_part_local_sums(tm_mesh* m) {
     return m->part->comm->sums[(m->part->sums_seq + 1) & 1];
 }
 
-int tm_part_exchange_sums(tm_mesh* m, int nq) {
+int tm_part_nranks(const tm_mesh* m) { return m->part ? m->part->nranks : 1; }
+
+int tm_part_exchange_sums(tm_mesh* m, int qlo, int qhi) {
     tm_part* P = m->part;
     if (!P) return 0;
     TM_CHECK(all_attached(P), "partitioned mesh: not every peer is attached (tm_part_attach_*)");
     P->sums_seq++;
-    k_exchange_sums<<<1, 32, 0, m->stream>>>(P->peers, P->comm, P->sums_seq, nq, m->sums, P->timeout_ns); TM_LAUNCHED();
+    k_exchange_sums<<<1, 32, 0, m->stream>>>(P->peers, P->comm, P->sums_seq, qlo, qhi, m->sums, P->timeout_ns); TM_LAUNCHED();
     TM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -487,7 +489,7 @@ int tm_part_allsum6(tm_mesh* m, const double in[6], double out[6]) {
     Six v;
     for (int q = 0; q < 6; q++) v.v[q] = in[q];
     k_store6<<<1, 32, 0, m->stream>>>(tm_part_local_sums(m), v); TM_LAUNCHED();   // by value: no copy-engine traffic
-    if (tm_part_exchange_sums(m, 6)) return 1;
+    if (tm_part_exchange_sums(m, 0, 6)) return 1;
     m->geo_epoch = 0;                 // m->sums no longer holds property sums
     if (check_error(m)) return 1;     // waits for the exchange
     TM_CUDA(cudaMemcpy(out, m->sums, 6 * sizeof(double), cudaMemcpyDeviceToHost));
